@@ -1,0 +1,229 @@
+/*
+ * abk.h -- C ABI of libabk.so: the B200 (sm_100a) implementation of the abacusutils
+ * density-field power-spectrum hot path.
+ *
+ * The reference (abacusorg/abacusutils) has no FFI on this path: its boundary is the Python
+ * module API of abacusnbody.analysis.tsc / abacusnbody.analysis.power_spectrum, whose hot loops
+ * are Numba @njit kernels.  Each entry point below replaces one of those kernels; the comment
+ * above it cites the reference function it stands in for (paths relative to
+ * /root/reference/abacusnbody/analysis/).  The Python shims in abacusutils_b200/analysis/ keep the
+ * reference signatures and call these through ctypes (see INTEGRATION.md for the binding a
+ * maintainer would add to the reference itself).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - plain pointers and sizes only, no framework types;
+ *   - every function returns 0 (ABK_OK) or a negative error code; abk_last_error() returns the
+ *     message of the last failure on the calling thread;
+ *   - work is enqueued on the context's stream (abk_ctx_set_stream) and is asynchronous unless
+ *     stated otherwise; the library never allocates large device buffers behind the caller's
+ *     back: scratch is sized by the *_scratch_bytes queries and passed in;
+ *   - grids are C-ordered (x slowest, z contiguous) float32 with a z row length of `ldz` floats
+ *     (ldz == nz for a plain grid, ldz == 2*(nz/2+1) for the in-place R2C layout).
+ */
+#ifndef ABK_H
+#define ABK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABK_VERSION 100
+
+#define ABK_OK 0
+#define ABK_ERR_INVALID (-1) /* bad argument */
+#define ABK_ERR_CUDA (-2)    /* CUDA runtime failure */
+#define ABK_ERR_CUFFT (-3)   /* cuFFT failure */
+#define ABK_ERR_SCRATCH (-4) /* scratch buffer too small */
+
+#define ABK_MAX_SEGMENTS 16
+#define ABK_MAX_POLES 16
+#define ABK_POLE_NCOEF 11 /* polynomial in mu = sqrt(mu2) up to degree 10 (ell <= 10) */
+
+typedef struct abk_ctx abk_ctx;
+typedef struct abk_fft_plan abk_fft_plan;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int abk_version(void);
+const char *abk_last_error(void);
+int abk_ctx_create(int device, abk_ctx **ctx);
+int abk_ctx_destroy(abk_ctx *ctx);
+/* `stream` is a cudaStream_t (NULL = legacy default stream). */
+int abk_ctx_set_stream(abk_ctx *ctx, void *stream);
+int abk_ctx_sync(abk_ctx *ctx);
+/* number of kernels this library has launched on this context (bench.py "gpu_launches") */
+int64_t abk_ctx_launch_count(abk_ctx *ctx);
+/* tuning knobs (0 = library default): tile-kernel particle capacity per pass */
+int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity);
+
+/* ---- TSC deposit --------------------------------------------------------------------------- */
+
+/* tsc.py:219-226 `_wrap_inplace`: one-shot periodic wrap of pos[N][3] into [0, box], in place.
+ * *n_changed_dev (device int64, may be NULL) is incremented by the number of coordinates that
+ * were modified, so a host caller can skip the write-back when nothing changed. */
+int abk_wrap_inplace(abk_ctx *ctx, float *pos, int64_t N, double box, int64_t *n_changed_dev);
+
+/* tsc.py:259-384 `partition_parallel`: counting sort of particles into `npart` stripes along
+ * `coord`; key = min(int32(pos[coord] * f32(npart/box)), npart-1).  out_starts is int64[npart+1].
+ * The order of particles inside a stripe is unspecified (atomic scatter), which the reference's
+ * own test allows (tests/test_tsc.py:194-208).  scratch: abk_partition_scratch_bytes(). */
+int abk_partition_scratch_bytes(int64_t N, int npart, size_t *bytes);
+int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int npart, double box,
+                  int coord, float *out_pos, float *out_w, int64_t *out_starts, void *scratch,
+                  size_t scratch_bytes);
+
+/* Particle bucketing for the deposit (replaces the x-stripe partition of tsc.py:178-188 and the
+ * two-colour stripe schedule of tsc.py:229-256 `_tsc_parallel`): particles are binned by the
+ * (TX x TY x TZ)-cell tile that contains the centre cell of their cloud,
+ *     cell = rint((pos + offset) * f32(n/box)) mod n          (tsc.py:424-433, 387-391)
+ * One call buckets one SEGMENT of up to 2^30 particles; several segments (e.g. host->device
+ * chunks that arrive one after another) can be bucketed independently and deposited together.
+ *   records  : out, float4[N]   (x, y, z, w) in bucket order (w = 1 when `w` is NULL)
+ *   tile_ends: out, uint32[ntiles] inclusive scan: tile t owns records [tile_ends[t-1], tile_ends[t])
+ * If `wrap` is non-zero the one-shot periodic wrap (tsc.py:219-226) is applied on the fly to the
+ * values that are bucketed (the input array is not modified). */
+int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles);
+int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);
+int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
+                   double box, double offset, int wrap, void *records, uint32_t *tile_ends,
+                   void *scratch, size_t scratch_bytes);
+
+/* tsc.py:394-507 `_tsc_scatter` (+ :229-256): 27-point TSC deposit of bucketed particles.
+ * One CTA per tile builds per-cell particle lists in shared memory, accumulates each cell's
+ * clouds in registers, combines neighbouring cells conflict-free in a shared-memory tile, and
+ * flushes the tile (+1-cell halo) to the grid with float reductions.  The grid is accumulated
+ * into, never zeroed (tsc.py:45-50).
+ *   nseg segments: records_seg[s] / tile_ends_seg[s] as produced by abk_tsc_bucket with the SAME
+ *   grid shape, box and offset.
+ *   x_lo / nx_local: multi-GPU slab mode.  The grid pointer holds planes x_lo-1 .. x_lo+nx_local
+ *   (nx_local+2 planes, the first and last being ghost planes of the neighbouring slabs) when
+ *   nx_local < nx; single GPU: x_lo = 0, nx_local = nx and the grid holds exactly nx planes. */
+int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
+                          const uint32_t *const *tile_ends_seg_h, float *grid, int nx, int ny, int nz,
+                          int64_t ldz, double box, double offset, int x_lo, int nx_local);
+
+/* Convenience: bucket one segment and deposit it (what tsc_parallel does for device inputs).
+ * scratch must hold abk_tsc_deposit_scratch_bytes(). */
+int abk_tsc_deposit_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);
+int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx,
+                    int ny, int nz, int64_t ldz, double box, double offset, int wrap, void *scratch,
+                    size_t scratch_bytes);
+
+/* Reference-order fallback used for validation only: one thread per particle, 27 global float
+ * reductions (no bucketing).  Same arithmetic as abk_tsc_deposit. */
+int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid,
+                          int nx, int ny, int nz, int64_t ldz, double box, double offset, int wrap);
+
+/* ---- real-space field ---------------------------------------------------------------------- */
+
+/* power_spectrum.py:860-901 `normalize_field` (in place): field <- field * f32(size/tot_weight) - 1
+ * over the nx*ny*nz valid cells of a (possibly padded) grid; size = size_total (the GLOBAL cell
+ * count, so a slab of a sharded grid is normalised with the global constant). */
+int abk_normalize_field(abk_ctx *ctx, float *grid, int64_t nx, int64_t ny, int64_t nz, int64_t ldz,
+                        double size_total, double tot_weight);
+
+/* ---- FFT ----------------------------------------------------------------------------------- */
+
+/* power_spectrum.py:980,986,1059 `scipy.fft.rfftn`: unnormalised forward R2C transform of an
+ * (nx,ny,nz) float32 grid stored in place with ldz = 2*(nz/2+1); output complex64
+ * (nx,ny,nz/2+1) in the same buffer.  cuFFT plan with a caller-provided work area. */
+int abk_rfft3_plan_create(abk_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, abk_fft_plan **plan,
+                          size_t *work_bytes);
+int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid_inplace, void *work, size_t work_bytes);
+/* inverse (C2R, unnormalised) of the same layout: power_spectrum.py:645 `irfftn` (xi(r) path) */
+int abk_irfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid_inplace, void *work, size_t work_bytes);
+int abk_fft_plan_destroy(abk_fft_plan *plan);
+
+/* Slab-decomposed pieces for a mesh sharded over GPUs by x-planes:
+ *   2-D R2C over (y,z) on `nplanes` local planes (in place, ldz = 2*(nz/2+1)), and
+ *   1-D C2C along x for `nrows` rows of `nzc` complex values (layout [x][row][nzc], in place). */
+int abk_fft_yz_plan_create(abk_ctx *ctx, int64_t nplanes, int64_t ny, int64_t nz, abk_fft_plan **plan,
+                           size_t *work_bytes);
+int abk_fft_x_plan_create(abk_ctx *ctx, int64_t nx, int64_t nrows, int64_t nzc, abk_fft_plan **plan,
+                          size_t *work_bytes);
+int abk_fft_exec_generic(abk_ctx *ctx, abk_fft_plan *plan, void *data_inplace, void *work,
+                         size_t work_bytes);
+
+/* ---- k-space ------------------------------------------------------------------------------- */
+
+/* Description of one complex (or real) k-space mesh and the part of it this GPU holds.
+ * Element (i,j,k) of the global (n,n,nzc) mesh lives at base[(i-i0)*stride_i + (j-j0)*stride_j + k]
+ * for i0 <= i < i1, j0 <= j < j1, 0 <= k < nzc.  Single GPU: i0=j0=0, i1=j1=n,
+ * stride_j=row length, stride_i=n*stride_j. */
+typedef struct abk_kmesh {
+    int32_t n;        /* global mesh size per dimension */
+    int32_t nzc;      /* number of k_z values visited: n/2+1 */
+    int32_t i0, i1;   /* local x-range */
+    int32_t j0, j1;   /* local y-range */
+    int64_t stride_i; /* in elements */
+    int64_t stride_j; /* in elements */
+} abk_kmesh;
+
+/* power_spectrum.py:904-948 `shift_field_fft`, :1073-1078 `_normalize`, :1062-1070 window
+ * compensation -- fused, in place on f:
+ *     f <- (f + fs * exp(i*pi*(i'+j'+k)/n)) * scale      (fs != NULL; scale = 0.5/n^3)
+ *     f <-  f * scale                                     (fs == NULL; scale = 1/n^3)
+ *     f <-  f / ((W[i]*W[j])*W[k])                        (W != NULL; float32 table of length n)
+ * i' = i (i < n/2) else i-n, likewise j'. */
+int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
+                         float scale);
+
+/* Binning request: power_spectrum.py:150-300 `bin_kmu` fused with :707-727 `get_raw_power` and,
+ * optionally, with the finishing step above (so calc_power never materialises delta(k) or P(k)).
+ *
+ *   value per mode:  real_in != NULL : real_in[(i,j,k)]                       (project_3d_to_poles)
+ *                    f2 == NULL      : |v1|^2                                 (auto power)
+ *                    else            : Re(conj(v1) * v2)                      (cross power)
+ *   with v = finish(f, fs, W, scale) when `finish` is non-zero, else v = f.
+ *
+ *   kmag2 = f32(i'^2+j'^2+k^2); mu2 = f32(k^2)/kmag2 (0 at DC); a mode is used iff
+ *   kedges2[0] <= kmag2 < kedges2[Nk]; bk = #{b in 1..Nk : kedges2[b] < kmag2},
+ *   bmu = min(#{b in 1..Nmu : muedges2[b] < mu2}, Nmu-1); multiplicity 1 for k==0, else 2.
+ *
+ * Outputs are RAW sums, ACCUMULATED into (the caller zeroes them; several GPUs add theirs with an
+ * all-reduce): counts u64[Nk*Nmu], sum_p f64[Nk*Nmu] (sum of mult*value), sum_k f64[Nk*Nmu]
+ * (sum of mult*sqrt(kmag2); multiply by dk on the host), sum_poles f64[Np*Nk]
+ * (sum of mult*value*(2l+1)P_l(mu)); the l=0 row is left untouched (the host sets it from sum_p,
+ * power_spectrum.py:282-284).
+ * pole_coef: float32[Np][ABK_POLE_NCOEF], (2l+1)P_l as a polynomial in mu=sqrt(mu2) (host-built
+ * from power_spectrum.py:121-147); pole_ell int32[Np]. */
+typedef struct abk_bin_request {
+    abk_kmesh mesh;
+    const void *f1, *f1s, *f2, *f2s; /* complex64 meshes (fs: half-cell-shifted grids) */
+    const float *real_in;            /* float32 mesh instead of f1 */
+    const float *W;                  /* float32[n] or NULL */
+    float scale;
+    int32_t finish;
+    const float *kedges2; /* float32[Nk+1], device */
+    const float *muedges2; /* float32[Nmu+1], device */
+    int32_t Nk, Nmu, Np;
+    const float *pole_coef; /* device */
+    const int32_t *pole_ell; /* device */
+    unsigned long long *counts;
+    double *sum_p, *sum_k, *sum_poles;
+} abk_bin_request;
+
+int abk_power_bin(abk_ctx *ctx, const abk_bin_request *req_h);
+
+/* ---- multi-GPU helpers (x-slab sharded mesh) ------------------------------------------------ */
+
+/* dst[i] += src[i] over an (nplanes, ny, nz) region of padded grids (ghost-plane accumulation) */
+int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_t nplanes, int64_t ny, int64_t nz,
+                   int64_t ldz);
+/* Slab->pencil transpose, pack side: from the local slab [nxl][ny][nzc] (complex64) gather, for
+ * every destination rank r, the block [nxl][j in rank r's y-range][nzc] contiguously into
+ * sendbuf at offset send_off_h[r] (elements).  y-ranges are given by jsplit_h[nranks+1]. */
+int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf, int64_t nxl, int64_t ny, int64_t nzc,
+                       int nranks, const int64_t *jsplit_h);
+/* unpack side: recvbuf holds, for every source rank r, [nxl_r][nyl][nzc]; scatter into the local
+ * pencil layout [nx][nyl][nzc] at x offset isplit_h[r]. */
+int abk_transpose_unpack(abk_ctx *ctx, const void *recvbuf, void *pencil, int64_t nx, int64_t nyl,
+                         int64_t nzc, int nranks, const int64_t *isplit_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABK_H */

@@ -1,0 +1,138 @@
+"""
+Seeded input definitions shared by make_golden.py (which stores the reference's OUTPUTS) and the
+parity tests (which re-create the same inputs and compare the oracle / the CUDA path with them).
+"""
+
+import numpy as np
+
+# planes of the 256^3 reference golden grid kept (sparsely) in ref_tsc_ngrid256.npz
+REF_TSC_256_PLANES = np.r_[0:12, 122:134, 250:256]
+
+PN_X = np.linspace(0.0, 1.0, 33, dtype=np.float32)
+
+
+def ref_tsc_inputs(dtype='f4'):
+    """Inputs of the reference's test_multi (tests/test_tsc.py:101-109)."""
+    rng = np.random.default_rng(234)
+    N, box = 10000, 123.0
+    pos = rng.random((N, 3), dtype='f4').astype(dtype) * box
+    weights = rng.random((N,), dtype='f4').astype(dtype)
+    return pos, weights, box
+
+
+# ---------------------------------------------------------------- TSC
+TSC_CASES = {
+    'cube24_w': dict(seed=11, N=5000, box=100.0, shape=(24, 24, 24), weighted=True, offset=0.0),
+    'cube24_w_off': dict(seed=11, N=5000, box=100.0, shape=(24, 24, 24), weighted=True, offset=0.5 * 100.0 / 24),
+    'cube40_now': dict(seed=12, N=20000, box=250.0, shape=(40, 40, 40), weighted=False, offset=0.0),
+    'aniso': dict(seed=13, N=4000, box=77.0, shape=(12, 18, 30), weighted=True, offset=0.0),
+    'unwrapped': dict(seed=14, N=3000, box=50.0, shape=(20, 20, 20), weighted=True, offset=0.0, spill=True),
+    'tiny10': dict(seed=15, N=500, box=123.0, shape=(10, 10, 10), weighted=False, offset=0.0, nthread=1),
+}
+
+PARTITION_CASES = {
+    'p16': dict(seed=21, N=10000, box=123.0, weighted=True, npartition=16),
+    'p1000': dict(seed=22, N=10000, box=123.0, weighted=True, npartition=1000),
+}
+
+
+def tsc_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    pos = rng.random((c['N'], 3), dtype='f4') * np.float32(c['box'])
+    if c.get('spill'):
+        # positions in [-box/2, 3box/2): exercises the one-shot periodic wrap
+        pos = pos * np.float32(2.0) - np.float32(0.5 * c['box'])
+    w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
+    return pos, w
+
+
+# ---------------------------------------------------------------- mode counts
+COUNT_CASES = {
+    'n16_k8': dict(n=16, L=100.0, Nk=8, Nmu=1, logk=False, poles=[0, 2, 4]),
+    'n32_k16_mu4': dict(n=32, L=500.0, Nk=16, Nmu=4, logk=False, poles=[0, 2, 4]),
+    'n48_k12_mu3_log': dict(n=48, L=750.0, Nk=12, Nmu=3, logk=True, poles=[0, 2]),
+    'n64_default': dict(n=64, L=1000.0, Nk=64, Nmu=1, logk=False, poles=[]),
+    'n72_testpower': dict(n=72, L=1000.0, Nk=36, Nmu=4, logk=False, poles=[0, 2, 4],
+                          k_max=np.pi * 72 / 1000.0 + 1e-6, k_lo=1e-6),
+    'n128_k100_mu10': dict(n=128, L=1000.0, Nk=100, Nmu=10, logk=False, poles=[0, 2, 4]),
+    'n90_k45_mu5': dict(n=90, L=333.0, Nk=45, Nmu=5, logk=False, poles=[2]),
+    'n50_halfk': dict(n=50, L=200.0, Nk=20, Nmu=2, logk=False, poles=[0, 4], k_max=0.5 * np.pi * 50 / 200.0),
+    'n40_log_mu7': dict(n=40, L=1234.5, Nk=25, Nmu=7, logk=True, poles=[0, 1, 2, 3]),
+}
+
+
+def count_edges(c):
+    n, L = c['n'], c['L']
+    k_max = c.get('k_max', np.pi * n / L)
+    if c['logk']:
+        k_min = (1.0 - 1.0e-4) * 2.0 * np.pi / L
+        kedges = np.geomspace(k_min, k_max, c['Nk'] + 1)
+    else:
+        kedges = np.linspace(c.get('k_lo', 0.0), k_max, c['Nk'] + 1)
+    muedges = np.linspace(0.0, 1.0, c['Nmu'] + 1)
+    return kedges, muedges
+
+
+# ---------------------------------------------------------------- calc_power / get_field_fft
+def _pc(seed, N, L, nmesh, kbins, mubins, poles, compensated, interlaced, weighted=True, cross=False,
+        logk=False, **kw):
+    return dict(seed=seed, N=N, L=L, nmesh=nmesh, kbins=kbins, mubins=mubins, poles=poles,
+                compensated=compensated, interlaced=interlaced, weighted=weighted, cross=cross, logk=logk, **kw)
+
+
+POWER_CASES = {
+    'n32_ci': _pc(31, 20000, 500.0, 32, 16, 4, [0, 2, 4], True, True),
+    'n32_c': _pc(31, 20000, 500.0, 32, 16, 4, [0, 2, 4], True, False),
+    'n32_i': _pc(31, 20000, 500.0, 32, 16, 4, [0, 2, 4], False, True),
+    'n32_raw': _pc(31, 20000, 500.0, 32, 16, 4, [0, 2, 4], False, False),
+    'n32_cross_ci': _pc(32, 15000, 500.0, 32, 16, 4, [0, 2, 4], True, True, cross=True),
+    'n32_cross_c': _pc(32, 15000, 500.0, 32, 16, 4, [0, 2, 4], True, False, cross=True),
+    'n48_log': _pc(33, 30000, 750.0, 48, 12, 3, [0, 2], True, True, logk=True),
+    'n40_defaults': _pc(34, 25000, 1000.0, 40, None, None, None, True, True, weighted=False),
+    'n36_nopoles_mu': _pc(35, 10000, 300.0, 36, 18, 5, None, True, False, weighted=False),
+    # BASELINE config 1 scaled down 8x in particle count (same L/nmesh/options)
+    'cfg1_small': _pc(12345, 125000, 1000.0, 128, None, None, [0, 2, 4], True, False, weighted=False),
+}
+
+FIELD_CASES = {
+    'f24_ci': _pc(41, 3000, 100.0, 24, 0, 0, None, True, True),
+    'f24_c': _pc(41, 3000, 100.0, 24, 0, 0, None, True, False),
+    'f24_i': _pc(41, 3000, 100.0, 24, 0, 0, None, False, True, weighted=False),
+    'f24_raw': _pc(41, 3000, 100.0, 24, 0, 0, None, False, False, weighted=False),
+}
+
+
+def power_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    L = np.float32(c['L'])
+    pos = rng.random((c['N'], 3), dtype='f4') * L
+    w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
+    pos2 = w2 = None
+    if c['cross']:
+        N2 = c['N'] // 2 + 17
+        pos2 = rng.random((N2, 3), dtype='f4') * L
+        # correlate the second catalogue with the first so the cross-spectrum is not pure noise
+        pos2[: N2 // 2] = np.mod(pos[: N2 // 2] + rng.normal(0, 0.01 * c['L'], (N2 // 2, 3)).astype('f4'), L)
+        pos2 = np.ascontiguousarray(pos2, dtype=np.float32)
+        pos2[pos2 >= L] = 0.0
+        w2 = rng.random(N2, dtype='f4') if c['weighted'] else None
+    return pos, w, pos2, w2
+
+
+# ---------------------------------------------------------------- binning of supplied arrays
+DELTAK_CASES = {
+    'd32': dict(seed=51, n=32, L=400.0, Nk=14, Nmu=4, logk=False, poles=[0, 2, 4]),
+    'd30_allpoles': dict(seed=52, n=30, L=90.0, Nk=10, Nmu=3, logk=False, poles=[0, 1, 2, 3, 4, 6, 8, 10]),
+    'd20_log': dict(seed=53, n=20, L=50.0, Nk=9, Nmu=1, logk=True, poles=[0, 2]),
+}
+
+
+def deltak_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    n = c['n']
+    shp = (n, n, n // 2 + 1)
+    f1 = (rng.standard_normal(shp, dtype='f4') + 1j * rng.standard_normal(shp, dtype='f4')).astype(np.complex64)
+    f2 = (0.5 * f1 + rng.standard_normal(shp, dtype='f4') + 1j * rng.standard_normal(shp, dtype='f4')).astype(
+        np.complex64)
+    raw = (rng.random(shp, dtype='f4') * 10).astype(np.float32)
+    return f1, f2, raw

@@ -1,0 +1,139 @@
+"""
+Generate the committed golden fixtures under tests/golden/ (run in the BUILD CONTAINER only).
+
+Two sources, both the reference's own:
+  1. the checked-in golden grids of the reference test-suite, tests/ref_tsc/*.asdf
+     (/root/reference/tests/test_tsc.py:128-159), decoded with asdf_blsc.py;
+  2. outputs of the UNMODIFIED reference modules imported from /root/reference via oracle/ref_shim.py
+     on seeded inputs (the inputs are re-generated from the seeds by tests/golden/cases.py, only
+     outputs are stored).
+
+Usage:  NUMBA_NUM_THREADS=2 python tests/golden/make_golden.py
+(2 threads keeps every reference run on the race-free stripe branch for nmesh >= 12)
+"""
+
+import os
+import sys
+from pathlib import Path
+
+os.environ.setdefault('NUMBA_NUM_THREADS', '2')
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(HERE))
+
+import numpy as np  # noqa: E402
+
+import cases  # noqa: E402
+from asdf_blsc import read_single_array  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+REF_TESTS = Path(ref_shim.REF_ROOT) / 'tests'
+
+
+def sparse_planes(a, planes):
+    sub = a[planes]
+    idx = np.flatnonzero(sub)
+    return idx.astype(np.int32), sub.reshape(-1)[idx]
+
+
+def golden_ref_tsc():
+    for n in (10, 256):
+        own = read_single_array(REF_TESTS / 'ref_tsc' / f'tsc_ngrid{n}.asdf', np.float32, (n, n, n))
+        nbk = read_single_array(REF_TESTS / 'ref_tsc' / f'nbodykit_tsc_ngrid{n}.asdf', np.float32, (n, n, n))
+        if n == 10:
+            np.savez_compressed(HERE / 'ref_tsc_ngrid10.npz', pydens=own, nbodykit=nbk)
+        else:
+            planes = cases.REF_TSC_256_PLANES
+            oi, ov = sparse_planes(own, planes)
+            ni, nv = sparse_planes(nbk, planes)
+            np.savez_compressed(
+                HERE / 'ref_tsc_ngrid256.npz', planes=planes, own_idx=oi, own_val=ov, nbk_idx=ni, nbk_val=nv,
+                own_sum=own.sum(dtype='f8'), own_sumsq=(own.astype('f8') ** 2).sum(), own_nnz=(own != 0).sum(),
+                nbk_sum=nbk.sum(dtype='f8'), nbk_sumsq=(nbk.astype('f8') ** 2).sum(),
+                own_xsum=own.sum(axis=(1, 2), dtype='f8'), own_zsum=own.sum(axis=(0, 1), dtype='f8'))
+        print('ref_tsc', n, own.sum(dtype='f8'))
+
+
+def golden_reference_runs():
+    tsc, ps = ref_shim.load(num_threads=2)
+    out = {}
+
+    # A. tsc_parallel on small grids (full grids stored)
+    for name, c in cases.TSC_CASES.items():
+        pos, w = cases.tsc_inputs(c)
+        dens = np.zeros(c['shape'], dtype=np.float32)
+        tsc.tsc_parallel(pos, dens, c['box'], weights=w, nthread=c.get('nthread', 2), offset=c['offset'],
+                         wrap=c.get('wrap', True))
+        out[f'tsc/{name}'] = dens
+        print('tsc', name, dens.sum(dtype='f8'))
+
+    # partition_parallel
+    for name, c in cases.PARTITION_CASES.items():
+        pos, w = cases.tsc_inputs(c)
+        ppart, starts, wpart = tsc.partition_parallel(pos, c['npartition'], c['box'], weights=w, nthread=2)
+        out[f'partition/{name}/starts'] = starts
+        out[f'partition/{name}/ppart'] = ppart
+        out[f'partition/{name}/wpart'] = wpart
+
+    # B. bin_kmu on an all-ones mesh: data-independent mode counts
+    for name, c in cases.COUNT_CASES.items():
+        n, L = c['n'], c['L']
+        kedges, muedges = cases.count_edges(c)
+        ones = np.ones((n, n, n // 2 + 1), dtype=np.float32)
+        poles = np.asarray(c['poles'], dtype=np.int64)
+        wc, cnt, wcp, cntp, wk = ps.bin_kmu(n, L, kedges, muedges, ones, poles=poles, nthread=2)
+        out[f'counts/{name}/N_mode'] = cnt
+        out[f'counts/{name}/N_mode_poles'] = cntp
+        out[f'counts/{name}/k_avg'] = wk
+        out[f'counts/{name}/power'] = wc
+        out[f'counts/{name}/poles'] = wcp
+        print('counts', name, cnt.sum())
+
+    # C. calc_power end to end
+    for name, c in cases.POWER_CASES.items():
+        pos, w, pos2, w2 = cases.power_inputs(c)
+        t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'),
+                          logk=c['logk'], paste='TSC', nmesh=c['nmesh'], compensated=c['compensated'],
+                          interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2, poles=c['poles'], nthread=2)
+        for key in t:
+            out[f'power/{name}/{key}'] = np.asarray(t[key])
+        print('power', name, np.asarray(t['power']).ravel()[:3])
+
+    # D. get_field_fft (materialised delta(k))
+    for name, c in cases.FIELD_CASES.items():
+        pos, w, _, _ = cases.power_inputs(c)
+        W = ps.get_W_compensated(c['L'], c['nmesh'], 'TSC', c['interlaced']) if c['compensated'] else None
+        f = ps.get_field_fft(pos, c['L'], c['nmesh'], 'TSC', w, W, c['compensated'], c['interlaced'], nthread=2)
+        out[f'field/{name}'] = f
+        if W is not None:
+            out[f'field/{name}/W'] = W
+
+    # E/F. binning of supplied arrays
+    for name, c in cases.DELTAK_CASES.items():
+        f1, f2, raw = cases.deltak_inputs(c)
+        kedges, muedges = cases.count_edges(c)
+        poles = np.asarray(c['poles'], dtype=np.int64)
+        P = ps.calc_pk_from_deltak(f1, c['L'], kedges, muedges, field2_fft=f2, poles=poles, nthread=2)
+        for key, v in P.items():
+            out[f'deltak/{name}/{key}'] = np.asarray(v)
+        bp, Np_ = ps.project_3d_to_poles(kedges, raw, c['L'], poles)
+        out[f'deltak/{name}/proj_poles'] = bp
+        out[f'deltak/{name}/proj_N'] = Np_
+
+    # window tables and edges (host formulas)
+    for n, L, inter in [(8, 100.0, True), (8, 100.0, False), (72, 1000.0, True), (128, 1000.0, False),
+                        (250, 2000.0, True)]:
+        out[f'W/{n}_{int(inter)}'] = ps.get_W_compensated(L, n, 'TSC', inter)
+        out[f'Wcic/{n}_{int(inter)}'] = ps.get_W_compensated(L, n, 'CIC', inter)
+    for ell in range(0, 11):
+        xs = cases.PN_X
+        out[f'P_n/{ell}'] = np.array([ps.P_n(np.float32(x), ell) for x in xs], dtype=np.float32)
+
+    np.savez_compressed(HERE / 'reference_runs.npz', **out)
+    print('wrote', HERE / 'reference_runs.npz', len(out), 'arrays')
+
+
+if __name__ == '__main__':
+    golden_ref_tsc()
+    golden_reference_runs()
