@@ -1,0 +1,598 @@
+r"""
+Density-field power spectra on B200 -- drop-in for ``abacusnbody.analysis.power_spectrum``.
+
+Same public names, argument order, defaults and return types as the reference
+(/root/reference/abacusnbody/analysis/power_spectrum.py); the heavy lifting (TSC painting, FFT,
+interlacing, window compensation, (k,mu) binning, Legendre multipoles) runs in libabk.so
+(abacusutils_b200/csrc) through ctypes.  Host-side pieces that are O(nmesh) or O(Nk) -- bin edges,
+the 1-D window table, the final divisions and the result table -- stay in NumPy, written so the
+float32/float64 tables are identical to the reference's.
+
+``calc_power`` never materialises delta(k) or P(k): the two painted grids are transformed in place
+and a single fused kernel applies 1/n^3, the interlacing phase and the window, forms |delta|^2 (or
+the cross spectrum) and bins it.  ``get_field_fft`` / ``calc_pk_from_deltak`` expose the same stages
+separately for callers that want delta(k) (the ZCV modules of the reference).
+
+Inputs may be NumPy arrays, torch CPU tensors (pinned memory is copied asynchronously) or torch CUDA
+tensors; array-valued results follow the kind of the input (NumPy in -> NumPy out).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+
+import numpy as np
+
+from .._lib import (ABK_MAX_POLES, ABK_MAX_SEGMENTS, ABK_POLE_NCOEF, SEGMENT_MAX, AbkError, BinRequest, Engine, KMesh,
+                    check, is_torch_tensor, ptr)
+from .tsc import padded_ldz, tsc_parallel
+
+__all__ = ['calc_power', 'calc_pk_from_deltak', 'pk_to_xi', 'project_3d_to_poles', 'get_k_mu_edges']
+
+MAX_THREADS = 1  # the reference's thread knob (numba.config.NUMBA_NUM_THREADS); ignored on the GPU
+
+try:  # the reference returns an astropy Table (power_spectrum.py:1318); use it when available
+    from astropy.table import Table as _AstropyTable
+except Exception:  # pragma: no cover - astropy is not installed in the build image
+    _AstropyTable = None
+
+
+class Table(dict):
+    """Fallback result container with the part of astropy.table.Table the callers use
+    (column access by name, ``.meta``, ``.colnames``)."""
+
+    def __init__(self, d, meta=None):
+        super().__init__(d)
+        self.meta = meta or {}
+
+    @property
+    def colnames(self):
+        return list(self.keys())
+
+
+def _make_table(res, meta):
+    if _AstropyTable is not None:
+        return _AstropyTable(res, meta=meta)
+    return Table(res, meta=meta)
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side O(n) pieces
+def get_k_mu_edges(Lbox, k_max, kbins, mubins, logk):
+    r"""Bin edges of k and mu (reference: power_spectrum.py:663-704).
+
+    ``kbins`` / ``mubins`` may be ints (number of bins) or arrays (returned unchanged).  Linear k bins
+    run from 0 to ``k_max``; logarithmic ones from :math:`(1-10^{-4})\,2\pi/L` to ``k_max``.
+    """
+    if isinstance(kbins, (int, np.integer)):
+        if logk:
+            k_min = (1.0 - 1.0e-4) * 2.0 * np.pi / Lbox
+            kbins = np.geomspace(k_min, k_max, kbins + 1)
+        else:
+            kbins = np.linspace(0.0, k_max, kbins + 1)
+    if isinstance(mubins, (int, np.integer)):
+        mubins = np.linspace(0.0, 1.0, mubins + 1)
+    return kbins, mubins
+
+
+def get_W_compensated(Lbox, nmesh, paste, interlaced):
+    """1-D mass-assignment window over ``fftfreq`` order (reference: power_spectrum.py:1081-1128).
+
+    Interlaced: ``sinc(k/2kN)**p`` with p=3 (TSC) / 2 (CIC); otherwise the first-order aliasing
+    correction ``sqrt(1 - s + 2/15 s^2)`` (TSC) / ``sqrt(1 - 2/3 s)`` (CIC), ``s = sin^2(pi k / 2 kN)``.
+    The wavenumbers are cast to float32 first, as in the reference.
+    """
+    d = Lbox / nmesh
+    kN = np.pi / d
+    k = (np.fft.fftfreq(nmesh, d=d) * 2.0 * np.pi).astype(np.float32)
+    paste = paste.upper()
+    if paste not in ('TSC', 'CIC'):
+        raise ValueError(f'Unknown pasting method {paste}')
+    if interlaced:
+        p = 3.0 if paste == 'TSC' else 2.0
+        W = np.sinc(0.5 * k / kN) ** p
+    else:
+        s = np.sin(0.5 * np.pi * k / kN) ** 2
+        W = (1 - s + 2.0 / 15 * s**2) ** 0.5 if paste == 'TSC' else (1 - 2.0 / 3 * s) ** 0.5
+    return W
+
+
+def legendre_coefficients(poles):
+    """(2l+1) P_l(mu) as polynomial coefficients in mu (degree <= 10), float32[Np][11].
+
+    Closed form used by the reference's ``P_n`` (power_spectrum.py:121-147):
+    P_l(mu) = 2^-l sum_k (-1)^k C(l,k) C(2l-2k,l) mu^(l-2k).
+    """
+    out = np.zeros((len(poles), ABK_POLE_NCOEF), dtype=np.float64)
+    for ip, ell in enumerate(poles):
+        ell = int(ell)
+        for k in range(ell // 2 + 1):
+            out[ip, ell - 2 * k] += (-1) ** k * math.comb(ell, k) * math.comb(2 * ell - 2 * k, ell) * 0.5**ell
+        out[ip] *= 2 * ell + 1
+    return out.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# device plumbing
+def _as_source(a, dtype_np):
+    """Normalise an input array: returns (kind, obj) with kind in {'cuda', 'host'}; host objects are
+    torch CPU tensors sharing memory with the caller's array (no copy for float32 C-contiguous)."""
+    import torch
+
+    if is_torch_tensor(a):
+        if a.is_cuda:
+            return 'cuda', a
+        return 'host', a.contiguous()
+    arr = np.ascontiguousarray(a)
+    if arr.dtype != dtype_np:
+        arr = arr.astype(dtype_np)
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return 'host', torch.from_numpy(arr)
+
+
+class _Painter:
+    """Stages a particle set on the device, buckets it for one or two offsets, deposits, normalises and
+    transforms in place.  Host inputs are streamed in chunks on a copy stream so the bucketing of
+    chunk i overlaps the host->device copy of chunk i+1; every chunk becomes one bucket segment."""
+
+    def __init__(self, eng, nmesh, Lbox):
+        self.eng = eng
+        self.n = int(nmesh)
+        self.L = float(Lbox)
+        self.ldz = padded_ldz(self.n)
+
+    def chunk_plan(self, N):
+        max_seg = ABK_MAX_SEGMENTS - 2
+        chunk = max(1 << 25, -(-N // max_seg))
+        chunk = min(chunk, SEGMENT_MAX)
+        return [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
+
+    def paint(self, pos, w, offsets, wrap=True, tag=''):
+        """Returns one padded device grid (n, n, ldz) float32 per offset, holding the raw deposit."""
+        import torch
+
+        eng, n, ldz = self.eng, self.n, self.ldz
+        lib = eng.lib
+        kind, psrc = _as_source(pos, np.float32)
+        N = int(psrc.shape[0])
+        wsrc = None
+        if w is not None:
+            wkind, wsrc = _as_source(w, np.float32)
+            if wkind != kind:
+                wsrc = wsrc.to(psrc.device)
+        compute = eng.bind_stream()
+        grids = [eng.zeros((n, n, ldz), torch.float32) for _ in offsets]
+        if N == 0:
+            return grids
+        if psrc.dtype != torch.float32:
+            psrc = psrc.to(torch.float32)
+        if wsrc is not None and wsrc.dtype != torch.float32:
+            wsrc = wsrc.to(torch.float32)
+
+        ntiles = C.c_int64()
+        check(lib.abk_tsc_num_tiles(n, n, n, C.byref(ntiles)))
+        ntiles = ntiles.value
+        chunks = self.chunk_plan(N)
+        nseg = len(chunks)
+        nb = C.c_size_t()
+        check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
+        scan_tmp = eng.scratch('bucket_scan', nb.value)
+        starts_stride = (ntiles + 1 + 63) // 64 * 64
+        records = [eng.scratch(f'records{tag}{o}', N * 16) for o in range(len(offsets))]
+        starts = [eng.scratch(f'starts{tag}{o}', nseg * starts_stride * 4) for o in range(len(offsets))]
+
+        host = kind == 'host'
+        if host:
+            csize = max(b - a for a, b in chunks)
+            copy_stream = torch.cuda.Stream(device=eng.device)
+            stage_p = [eng.scratch(f'stage_p{i}', csize * 12) for i in range(2)]
+            stage_w = [eng.scratch(f'stage_w{i}', csize * 4) for i in range(2)] if wsrc is not None else None
+            ready = [torch.cuda.Event() for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(2)]
+            for ev in done:
+                ev.record(compute)
+
+        for s, (a, b) in enumerate(chunks):
+            m = b - a
+            if host:
+                slot = s % 2
+                copy_stream.wait_event(done[slot])
+                with torch.cuda.stream(copy_stream):
+                    pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
+                    pd.copy_(psrc[a:b], non_blocking=True)
+                    wd = None
+                    if wsrc is not None:
+                        wd = stage_w[slot][: m * 4].view(torch.float32)
+                        wd.copy_(wsrc[a:b], non_blocking=True)
+                    ready[slot].record(copy_stream)
+                compute.wait_event(ready[slot])
+            else:
+                pd = psrc[a:b]
+                wd = None if wsrc is None else wsrc[a:b]
+                if not pd.is_contiguous():
+                    pd = pd.contiguous()
+            for o, off in enumerate(offsets):
+                rec_ptr = records[o].data_ptr() + a * 16
+                st_ptr = starts[o].data_ptr() + s * starts_stride * 4
+                check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(off), int(bool(wrap)),
+                                         C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp), scan_tmp.numel()))
+            if host:
+                done[slot].record(compute)
+
+        VP = C.c_void_p * nseg
+        I64 = C.c_int64 * nseg
+        counts = I64(*[b - a for a, b in chunks])
+        for o, off in enumerate(offsets):
+            recs = VP(*[records[o].data_ptr() + a * 16 for a, _ in chunks])
+            sts = VP(*[starts[o].data_ptr() + s * starts_stride * 4 for s in range(nseg)])
+            check(lib.abk_tsc_deposit_tiles(eng.ctx, nseg, recs, sts, counts, ptr(grids[o]), n, n, n, ldz, self.L,
+                                            float(off), 0, n))
+        return grids
+
+    def normalize_fft(self, grid, tot_weight):
+        eng, n, ldz = self.eng, self.n, self.ldz
+        eng.bind_stream()
+        check(eng.lib.abk_normalize_field(eng.ctx, ptr(grid), n, n, n, ldz, float(n) ** 3, float(tot_weight)))
+        eng.rfft3_inplace(grid, n, n, n)
+
+
+def _kmesh(n, row_len=None):
+    nzc = n // 2 + 1
+    row_len = nzc if row_len is None else int(row_len)
+    return KMesh(n=n, nzc=nzc, i0=0, i1=n, j0=0, j1=n, stride_i=n * row_len, stride_j=row_len)
+
+
+def _complex_view(grid_padded, n):
+    """(n, n, ldz) float32 in-place FFT buffer -> (n, n, n//2+1) complex64 view (same memory)."""
+    import torch
+
+    return torch.view_as_complex(grid_padded.view(n, n, n // 2 + 1, 2))
+
+
+def _check_paste(paste):
+    paste_u = str(paste).upper()
+    if paste_u == 'CIC':
+        raise NotImplementedError("paste='CIC' is not implemented on the GPU path yet (TSC only)")
+    if paste_u != 'TSC':
+        raise ValueError(f'Unknown pasting method: {paste}')
+    return paste_u
+
+
+# ---------------------------------------------------------------------------------------------
+# real-space field
+def normalize_field(field, tot_weight=None, inplace=False, nthread=MAX_THREADS):
+    """``field / field.mean() - 1`` as ``field * f32(size/tot_weight) - 1`` (power_spectrum.py:860-901)."""
+    import torch
+
+    on_device = is_torch_tensor(field) and field.is_cuda
+    eng = Engine.get(field.device if on_device else None)
+    eng.bind_stream()
+    fd = field if on_device else eng.to_device(field, torch.float32)
+    if tot_weight is None:
+        tot_weight = float(fd.sum(dtype=torch.float32).item())
+    if on_device and not inplace:
+        fd = fd.clone()
+    if not fd.is_contiguous() or fd.dtype != torch.float32:
+        raise AbkError('normalize_field: device field must be contiguous float32')
+    nz = fd.shape[-1]
+    rows = fd.numel() // nz
+    check(eng.lib.abk_normalize_field(eng.ctx, ptr(fd), 1, rows, nz, nz, float(fd.numel()), float(tot_weight)))
+    if on_device:
+        return fd
+    out = fd.cpu().numpy()
+    if inplace:
+        np.copyto(field, out.astype(field.dtype, copy=False))
+        return field
+    return out
+
+
+def get_field(pos, Lbox, nmesh, paste, w=None, d=0.0, nthread=MAX_THREADS, dtype=np.float32):
+    """Paint + normalise: returns the overdensity field (nmesh,)*3 float32 (power_spectrum.py:808-857).
+    Normalisation uses ``len(pos)``, not ``sum(w)``, like the reference (:856)."""
+    if w is not None:
+        assert pos.shape[0] == len(w)
+    _check_paste(paste)
+    on_device = is_torch_tensor(pos) and pos.is_cuda
+    eng = Engine.get(pos.device if on_device else None)
+    P = _Painter(eng, nmesh, Lbox)
+    (grid,) = P.paint(pos, w, [d])
+    n = int(nmesh)
+    check(eng.lib.abk_normalize_field(eng.ctx, ptr(grid), n, n, n, P.ldz, float(n) ** 3, float(len(pos))))
+    field = grid[:, :, :n].contiguous()
+    return field if on_device else field.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Fourier-space fields
+def shift_field_fft(field_fft, field_shift_fft, n1d, L, d, dtype=np.float32):
+    """In place ``f <- (f + fs * exp(i*0.5*d*(kx+ky+kz))) * 0.5/n^3`` (power_spectrum.py:904-948).
+    Only the reference's own call pattern ``d == L/n1d`` (half-cell interlacing) is supported."""
+    import torch
+
+    if not math.isclose(float(d), float(L) / int(n1d), rel_tol=1e-6):
+        raise NotImplementedError('shift_field_fft: only d == L/n1d (the interlacing shift) is implemented')
+    on_device = is_torch_tensor(field_fft) and field_fft.is_cuda
+    eng = Engine.get(field_fft.device if on_device else None)
+    eng.bind_stream()
+    n = int(n1d)
+    f = field_fft if on_device else eng.to_device(field_fft, torch.complex64)
+    fs = eng.to_device(field_shift_fft, torch.complex64)
+    mesh = _kmesh(n)
+    check(eng.lib.abk_field_fft_finish(eng.ctx, C.byref(mesh), ptr(f), ptr(fs), None, np.float32(0.5 / n**3)))
+    if not on_device:
+        np.copyto(field_fft, f.cpu().numpy())
+
+
+def _field_fft_device(eng, pos, Lbox, nmesh, w, interlaced, tag=''):
+    """Paint, normalise and FFT; returns the in-place padded grids [A] or [A, B(shifted)] (unscaled)."""
+    n = int(nmesh)
+    P = _Painter(eng, n, Lbox)
+    offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
+    grids = P.paint(pos, w, offsets, tag=tag)
+    for g in grids:
+        P.normalize_fft(g, len(pos))
+    return grids
+
+
+def get_interlaced_field_fft(pos, Lbox, nmesh, paste, w, nthread=MAX_THREADS, verbose=False):
+    """Interlaced delta(k), complex64 (n, n, n//2+1) (power_spectrum.py:951-998)."""
+    return get_field_fft(pos, Lbox, nmesh, paste, w, None, False, True, nthread=nthread, verbose=verbose)
+
+
+def get_field_fft(pos, Lbox, nmesh, paste, w, W, compensated, interlaced, nthread=MAX_THREADS, verbose=False,
+                  dtype=np.float32):
+    """delta(k) of a particle set, complex64 (n, n, n//2+1), NumPy rfftn conventions
+    (power_spectrum.py:1001-1070): paint (+ half-cell-shifted paint), normalise by len(pos), FFT,
+    scale by 1/n^3 (0.5/n^3 and the interlacing phase when ``interlaced``), divide by the window."""
+    import torch
+
+    _check_paste(paste)
+    if w is not None:
+        assert pos.shape[0] == len(w)
+    if compensated:
+        assert W is not None
+    on_device = is_torch_tensor(pos) and pos.is_cuda
+    eng = Engine.get(pos.device if on_device else None)
+    n = int(nmesh)
+    grids = _field_fft_device(eng, pos, Lbox, n, w, interlaced)
+    W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
+    mesh = _kmesh(n)
+    scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
+    eng.bind_stream()
+    check(eng.lib.abk_field_fft_finish(eng.ctx, C.byref(mesh), ptr(grids[0]), ptr(grids[1]) if interlaced else None,
+                                       ptr(W_d), scale))
+    out = _complex_view(grids[0], n)
+    if on_device:
+        return out
+    return out.cpu().numpy()
+
+
+def get_raw_power(field_fft, field2_fft=None):
+    """``|f|^2`` or ``Re(conj(f) f2)`` as a float32 array (power_spectrum.py:707-727)."""
+    import torch
+
+    on_device = is_torch_tensor(field_fft) and field_fft.is_cuda
+    eng = Engine.get(field_fft.device if on_device else None)
+    eng.bind_stream()
+    f1 = eng.to_device(field_fft, torch.complex64)
+    f2 = None if field2_fft is None else eng.to_device(field2_fft, torch.complex64)
+    out = eng.empty(tuple(f1.shape), torch.float32)
+    check(eng.lib.abk_raw_power(eng.ctx, ptr(f1), ptr(f2), ptr(out), f1.numel()))
+    return out if on_device else out.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# binning
+def _bin_device(eng, n, L, kedges, muedges, poles, fourier, *, f1=None, f1s=None, f2=None, f2s=None, real_in=None,
+                row_len=None, W_d=None, scale=1.0, finish=False):
+    """Run abk_power_bin and return the reference's five arrays as float64/int64 NumPy
+    (means, not yet cast): (weighted_counts, counts, weighted_counts_poles, counts_poles, weighted_counts_k)."""
+    import torch
+
+    kedges = np.asarray(kedges, dtype=np.float64)
+    muedges = np.asarray(muedges, dtype=np.float64)
+    poles = np.asarray(poles, dtype=np.int64).reshape(-1)
+    Nk, Nmu, Np = len(kedges) - 1, len(muedges) - 1, len(poles)
+    if Nk < 1 or Nmu < 1:
+        raise ValueError('need at least one k bin and one mu bin')
+    if Np > ABK_MAX_POLES:
+        raise ValueError(f'at most {ABK_MAX_POLES} multipoles per call')
+    if Np and (poles.max() > 10 or poles.min() < 0):
+        raise ValueError('multipoles must be in [0, 10]')
+    dk = 2.0 * np.pi / L if fourier else L / n
+    # power_spectrum.py:217-218: square in float64, THEN cast to float32
+    kedges2 = ((kedges / dk) ** 2).astype(np.float32)
+    muedges2 = (muedges**2).astype(np.float32)
+
+    Nb = Nk * Nmu
+    tables = np.concatenate([kedges2, muedges2, legendre_coefficients(poles).reshape(-1)]).astype(np.float32)
+    tables_d = eng.to_device(tables, torch.float32)
+    sums = eng.zeros((3 * Nb + Np * Nk,), torch.float64)
+
+    req = BinRequest()
+    req.mesh = _kmesh(n, row_len)
+    for name, t in (('f1', f1), ('f1s', f1s), ('f2', f2), ('f2s', f2s), ('real_in', real_in), ('W', W_d)):
+        setattr(req, name, None if t is None else t.data_ptr())
+    req.scale = float(scale)
+    req.finish = int(bool(finish))
+    base = tables_d.data_ptr()
+    req.kedges2 = base
+    req.muedges2 = base + 4 * (Nk + 1)
+    req.pole_coef = base + 4 * (Nk + 1 + Nmu + 1)
+    for ip in range(Np):
+        req.pole_ell[ip] = int(poles[ip])
+    req.Nk, req.Nmu, req.Np = Nk, Nmu, Np
+    sb = sums.data_ptr()
+    req.counts = sb
+    req.sum_p = sb + 8 * Nb
+    req.sum_k = sb + 16 * Nb
+    req.sum_poles = sb + 24 * Nb
+    eng.bind_stream()
+    check(eng.lib.abk_power_bin(eng.ctx, C.byref(req)))
+    return _finalize_bins(sums, Nk, Nmu, poles, dk)
+
+
+def _finalize_bins(sums, Nk, Nmu, poles, dk):
+    """Host tail of bin_kmu (power_spectrum.py:276-293): pole l=0 from the wedge sums, divisions by
+    the mode counts where non-zero (empty bins stay 0)."""
+    Np, Nb = len(poles), Nk * Nmu
+    h = sums.cpu().numpy()
+    counts = h[:Nb].view(np.int64).reshape(Nk, Nmu).copy()
+    sw = h[Nb:2 * Nb].reshape(Nk, Nmu).copy()
+    sk = h[2 * Nb:3 * Nb].reshape(Nk, Nmu) * dk
+    sp = h[3 * Nb:].reshape(Np, Nk).copy()
+    counts_poles = counts.sum(axis=1)
+    for ip, pole in enumerate(poles):
+        if pole == 0:
+            sp[ip] = sw.sum(axis=1)
+    nz = counts != 0
+    sw[nz] /= counts[nz]
+    sk[nz] /= counts[nz]
+    nzp = counts_poles != 0
+    if Np:
+        sp[:, nzp] /= counts_poles[nzp]
+    return sw, counts, sp, counts_poles, sk
+
+
+def bin_kmu(n1d, L, kedges, muedges, weights, poles=np.empty(0, 'i8'), dtype=np.float32, fourier=True,
+            nthread=MAX_THREADS):
+    """Mean and mode count of a 3-D mesh in (k, mu) bins, plus Legendre multipoles
+    (power_spectrum.py:150-300).  ``weights`` is real, shape (n1d, n1d, n1d//2+1) (rfft layout) or
+    (n1d, n1d, n1d) (real-space mesh, ``fourier=False``).  Bins are right-closed, Nyquist-plane modes
+    count twice, empty bins are 0 -- all as in the reference."""
+    import torch
+
+    on_device = is_torch_tensor(weights) and weights.is_cuda
+    eng = Engine.get(weights.device if on_device else None)
+    wd = eng.to_device(weights, torch.float32)
+    n = int(n1d)
+    if wd.ndim != 3 or wd.shape[0] != n or wd.shape[1] != n or wd.shape[2] < n // 2 + 1:
+        raise ValueError(f'weights has shape {tuple(wd.shape)}, expected ({n},{n},>={n // 2 + 1})')
+    sw, counts, sp, counts_poles, sk = _bin_device(eng, n, float(L), kedges, muedges, poles, fourier, real_in=wd,
+                                                   row_len=wd.shape[2])
+    dt = np.dtype(dtype)
+    return sw.astype(dt), counts, sp.astype(dt), counts_poles, sk.astype(dt)
+
+
+def project_3d_to_poles(k_bin_edges, raw_p3d, Lbox, poles):
+    """Project a 3-D power array (rfftn layout) onto multipoles (power_spectrum.py:415-447).
+    Returns ``(binned_poles * Lbox**3  (Np, Nk) float32, N_mode_poles (Nk,) int64)``."""
+    assert np.max(poles) <= 10, 'numba implementation works up to ell = 10'
+    nmesh = raw_p3d.shape[0]
+    poles = np.asarray(poles)
+    muedges = np.array([0.0, 1.0])
+    _, _, binned_poles, Npoles, _ = bin_kmu(nmesh, Lbox, k_bin_edges, muedges, raw_p3d, poles=poles)
+    binned_poles *= Lbox**3
+    return binned_poles, Npoles
+
+
+def _package_pk(binned, Lbox, mu_bin_edges, poles, squeeze_mu_axis):
+    sw, counts, sp, counts_poles, sk = binned
+    power = sw.astype(np.float32)
+    k_avg = sk.astype(np.float32)
+    binned_poles = sp.astype(np.float32)
+    power *= Lbox**3  # power_spectrum.py:790
+    if len(poles) > 0:
+        binned_poles *= Lbox**3
+    N_mode = counts
+    if squeeze_mu_axis and len(mu_bin_edges) == 2:
+        power = power[:, 0]
+        N_mode = N_mode[:, 0]
+        k_avg = k_avg[:, 0]
+    return dict(power=power, N_mode=N_mode, binned_poles=binned_poles, N_mode_poles=counts_poles, k_avg=k_avg)
+
+
+def calc_pk_from_deltak(field_fft, Lbox, k_bin_edges, mu_bin_edges, field2_fft=None, poles=np.empty(0, 'i8'),
+                        squeeze_mu_axis=True, nthread=MAX_THREADS):
+    """Bin ``|delta(k)|^2`` (or ``Re(conj(d1) d2)``) of supplied Fourier fields in (k, mu) and multipoles
+    (power_spectrum.py:730-805).  Inputs are not modified.  Returns a dict with ``power``, ``N_mode``,
+    ``binned_poles`` (Np, Nk), ``N_mode_poles``, ``k_avg``; ``power`` and the poles are multiplied by
+    ``Lbox**3``."""
+    import torch
+
+    on_device = is_torch_tensor(field_fft) and field_fft.is_cuda
+    eng = Engine.get(field_fft.device if on_device else None)
+    f1 = eng.to_device(field_fft, torch.complex64)
+    f2 = None if field2_fft is None else eng.to_device(field2_fft, torch.complex64)
+    n = int(f1.shape[0])
+    if tuple(f1.shape) != (n, n, n // 2 + 1) or (f2 is not None and f2.shape != f1.shape):
+        raise ValueError(f'field_fft must have shape (n, n, n//2+1), got {tuple(f1.shape)}')
+    poles = np.asarray(poles, dtype=np.int64)
+    binned = _bin_device(eng, n, float(Lbox), k_bin_edges, mu_bin_edges, poles, True, f1=f1, f2=f2)
+    return _package_pk(binned, Lbox, mu_bin_edges, poles, squeeze_mu_axis)
+
+
+def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste='TSC', nmesh=128, compensated=True,
+               interlaced=True, w=None, pos2=None, w2=None, poles=None, squeeze_mu_axis=True, nthread=MAX_THREADS,
+               dtype=np.float32):
+    r"""
+    3-D power spectrum of a particle set in (k, mu) wedges and Legendre multipoles
+    (reference: power_spectrum.py:1131-1319; same parameters and returned columns).
+
+    Returns a table with columns ``k_min, k_max, k_mid`` (float64), ``k_avg, power`` (float32),
+    ``N_mode`` (int64), and when ``poles`` is given ``poles`` (Nk, Np) float32 and ``N_mode_poles``;
+    ``mu_min, mu_max, mu_mid`` when ``mubins`` is given.  ``meta`` records the run parameters.
+    With ``pos2`` (and ``w2``) the cross spectrum of the two catalogues is returned.
+    """
+    import torch
+
+    if kbins is None:
+        kbins = nmesh
+    if k_max is None:
+        k_max = np.pi * nmesh / Lbox
+    return_mubins = mubins is not None
+    if mubins is None:
+        mubins = 1
+    meta = dict(Lbox=Lbox, logk=logk, paste=paste, nmesh=nmesh, compensated=compensated, interlaced=interlaced,
+                poles=poles, nthread=nthread, N_pos=len(pos), is_weighted=w is not None, field_dtype=dtype,
+                squeeze_mu_axis=squeeze_mu_axis)
+    if pos2 is not None:
+        meta['N_pos2'] = len(pos2)
+        meta['is_weighted2'] = w2 is not None
+    _check_paste(paste)
+    if w is not None:
+        assert pos.shape[0] == len(w)
+    if pos2 is not None and w2 is not None:
+        assert pos2.shape[0] == len(w2)
+
+    on_device = is_torch_tensor(pos) and pos.is_cuda
+    eng = Engine.get(pos.device if on_device else None)
+    n = int(nmesh)
+    W = get_W_compensated(Lbox, n, paste, interlaced) if compensated else None
+    W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
+
+    g1 = _field_fft_device(eng, pos, Lbox, n, w, interlaced, tag='a')
+    g2 = _field_fft_device(eng, pos2, Lbox, n, w2, interlaced, tag='a') if pos2 is not None else None
+
+    poles_arr = np.asarray(poles or [], dtype=np.int64)
+    kbins, mubins = get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)
+    scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
+    binned = _bin_device(eng, n, float(Lbox), kbins, mubins, poles_arr, True, f1=g1[0],
+                         f1s=g1[1] if interlaced else None, f2=None if g2 is None else g2[0],
+                         f2s=g2[1] if (g2 is not None and interlaced) else None, W_d=W_d, scale=scale, finish=True)
+    P = _package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
+
+    kbins = np.asarray(kbins)
+    mubins = np.asarray(mubins)
+    k_binc = (kbins[1:] + kbins[:-1]) * 0.5
+    mu_binc = (mubins[1:] + mubins[:-1]) * 0.5
+    res = dict(k_min=kbins[:-1], k_max=kbins[1:], k_mid=k_binc, k_avg=P['k_avg'], power=P['power'],
+               N_mode=P['N_mode'])
+    if len(poles_arr) > 0:
+        res.update(poles=P['binned_poles'].T, N_mode_poles=P['N_mode_poles'])
+    if return_mubins:
+        res.update(mu_min=np.broadcast_to(mubins[:-1], res['power'].shape),
+                   mu_max=np.broadcast_to(mubins[1:], res['power'].shape),
+                   mu_mid=np.broadcast_to(mu_binc, res['power'].shape))
+    return _make_table(res, meta)
+
+
+def pk_to_xi(*args, **kwargs):
+    """xi(r) multipoles (power_spectrum.py:620-660) -- next on the roadmap, not yet on the GPU."""
+    raise NotImplementedError('pk_to_xi is not implemented on the GPU path yet')
+
+
+_ = (warnings, tsc_parallel)

@@ -1,0 +1,166 @@
+// Context, error reporting and small device utilities of libabk.
+#include <stdarg.h>
+#include <string.h>
+
+#include "abk_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void abk_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *abk_last_error(void) { return g_err; }
+extern "C" int abk_version(void) { return ABK_VERSION; }
+
+extern "C" int abk_ctx_create(int device, abk_ctx **out)
+{
+    ABK_REQUIRE(out != nullptr, "abk_ctx_create: null output pointer");
+    int ndev = 0;
+    ABK_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+    ABK_REQUIRE(device >= 0 && device < ndev, "abk_ctx_create: device %d out of range (%d visible)", device, ndev);
+    ABK_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ABK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        abk_set_error("abk_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                      device, prop.major, prop.minor);
+        return ABK_ERR_INVALID;
+    }
+    abk_ctx *c = new abk_ctx();
+    c->device = device;
+    c->stream = nullptr;
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c->launches = 0;
+    c->tile_capacity = 0;
+    c->d_scalars = nullptr;
+    ABK_CHECK_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(unsigned long long)));
+    ABK_CHECK_CUDA(cudaMemset(c->d_scalars, 0, 64 * sizeof(unsigned long long)));
+    *out = c;
+    return ABK_OK;
+}
+
+extern "C" int abk_ctx_destroy(abk_ctx *ctx)
+{
+    if (!ctx) return ABK_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+    delete ctx;
+    return ABK_OK;
+}
+
+extern "C" int abk_ctx_set_stream(abk_ctx *ctx, void *stream)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ctx->stream = (cudaStream_t)stream;
+    return ABK_OK;
+}
+
+extern "C" int abk_ctx_sync(abk_ctx *ctx)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ABK_OK;
+}
+
+extern "C" int64_t abk_ctx_launch_count(abk_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ABK_REQUIRE(capacity == 0 || (capacity >= 256 && capacity <= 12288), "tile capacity %d out of range", capacity);
+    ctx->tile_capacity = capacity;
+    return ABK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Inclusive scan of uint32 (tile histograms -> bucket boundaries).  Three-level recursive
+// block scan; the arrays are small (<= a few 10^7 entries) next to the particle data.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_kernel(uint32_t *data, int64_t n, uint32_t *block_sums)
+{
+    __shared__ uint32_t warp_tot[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+        const int64_t i = base + q;
+        run += (i < n) ? data[i] : 0u;
+        v[q] = run;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += t;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t prefix = (inc - run) + (wid ? warp_tot[wid - 1] : 0u);
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+        const int64_t i = base + q;
+        if (i < n) data[i] = v[q] + prefix;
+    }
+    if (block_sums && threadIdx.x == SCAN_THREADS - 1) block_sums[blockIdx.x] = prefix + run;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *data, int64_t n, const uint32_t *block_incl)
+{
+    if (blockIdx.x == 0) return;
+    const uint32_t add = block_incl[blockIdx.x - 1];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+        const int64_t i = base + q;
+        if (i < n) data[i] += add;
+    }
+}
+
+size_t abk_scan_tmp_bytes(int64_t n)
+{
+    size_t total = 0;
+    int64_t m = n;
+    while (m > SCAN_BLOCK) {
+        m = (m + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        total += abk_align_up((size_t)m * sizeof(uint32_t), 256);
+    }
+    return total + 256;
+}
+
+int abk_inclusive_scan_u32(abk_ctx *ctx, uint32_t *data, int64_t n, void *tmp)
+{
+    if (n <= 0) return ABK_OK;
+    const int64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    uint32_t *sums = (nblocks > 1) ? (uint32_t *)tmp : nullptr;
+    scan_block_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
+    ABK_CHECK_LAUNCH(ctx);
+    if (nblocks > 1) {
+        char *next = (char *)tmp + abk_align_up((size_t)nblocks * sizeof(uint32_t), 256);
+        int rc = abk_inclusive_scan_u32(ctx, sums, nblocks, next);
+        if (rc) return rc;
+        scan_add_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
+        ABK_CHECK_LAUNCH(ctx);
+    }
+    return ABK_OK;
+}

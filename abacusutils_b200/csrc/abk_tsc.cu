@@ -1,0 +1,603 @@
+// TSC mass assignment on B200 (sm_100a).
+//
+// Replaces, with a different algorithm, the reference's Numba kernels
+//   _wrap_inplace        analysis/tsc.py:219-226
+//   partition_parallel   analysis/tsc.py:259-384
+//   _tsc_parallel        analysis/tsc.py:229-256   (two-colour x-stripe schedule)
+//   _tsc_scatter         analysis/tsc.py:394-507   (27 read-modify-writes per particle)
+//
+// Design (see DESIGN.md "TSC deposit"):
+//   A. bucket particles by the (8 x 8 x 32)-cell tile of their cloud's centre cell: histogram
+//      (one 4-byte reduction per particle), scan, scatter of 16-byte (x,y,z,w) records.  The open
+//      write frontier is one 128-byte line per tile, which stays resident in the 126 MB L2, so the
+//      scatter reaches DRAM as full lines.
+//   B. one CTA per tile: per-cell particle lists are built in shared memory with one integer
+//      exchange per particle; then warp = y-row, lane = z-cell, x walked serially: every lane sums
+//      the 27 stencil weights of ITS cell's particles in registers (a rolling 3-plane window along
+//      x), neighbouring lanes are combined with two shuffles, neighbouring rows through a
+//      shared-memory tile written without atomics (each (plane,row) is owned by exactly one warp
+//      per phase).  Shared-memory float atomics are a CAS loop on sm_100a
+//      (ATOMS.CAST.SPIN), so the kernel uses none.  The finished tile + 1-cell halo is added to
+//      the grid with coalesced float reductions (REDG.ADD.F32): ~1.7 per CELL instead of 27 per
+//      PARTICLE.
+#include "abk_common.cuh"
+
+namespace {
+
+struct TscParams {
+    float inv_hx, inv_hy, inv_hz;  // f32(g/box), tsc.py:408-411
+    float off;                     // f32(offset), tsc.py:413
+    double box;
+    int nx, ny, nz;                // global grid
+    int nxe;                       // x-extent of the tiled region (== nx single GPU; slab mode: local planes)
+    int x_lo;                      // first global x-plane of the tiled region
+    int nty, ntz;
+    int wrap;
+};
+
+// tsc.py:219-226: one-shot wrap; compare against the double box, store float32
+__device__ __forceinline__ float wrap_coord(float v, double box)
+{
+    if ((double)v >= box) return (float)((double)v - box);
+    if (v < 0.0f) return (float)((double)v + box);
+    return v;
+}
+
+// tsc.py:424-440: p = (x + off) * inv_h; i = round-half-even(p); d = f32(i) - p
+__device__ __forceinline__ void cell_of(float x, float off, float inv_h, int n, int &cell, float &d)
+{
+    const float p = __fmul_rn(__fadd_rn(x, off), inv_h);
+    const float r = rintf(p);
+    d = r - p;
+    cell = abk_wrap_cell((int)r, n);
+}
+
+__device__ __forceinline__ bool tile_of(const TscParams &P, float x, float y, float z, uint32_t &tile)
+{
+    int cx, cy, cz;
+    float d;
+    cell_of(x, P.off, P.inv_hx, P.nx, cx, d);
+    cell_of(y, P.off, P.inv_hy, P.ny, cy, d);
+    cell_of(z, P.off, P.inv_hz, P.nz, cz, d);
+    int lx = cx - P.x_lo;
+    if (lx < 0) lx += P.nx;
+    if (lx >= P.nxe) return false;  // not owned by this slab
+    tile = ((uint32_t)(lx / ABK_TX) * P.nty + (uint32_t)(cy / ABK_TY)) * P.ntz + (uint32_t)(cz / ABK_TZ);
+    return true;
+}
+
+// Loads particle i (AoS float[N][3]); VEC4 path handles 4 particles per thread with 3 x 128-bit loads.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict__ pos, const float *__restrict__ w,
+                                                         int64_t N, TscParams P, uint32_t *__restrict__ counts,
+                                                         float4 *__restrict__ records, int vec_ok,
+                                                         unsigned long long *__restrict__ n_dropped)
+{
+    const int64_t ngroups = (N + 3) / 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = g * 4;
+        float c[12];
+        const int cnt = (int)min((int64_t)4, N - base);
+        if (vec_ok && cnt == 4) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(pos + 3 * base);
+            const float4 a = __ldcs(p4), b = __ldcs(p4 + 1), d = __ldcs(p4 + 2);
+            c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+            c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
+        } else {
+            for (int q = 0; q < 3 * cnt; q++) c[q] = __ldcs(pos + 3 * base + q);
+        }
+        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (SCATTER && w) {
+            if (vec_ok && cnt == 4) {
+                const float4 t = __ldcs(reinterpret_cast<const float4 *>(w + base));
+                wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
+            } else {
+                for (int q = 0; q < cnt; q++) wv[q] = __ldcs(w + base + q);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q >= cnt) break;
+            float x = c[3 * q], y = c[3 * q + 1], z = c[3 * q + 2];
+            if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
+            uint32_t tile;
+            if (!tile_of(P, x, y, z, tile)) {
+                if (!SCATTER) atomicAdd(n_dropped, 1ull);
+                continue;
+            }
+            if (!SCATTER) {
+                atomicAdd(&counts[tile], 1u);
+            } else {
+                // cursors count DOWN from the inclusive scan, so they end as the exclusive scan
+                const uint32_t slot = atomicSub(&counts[tile], 1u) - 1u;
+                records[slot] = make_float4(x, y, z, wv[q]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int OUT_X = ABK_TX + 2, OUT_Y = ABK_TY + 2, OUT_Z = ABK_TZ + 2;
+constexpr int OUT_N = OUT_X * OUT_Y * OUT_Z;
+constexpr int NCELL = ABK_TX * ABK_TY * ABK_TZ;
+constexpr int DEP_THREADS = ABK_TY * 32;
+constexpr uint32_t NIL = 0xffffffffu;
+
+struct SegList {
+    int nseg;
+    const float4 *rec[ABK_MAX_SEGMENTS];
+    const uint32_t *starts[ABK_MAX_SEGMENTS];
+};
+
+static size_t deposit_smem_bytes(int cap)
+{
+    return (size_t)OUT_N * 4 + (size_t)NCELL * 4 + (size_t)cap * 16 + (size_t)cap * 2 + 64;
+}
+
+// tsc.py:442-451: the three 1-D TSC weights for cells i-1, i, i+1 given d = i - p
+__device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
+{
+    const float a = 0.5f + d, b = 0.5f - d;
+    wm = 0.5f * a * a;
+    w0 = 0.75f - d * d;
+    wp = 0.5f * b * b;
+}
+
+__device__ __forceinline__ void emit_plane(float *__restrict__ out, const float (&S)[3][3], int x, int wy, int lane)
+{
+    // S[b][c]: this lane's (cell cz = lane) contribution to row wy-1+b, cell cz-1+c of plane x.
+    // Lane cz receives c=+1 from lane cz-1 and c=-1 from lane cz+1.
+    float *plane = out + (x + 1) * (OUT_Y * OUT_Z);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
+        const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
+        float v = S[b][1];
+        if (lane > 0) v += up;
+        if (lane < 31) v += dn;
+        float *row = plane + (wy + b) * OUT_Z;
+        row[lane + 1] += v;
+        if (lane == 0) row[0] += S[b][0];
+        if (lane == 31) row[OUT_Z - 1] += S[b][2];
+        __syncthreads();  // rows wy+b of different warps are distinct within a phase, not across phases
+    }
+}
+
+__global__ void __launch_bounds__(DEP_THREADS, 3)
+tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *out = reinterpret_cast<float *>(smem_raw);
+    uint32_t *head = reinterpret_cast<uint32_t *>(out + OUT_N);
+    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);  // (OUT_N + NCELL)*4 is a multiple of 16
+    uint16_t *next = reinterpret_cast<uint16_t *>(srec + cap);
+    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
+    __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
+
+    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (tid < segs.nseg) {
+        const uint32_t b = segs.starts[tid][tile], e = segs.starts[tid][tile + 1];
+        seg_beg[tid] = b;
+        seg_cnt[tid] = e - b;
+        seg_rec[tid] = segs.rec[tid];
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    for (int s = 0; s < segs.nseg; s++) total += seg_cnt[s];
+    if (total == 0) return;
+
+    const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
+    const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
+
+    for (int i = tid; i < OUT_N; i += DEP_THREADS) out[i] = 0.0f;
+
+    for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
+        const int m = (int)min((uint32_t)cap, total - chunk0);
+        for (int c = tid; c < NCELL; c += DEP_THREADS) head[c] = NIL;
+        __syncthreads();
+        // ---- build per-cell lists -----------------------------------------------------------
+        for (int v = tid; v < m; v += DEP_THREADS) {
+            uint32_t u = chunk0 + v;
+            int s = 0;
+            while (u >= seg_cnt[s]) { u -= seg_cnt[s]; s++; }
+            const float4 r = __ldcs(seg_rec[s] + seg_beg[s] + u);
+            int cx, cy, cz;
+            float dx, dy, dz;
+            cell_of(r.x, P.off, P.inv_hx, P.nx, cx, dx);
+            cell_of(r.y, P.off, P.inv_hy, P.ny, cy, dy);
+            cell_of(r.z, P.off, P.inv_hz, P.nz, cz, dz);
+            int lx = cx - P.x_lo;
+            if (lx < 0) lx += P.nx;
+            const int c = ((lx - x0) * ABK_TY + (cy - y0)) * ABK_TZ + (cz - z0);
+            srec[v] = make_float4(dx, dy, dz, r.w);
+            next[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+        }
+        __syncthreads();
+        // ---- accumulate: lane owns cell (cx, wy, lane); rolling window over x ------------------
+        float S0[3][3], S1[3][3], S2[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) S0[b][c] = S1[b][c] = S2[b][c] = 0.0f;
+
+#pragma unroll 1
+        for (int cx = 0; cx < ABK_TX; cx++) {
+            uint32_t i = head[(cx * ABK_TY + wy) * ABK_TZ + lane];
+            while (i != NIL) {
+                const float4 r = srec[i];
+                const uint16_t nxt = next[i];
+                i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
+                float wxm, wx0, wxp, wym, wy0, wyp, wzm, wz0, wzp;
+                tsc_w(r.x, wxm, wx0, wxp);
+                tsc_w(r.y, wym, wy0, wyp);
+                tsc_w(r.z, wzm, wz0, wzp);
+                const float wyv[3] = {wym, wy0, wyp}, wzv[3] = {wzm, wz0, wzp};
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float t = wyv[b] * wzv[c] * r.w;
+                        S0[b][c] = fmaf(wxm, t, S0[b][c]);
+                        S1[b][c] = fmaf(wx0, t, S1[b][c]);
+                        S2[b][c] = fmaf(wxp, t, S2[b][c]);
+                    }
+            }
+            emit_plane(out, S0, cx - 1, wy, lane);
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
+        }
+        emit_plane(out, S0, ABK_TX - 1, wy, lane);
+        emit_plane(out, S1, ABK_TX, wy, lane);
+    }
+
+    // ---- flush tile + halo ---------------------------------------------------------------------
+    const int64_t sx = (int64_t)P.ny * ldz;
+    for (int i = tid; i < OUT_N; i += DEP_THREADS) {
+        const float v = out[i];
+        if (v == 0.0f) continue;
+        const int oz = i % OUT_Z, oy = (i / OUT_Z) % OUT_Y, ox = i / (OUT_Z * OUT_Y);
+        int64_t gx;
+        if (slab) gx = x0 + ox;  // grid plane 0 is the ghost plane x_lo-1
+        else gx = abk_wrap_cell(x0 + ox - 1, P.nx);
+        const int gy = abk_wrap_cell(y0 + oy - 1, P.ny);
+        const int gz = abk_wrap_cell(z0 + oz - 1, P.nz);
+        atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gz, v);
+    }
+}
+
+// validation path: one thread per particle, 27 global reductions in the reference's cell order
+__global__ void __launch_bounds__(256) tsc_naive_kernel(const float *__restrict__ pos, const float *__restrict__ w,
+                                                        int64_t N, float *__restrict__ grid, TscParams P, int64_t ldz)
+{
+    const int64_t sx = (int64_t)P.ny * ldz;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        float x = pos[3 * n], y = pos[3 * n + 1], z = pos[3 * n + 2];
+        if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
+        const float W = w ? w[n] : 1.0f;
+        int cx, cy, cz;
+        float dx, dy, dz;
+        cell_of(x, P.off, P.inv_hx, P.nx, cx, dx);
+        cell_of(y, P.off, P.inv_hy, P.ny, cy, dy);
+        cell_of(z, P.off, P.inv_hz, P.nz, cz, dz);
+        float wx[3], wy[3], wz[3];
+        tsc_w(dx, wx[0], wx[1], wx[2]);
+        tsc_w(dy, wy[0], wy[1], wy[2]);
+        tsc_w(dz, wz[0], wz[1], wz[2]);
+        for (int a = 0; a < 3; a++) {
+            const int64_t gx = abk_wrap_cell(cx + a - 1, P.nx);
+            for (int b = 0; b < 3; b++) {
+                const int gy = abk_wrap_cell(cy + b - 1, P.ny);
+                for (int c = 0; c < 3; c++) {
+                    const int gz = abk_wrap_cell(cz + c - 1, P.nz);
+                    atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gz, wx[a] * wy[b] * wz[c] * W);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) wrap_inplace_kernel(float *__restrict__ pos, int64_t n3, double box,
+                                                           unsigned long long *__restrict__ n_changed)
+{
+    unsigned long long changed = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = pos[i];
+        const float r = wrap_coord(v, box);
+        if (r != v && v == v) {
+            pos[i] = r;
+            changed++;
+        }
+    }
+    if (n_changed && changed) atomicAdd(n_changed, changed);
+}
+
+// ---- partition_parallel (tsc.py:259-384) ---------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) partition_kernel(const float *__restrict__ pos, const float *__restrict__ w,
+                                                        int64_t N, int npart, float inv_pwidth, int coord,
+                                                        uint32_t *__restrict__ counts, float *__restrict__ out_pos,
+                                                        float *__restrict__ out_w)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        const float v = coord == 0 ? x : (coord == 1 ? y : z);
+        int key = (int)(v * inv_pwidth);  // truncation, like np.int32()
+        key = max(0, min(key, npart - 1));
+        if (!SCATTER) {
+            atomicAdd(&counts[key], 1u);
+        } else {
+            const uint32_t s = atomicSub(&counts[key], 1u) - 1u;
+            out_pos[3 * (int64_t)s] = x;
+            out_pos[3 * (int64_t)s + 1] = y;
+            out_pos[3 * (int64_t)s + 2] = z;
+            if (w) out_w[s] = w[i];
+        }
+    }
+}
+
+__global__ void starts_to_i64_kernel(const uint32_t *__restrict__ excl, int npart, int64_t N, int64_t *__restrict__ starts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npart) starts[i] = excl[i];
+    if (i == npart) starts[i] = N;
+}
+
+int make_params(TscParams &P, int nx, int ny, int nz, double box, double offset, int wrap, int x_lo, int nxe)
+{
+    ABK_REQUIRE(nx > 0 && ny > 0 && nz > 0, "grid shape (%d,%d,%d) must be positive", nx, ny, nz);
+    ABK_REQUIRE(box > 0, "box must be positive");
+    ABK_REQUIRE(nxe > 0 && nxe <= nx + 1 && x_lo >= 0 && x_lo < nx, "bad slab range x_lo=%d nxe=%d nx=%d", x_lo, nxe, nx);
+    P.inv_hx = (float)(nx / box);
+    P.inv_hy = (float)(ny / box);
+    P.inv_hz = (float)(nz / box);
+    P.off = (float)offset;
+    P.box = box;
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.nxe = nxe; P.x_lo = x_lo;
+    const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
+    P.nty = g.nty; P.ntz = g.ntz;
+    P.wrap = wrap;
+    return ABK_OK;
+}
+
+int grid_for(const abk_ctx *ctx, int64_t work_items, int threads, int per_sm)
+{
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)ctx->num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+// ==============================================================================================
+extern "C" int abk_wrap_inplace(abk_ctx *ctx, float *pos, int64_t N, double box, int64_t *n_changed_dev)
+{
+    ABK_REQUIRE(ctx && (pos || N == 0) && N >= 0, "abk_wrap_inplace: bad arguments");
+    if (N == 0) return ABK_OK;
+    wrap_inplace_kernel<<<grid_for(ctx, 3 * N, 256, 16), 256, 0, ctx->stream>>>(pos, 3 * N, box,
+                                                                                 (unsigned long long *)n_changed_dev);
+    ABK_CHECK_LAUNCH(ctx);
+    return ABK_OK;
+}
+
+extern "C" int abk_partition_scratch_bytes(int64_t N, int npart, size_t *bytes)
+{
+    ABK_REQUIRE(bytes && npart > 0 && N >= 0, "abk_partition_scratch_bytes: bad arguments");
+    *bytes = abk_align_up((size_t)(npart + 1) * 4, 256) + abk_scan_tmp_bytes(npart);
+    return ABK_OK;
+}
+
+extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int npart, double box,
+                             int coord, float *out_pos, float *out_w, int64_t *out_starts, void *scratch,
+                             size_t scratch_bytes)
+{
+    ABK_REQUIRE(ctx && out_starts && npart > 0 && N >= 0 && coord >= 0 && coord < 3, "abk_partition: bad arguments");
+    ABK_REQUIRE(N < (int64_t)1 << 32, "abk_partition: N=%lld exceeds 2^32-1", (long long)N);
+    size_t need;
+    abk_partition_scratch_bytes(N, npart, &need);
+    if (scratch_bytes < need) {
+        abk_set_error("abk_partition: scratch %zu < %zu", scratch_bytes, need);
+        return ABK_ERR_SCRATCH;
+    }
+    uint32_t *counts = (uint32_t *)scratch;
+    void *tmp = (char *)scratch + abk_align_up((size_t)(npart + 1) * 4, 256);
+    ABK_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)(npart + 1) * 4, ctx->stream));
+    const float inv_pwidth = (float)((double)npart / box);
+    if (N > 0) {
+        const int blocks = grid_for(ctx, N, 256, 16);
+        partition_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, nullptr, nullptr);
+        ABK_CHECK_LAUNCH(ctx);
+        int rc = abk_inclusive_scan_u32(ctx, counts, npart, tmp);
+        if (rc) return rc;
+        partition_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, out_pos, out_w);
+        ABK_CHECK_LAUNCH(ctx);
+    }
+    starts_to_i64_kernel<<<(npart + 256) / 256, 256, 0, ctx->stream>>>(counts, npart, N, out_starts);
+    ABK_CHECK_LAUNCH(ctx);
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles)
+{
+    ABK_REQUIRE(ntiles && nx > 0 && ny > 0 && nz > 0, "abk_tsc_num_tiles: bad arguments");
+    *ntiles = abk_make_geom(nx, ny, nz).ntiles;
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes)
+{
+    ABK_REQUIRE(bytes && nx > 0 && ny > 0 && nz > 0 && N >= 0, "abk_tsc_bucket_scratch_bytes: bad arguments");
+    *bytes = abk_scan_tmp_bytes(abk_make_geom(nx, ny, nz).ntiles) + 256;
+    return ABK_OK;
+}
+
+static int bucket_impl(abk_ctx *ctx, const float *pos, const float *w, int64_t N, const TscParams &P, void *records,
+                       uint32_t *tile_starts, void *scratch, size_t scratch_bytes)
+{
+    const abk_tile_geom g = abk_make_geom(P.nxe, P.ny, P.nz);
+    ABK_REQUIRE(g.ntiles < ((int64_t)1 << 31), "too many tiles (%lld)", (long long)g.ntiles);
+    ABK_REQUIRE(N <= ((int64_t)1 << 30), "a bucket segment holds at most 2^30 particles (got %lld)", (long long)N);
+    size_t need = abk_scan_tmp_bytes(g.ntiles) + 256;
+    if (scratch_bytes < need) {
+        abk_set_error("abk_tsc_bucket: scratch %zu < %zu", scratch_bytes, need);
+        return ABK_ERR_SCRATCH;
+    }
+    ABK_CHECK_CUDA(cudaMemsetAsync(tile_starts, 0, (size_t)(g.ntiles + 1) * 4, ctx->stream));
+    unsigned long long *dropped = ctx->d_scalars + 1;
+    if (N > 0) {
+        const int vec_ok = (((uintptr_t)pos & 15) == 0) && (!w || ((uintptr_t)w & 15) == 0);
+        const int blocks = grid_for(ctx, (N + 3) / 4, 256, 16);
+        tsc_bucket_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped);
+        ABK_CHECK_LAUNCH(ctx);
+        int rc = abk_inclusive_scan_u32(ctx, tile_starts, g.ntiles, scratch);
+        if (rc) return rc;
+        // sentinel tile_starts[ntiles] = number of bucketed particles = inclusive total
+        ABK_CHECK_CUDA(cudaMemcpyAsync(tile_starts + g.ntiles, tile_starts + g.ntiles - 1, 4, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+        tsc_bucket_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped);
+        ABK_CHECK_LAUNCH(ctx);
+    }
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
+                              double box, double offset, int wrap, void *records, uint32_t *tile_starts,
+                              void *scratch, size_t scratch_bytes)
+{
+    ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket: null argument");
+    TscParams P;
+    int rc = make_params(P, nx, ny, nz, box, offset, wrap, 0, nx);
+    if (rc) return rc;
+    return bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
+}
+
+extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
+                                   double box, double offset, int wrap, int x_lo, int nxe, void *records,
+                                   uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
+                                   unsigned long long *n_dropped_h)
+{
+    ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket_slab: null argument");
+    TscParams P;
+    int rc = make_params(P, nx, ny, nz, box, offset, wrap, x_lo, nxe);
+    if (rc) return rc;
+    ABK_CHECK_CUDA(cudaMemsetAsync(ctx->d_scalars + 1, 0, 8, ctx->stream));
+    rc = bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
+    if (rc) return rc;
+    if (n_dropped_h) {
+        ABK_CHECK_CUDA(cudaMemcpyAsync(n_dropped_h, ctx->d_scalars + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return ABK_OK;
+}
+
+static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles)
+{
+    if (ctx->tile_capacity) return ctx->tile_capacity;
+    // mean occupancy + 5 sigma (Poisson), rounded up to 256, so a uniform catalogue needs one pass
+    const double mean = ntiles > 0 ? (double)n_total / (double)ntiles : 0.0;
+    double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
+    int cap = (int)((want + 255.0) / 256.0) * 256;
+    if (cap < 512) cap = 512;
+    if (cap > 8192) cap = 8192;
+    return cap;
+}
+
+extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
+                                     const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h,
+                                     float *grid, int nx, int ny, int nz, int64_t ldz, double box, double offset,
+                                     int x_lo, int nxe)
+{
+    ABK_REQUIRE(ctx && grid && nseg >= 1 && nseg <= ABK_MAX_SEGMENTS, "abk_tsc_deposit_tiles: bad arguments");
+    ABK_REQUIRE(ldz >= nz, "ldz %lld < nz %d", (long long)ldz, nz);
+    TscParams P;
+    int rc = make_params(P, nx, ny, nz, box, offset, 0, x_lo, nxe);
+    if (rc) return rc;
+    const int slab = !(x_lo == 0 && nxe == nx);
+    const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
+    SegList segs;
+    segs.nseg = nseg;
+    int64_t n_total = 0;
+    for (int s = 0; s < nseg; s++) {
+        segs.rec[s] = (const float4 *)records_seg_h[s];
+        segs.starts[s] = tile_starts_seg_h[s];
+        n_total += seg_counts_h ? seg_counts_h[s] : 0;
+    }
+    const int cap = pick_capacity(ctx, n_total, g.ntiles);
+    const size_t smem = deposit_smem_bytes(cap);
+    ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
+    ABK_CHECK_CUDA(cudaFuncSetAttribute(tsc_tile_deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tsc_tile_deposit_kernel<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab);
+    ABK_CHECK_LAUNCH(ctx);
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_deposit_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes)
+{
+    ABK_REQUIRE(bytes && nx > 0 && ny > 0 && nz > 0 && N >= 0, "abk_tsc_deposit_scratch_bytes: bad arguments");
+    const int64_t ntiles = abk_make_geom(nx, ny, nz).ntiles;
+    const int64_t nseg = (N + ((int64_t)1 << 30) - 1) >> 30;
+    size_t b = abk_align_up((size_t)N * 16, 256);                                   // records
+    b += (size_t)(nseg > 0 ? nseg : 1) * abk_align_up((size_t)(ntiles + 1) * 4, 256);  // tile_starts per segment
+    b += abk_scan_tmp_bytes(ntiles) + 256;
+    *bytes = b;
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx, int ny,
+                               int nz, int64_t ldz, double box, double offset, int wrap, void *scratch,
+                               size_t scratch_bytes)
+{
+    ABK_REQUIRE(ctx && grid && (pos || N == 0) && N >= 0, "abk_tsc_deposit: bad arguments");
+    if (N == 0) return ABK_OK;
+    size_t need;
+    int rc = abk_tsc_deposit_scratch_bytes(N, nx, ny, nz, &need);
+    if (rc) return rc;
+    if (scratch_bytes < need) {
+        abk_set_error("abk_tsc_deposit: scratch %zu < %zu", scratch_bytes, need);
+        return ABK_ERR_SCRATCH;
+    }
+    const int64_t ntiles = abk_make_geom(nx, ny, nz).ntiles;
+    const int64_t SEG = (int64_t)1 << 30;
+    const int nseg = (int)((N + SEG - 1) / SEG);
+    ABK_REQUIRE(nseg <= ABK_MAX_SEGMENTS, "N=%lld needs more than %d segments", (long long)N, ABK_MAX_SEGMENTS);
+    char *p = (char *)scratch;
+    float4 *records = (float4 *)p;
+    p += abk_align_up((size_t)N * 16, 256);
+    const void *rec_h[ABK_MAX_SEGMENTS];
+    const uint32_t *starts_h[ABK_MAX_SEGMENTS];
+    int64_t cnt_h[ABK_MAX_SEGMENTS];
+    uint32_t *starts0 = (uint32_t *)p;
+    p += (size_t)nseg * abk_align_up((size_t)(ntiles + 1) * 4, 256);
+    void *scan_tmp = p;
+    const size_t scan_bytes = abk_scan_tmp_bytes(ntiles) + 256;
+    for (int s = 0; s < nseg; s++) {
+        const int64_t b = (int64_t)s * SEG, n = (N - b < SEG) ? N - b : SEG;
+        uint32_t *starts = (uint32_t *)((char *)starts0 + (size_t)s * abk_align_up((size_t)(ntiles + 1) * 4, 256));
+        rc = abk_tsc_bucket(ctx, pos + 3 * b, w ? w + b : nullptr, n, nx, ny, nz, box, offset, wrap, records + b, starts,
+                            scan_tmp, scan_bytes);
+        if (rc) return rc;
+        rec_h[s] = records + b;
+        starts_h[s] = starts;
+        cnt_h[s] = n;
+    }
+    return abk_tsc_deposit_tiles(ctx, nseg, rec_h, starts_h, cnt_h, grid, nx, ny, nz, ldz, box, offset, 0, nx);
+}
+
+extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx,
+                                     int ny, int nz, int64_t ldz, double box, double offset, int wrap)
+{
+    ABK_REQUIRE(ctx && grid && (pos || N == 0) && N >= 0, "abk_tsc_deposit_naive: bad arguments");
+    if (N == 0) return ABK_OK;
+    TscParams P;
+    int rc = make_params(P, nx, ny, nz, box, offset, wrap, 0, nx);
+    if (rc) return rc;
+    tsc_naive_kernel<<<grid_for(ctx, N, 256, 16), 256, 0, ctx->stream>>>(pos, w, N, grid, P, ldz);
+    ABK_CHECK_LAUNCH(ctx);
+    return ABK_OK;
+}

@@ -77,33 +77,42 @@ int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int
 
 /* Particle bucketing for the deposit (replaces the x-stripe partition of tsc.py:178-188 and the
  * two-colour stripe schedule of tsc.py:229-256 `_tsc_parallel`): particles are binned by the
- * (TX x TY x TZ)-cell tile that contains the centre cell of their cloud,
+ * (8 x 8 x 32)-cell tile that contains the centre cell of their cloud,
  *     cell = rint((pos + offset) * f32(n/box)) mod n          (tsc.py:424-433, 387-391)
  * One call buckets one SEGMENT of up to 2^30 particles; several segments (e.g. host->device
  * chunks that arrive one after another) can be bucketed independently and deposited together.
- *   records  : out, float4[N]   (x, y, z, w) in bucket order (w = 1 when `w` is NULL)
- *   tile_ends: out, uint32[ntiles] inclusive scan: tile t owns records [tile_ends[t-1], tile_ends[t])
+ *   records    : out, float4[N]   (x, y, z, w) in bucket order (w = 1 when `w` is NULL)
+ *   tile_starts: out, uint32[ntiles+1] exclusive scan: tile t owns records
+ *                [tile_starts[t], tile_starts[t+1])
  * If `wrap` is non-zero the one-shot periodic wrap (tsc.py:219-226) is applied on the fly to the
  * values that are bucketed (the input array is not modified). */
 int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles);
 int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);
 int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
-                   double box, double offset, int wrap, void *records, uint32_t *tile_ends,
+                   double box, double offset, int wrap, void *records, uint32_t *tile_starts,
                    void *scratch, size_t scratch_bytes);
+/* Slab mode (mesh sharded over GPUs by x-planes): only particles whose centre cell lies in planes
+ * [x_lo, x_lo+nxe) (mod nx) are bucketed; tiles cover that x-range.  The number of particles that
+ * fell outside is returned in *n_dropped_h (host; the call then synchronises the stream). */
+int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
+                        double box, double offset, int wrap, int x_lo, int nxe, void *records,
+                        uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
+                        unsigned long long *n_dropped_h);
 
 /* tsc.py:394-507 `_tsc_scatter` (+ :229-256): 27-point TSC deposit of bucketed particles.
  * One CTA per tile builds per-cell particle lists in shared memory, accumulates each cell's
  * clouds in registers, combines neighbouring cells conflict-free in a shared-memory tile, and
  * flushes the tile (+1-cell halo) to the grid with float reductions.  The grid is accumulated
  * into, never zeroed (tsc.py:45-50).
- *   nseg segments: records_seg[s] / tile_ends_seg[s] as produced by abk_tsc_bucket with the SAME
- *   grid shape, box and offset.
- *   x_lo / nx_local: multi-GPU slab mode.  The grid pointer holds planes x_lo-1 .. x_lo+nx_local
- *   (nx_local+2 planes, the first and last being ghost planes of the neighbouring slabs) when
- *   nx_local < nx; single GPU: x_lo = 0, nx_local = nx and the grid holds exactly nx planes. */
+ *   nseg segments: records_seg_h[s] / tile_starts_seg_h[s] (host arrays of device pointers) as
+ *   produced by abk_tsc_bucket with the SAME grid shape, box and offset; seg_counts_h[s] = N of
+ *   segment s (sizes the shared-memory particle capacity).
+ *   Single GPU: x_lo = 0, nxe = nx, the grid holds nx planes and x wraps periodically.
+ *   Slab mode : the grid holds nxe+2 planes: plane 0 is the ghost plane x_lo-1, planes 1..nxe are
+ *   x_lo..x_lo+nxe-1, plane nxe+1 is the ghost plane x_lo+nxe (no wrap in x). */
 int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
-                          const uint32_t *const *tile_ends_seg_h, float *grid, int nx, int ny, int nz,
-                          int64_t ldz, double box, double offset, int x_lo, int nx_local);
+                          const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h, float *grid,
+                          int nx, int ny, int nz, int64_t ldz, double box, double offset, int x_lo, int nxe);
 
 /* Convenience: bucket one segment and deposit it (what tsc_parallel does for device inputs).
  * scratch must hold abk_tsc_deposit_scratch_bytes(). */
@@ -171,6 +180,10 @@ typedef struct abk_kmesh {
 int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
                          float scale);
 
+/* power_spectrum.py:707-727 `get_raw_power`: out[t] = |f1[t]|^2, or Re(conj(f1[t]) f2[t]) when f2 != NULL,
+ * over `size` complex64 elements (materialised; calc_power itself uses the fused abk_power_bin). */
+int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float *out, int64_t size);
+
 /* Binning request: power_spectrum.py:150-300 `bin_kmu` fused with :707-727 `get_raw_power` and,
  * optionally, with the finishing step above (so calc_power never materialises delta(k) or P(k)).
  *
@@ -188,8 +201,8 @@ int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const v
  * (sum of mult*sqrt(kmag2); multiply by dk on the host), sum_poles f64[Np*Nk]
  * (sum of mult*value*(2l+1)P_l(mu)); the l=0 row is left untouched (the host sets it from sum_p,
  * power_spectrum.py:282-284).
- * pole_coef: float32[Np][ABK_POLE_NCOEF], (2l+1)P_l as a polynomial in mu=sqrt(mu2) (host-built
- * from power_spectrum.py:121-147); pole_ell int32[Np]. */
+ * pole_coef: device float32[Np][ABK_POLE_NCOEF], (2l+1)P_l as a polynomial in mu=sqrt(mu2) (host-built
+ * from power_spectrum.py:121-147); pole_ell: the Np multipole orders, stored in the request. */
 typedef struct abk_bin_request {
     abk_kmesh mesh;
     const void *f1, *f1s, *f2, *f2s; /* complex64 meshes (fs: half-cell-shifted grids) */
@@ -201,7 +214,7 @@ typedef struct abk_bin_request {
     const float *muedges2; /* float32[Nmu+1], device */
     int32_t Nk, Nmu, Np;
     const float *pole_coef; /* device */
-    const int32_t *pole_ell; /* device */
+    int32_t pole_ell[ABK_MAX_POLES];
     unsigned long long *counts;
     double *sum_p, *sum_k, *sum_poles;
 } abk_bin_request;
@@ -215,13 +228,11 @@ int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_t nplanes, 
                    int64_t ldz);
 /* Slab->pencil transpose, pack side: from the local slab [nxl][ny][nzc] (complex64) gather, for
  * every destination rank r, the block [nxl][j in rank r's y-range][nzc] contiguously into
- * sendbuf at offset send_off_h[r] (elements).  y-ranges are given by jsplit_h[nranks+1]. */
+ * sendbuf at element offset nxl*jsplit_h[r]*nzc.  y-ranges are given by jsplit_h[nranks+1] (host).
+ * No unpack kernel is needed: if rank r's block is received at element offset
+ * isplit[r]*nyl*nzc, the receive buffer IS the pencil layout [nx][nyl][nzc]. */
 int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf, int64_t nxl, int64_t ny, int64_t nzc,
                        int nranks, const int64_t *jsplit_h);
-/* unpack side: recvbuf holds, for every source rank r, [nxl_r][nyl][nzc]; scatter into the local
- * pencil layout [nx][nyl][nzc] at x offset isplit_h[r]. */
-int abk_transpose_unpack(abk_ctx *ctx, const void *recvbuf, void *pencil, int64_t nx, int64_t nyl,
-                         int64_t nzc, int nranks, const int64_t *isplit_h);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,207 @@
+"""
+GPU parity of the TSC deposit (abk_tsc.cu through the C ABI / the tsc_parallel shim) against
+  * the reference's analytic single-particle KAT (tests/test_tsc.py:25-90),
+  * the reference's own golden grids (tests/ref_tsc/*.asdf, committed as tests/golden/ref_tsc_*.npz),
+  * grids produced by the unmodified reference (tests/golden/reference_runs.npz),
+  * the CPU oracle on seeded inputs, incl. edge cases (empty input, tiny/odd/anisotropic grids,
+    unwrapped positions, positions exactly on cell edges and at the box edge, clustered input that
+    overflows a tile's shared-memory capacity, accumulation into an existing grid).
+Float32 grids: tolerance rtol=1e-4, atol=1e-5 of the reference's own test (tests/test_tsc.py:137).
+"""
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def tsc():
+    from abacusutils_b200.analysis import tsc as m
+
+    return m
+
+
+@pytest.mark.parametrize('ngrid', [10, 256])
+@pytest.mark.parametrize('dtype', ['f4', 'f8'])
+@pytest.mark.filterwarnings('ignore:.*dtype')
+def test_single(tsc, ngrid, dtype):
+    box = 123.0
+    cen = np.array([5, 6, 7])
+    single = (cen / ngrid * box).astype(dtype).reshape(1, -1)
+    dens = tsc.tsc_parallel(single, ngrid, box)
+    assert (dens == 0).sum() == ngrid**3 - 27
+    assert np.isclose(dens.sum(), 1.0)
+    cube = dens[cen[0] - 1:cen[0] + 2, cen[1] - 1:cen[1] + 2, cen[2] - 1:cen[2] + 2]
+    ncen = (np.indices((3, 3, 3)) == 1).sum(axis=0)
+    assert np.allclose(cube[ncen == 0], 0.5**9)
+    assert np.allclose(cube[ncen == 1], 0.5**6 * 0.75)
+    assert np.allclose(cube[ncen == 2], 0.5**3 * 0.75**2)
+    assert np.allclose(cube[ncen == 3], 0.75**3)
+
+
+@pytest.mark.parametrize('dtype', ['f4', 'f8'])
+@pytest.mark.filterwarnings('ignore:.*dtype')
+def test_multi_reference_golden_ngrid10(tsc, dtype):
+    pos, weights, box = cases.ref_tsc_inputs(dtype)
+    g = np.load(cases.__file__.replace('cases.py', 'ref_tsc_ngrid10.npz'))
+    dens = tsc.tsc_parallel(pos, 10, box, weights=weights)
+    assert np.isclose(dens.sum(dtype='f8'), weights.sum(dtype='f8'))
+    assert np.allclose(dens, g['pydens'], rtol=1e-4, atol=1e-5)
+    assert np.allclose(dens, g['nbodykit'], rtol=1e-4, atol=1e-5)
+
+
+def test_multi_reference_golden_ngrid256(tsc):
+    pos, weights, box = cases.ref_tsc_inputs()
+    g = np.load(cases.__file__.replace('cases.py', 'ref_tsc_ngrid256.npz'))
+    dens = tsc.tsc_parallel(pos, 256, box, weights=weights)
+    assert np.isclose(dens.sum(dtype='f8'), weights.sum(dtype='f8'))
+    assert np.isclose((dens.astype('f8') ** 2).sum(), float(g['own_sumsq']), rtol=1e-5)
+    assert (dens != 0).sum() == int(g['own_nnz'])
+    assert np.allclose(dens.sum(axis=(1, 2), dtype='f8'), g['own_xsum'], rtol=1e-5, atol=1e-5)
+    sub = dens[g['planes']].reshape(-1)
+    for tag in ('own', 'nbk'):
+        want = np.zeros_like(sub)
+        want[g[f'{tag}_idx']] = g[f'{tag}_val']
+        assert np.allclose(sub, want, rtol=1e-4, atol=1e-5), tag
+
+
+@pytest.mark.parametrize('name', list(cases.TSC_CASES))
+def test_vs_reference_runs(tsc, golden, oracle, name):
+    c = cases.TSC_CASES[name]
+    pos, w = cases.tsc_inputs(c)
+    want = golden[f'tsc/{name}']
+    dens = np.zeros(c['shape'], dtype=np.float32)
+    p = pos.copy()
+    assert tsc.tsc_parallel(p, dens, c['box'], weights=w, offset=c['offset']) is None
+    assert np.allclose(dens, want, rtol=1e-4, atol=1e-5)
+    # wrapped in place exactly like the reference / oracle
+    p2 = pos.copy()
+    d2 = np.zeros(c['shape'], dtype=np.float32)
+    oracle.tsc_parallel(p2, d2, c['box'], weights=w, nthread=1, offset=c['offset'])
+    np.testing.assert_array_equal(p, p2)
+    assert np.allclose(dens, d2, rtol=1e-5, atol=2e-6)
+
+
+def test_tile_and_naive_kernels_agree(tsc, oracle):
+    """abk_tsc_deposit (tiles) vs abk_tsc_deposit_naive (27 reductions per particle) vs oracle."""
+    import ctypes as C
+
+    import torch
+
+    from abacusutils_b200._lib import Engine, check, ptr
+
+    rng = np.random.default_rng(5)
+    N, box, shape = 200000, 500.0, (72, 40, 100)
+    pos = rng.random((N, 3), dtype='f4') * np.float32(box)
+    w = rng.random(N, dtype='f4')
+    eng = Engine.get()
+    eng.bind_stream()
+    pd, wd = eng.to_device(pos), eng.to_device(w)
+    g1 = eng.zeros(shape, torch.float32)
+    check(eng.lib.abk_tsc_deposit_naive(eng.ctx, ptr(pd), ptr(wd), N, ptr(g1), *shape, shape[2], box, 1.7, 1))
+    g2 = tsc.tsc_parallel(pd, shape, box, weights=wd, offset=1.7)
+    ref = np.zeros(shape, dtype=np.float32)
+    oracle.tsc_scatter_serial(pos, ref, box, weights=w, offset=1.7)
+    assert np.allclose(g1.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    assert np.allclose(g2.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    _ = C
+
+
+def test_edge_positions(tsc, oracle):
+    """Particles exactly on cell centres, cell edges (round-half-even), 0, and the largest float below box."""
+    box, n = 64.0, 16
+    h = box / n
+    vals = np.array([0.0, h / 2, h, 1.5 * h, 2.5 * h, box - h / 2, np.nextafter(np.float32(box), np.float32(0)),
+                     box - h, 7.5 * h, 8.5 * h], dtype=np.float32)
+    pos = np.stack(np.meshgrid(vals, vals, vals, indexing='ij'), axis=-1).reshape(-1, 3).astype(np.float32)
+    for off in (0.0, 0.5 * h):
+        got = tsc.tsc_parallel(pos.copy(), n, box, offset=off)
+        ref = np.zeros((n, n, n), dtype=np.float32)
+        oracle.tsc_scatter_serial(pos, ref, box, offset=off)
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-6), off
+        assert np.isclose(got.sum(dtype='f8'), len(pos))
+
+
+def test_empty_and_tiny(tsc):
+    dens = tsc.tsc_parallel(np.zeros((0, 3), dtype=np.float32), 8, 1.0)
+    assert dens.shape == (8, 8, 8) and not dens.any()
+    for n in (1, 2, 3, 5):
+        pos = np.random.default_rng(n).random((50, 3), dtype='f4')
+        dens = tsc.tsc_parallel(pos, n, 1.0)
+        assert np.isclose(dens.sum(dtype='f8'), 50.0)
+
+
+def test_clustered_overflows_tile_capacity(tsc, oracle):
+    """All particles inside one tile: many shared-memory passes per tile, heavy per-cell lists."""
+    rng = np.random.default_rng(77)
+    N, box, n = 300000, 100.0, 64
+    pos = (rng.normal(50.0, 0.6, (N, 3))).astype(np.float32)
+    pos[: N // 3] = np.float32(50.2)  # a third of them on one point
+    w = rng.random(N, dtype='f4')
+    got = tsc.tsc_parallel(pos.copy(), n, box, weights=w)
+    ref = np.zeros((n, n, n), dtype=np.float32)
+    oracle.tsc_parallel(pos.copy(), ref, box, weights=w, nthread=1)
+    assert np.isclose(got.sum(dtype='f8'), w.sum(dtype='f8'), rtol=1e-6)
+    # ~1e5 float32 terms land in single cells: the serial float32 sums of oracle and GPU differ by
+    # summation order at the sqrt(N)*eps..N*eps level, far above the 1e-4 of well-conditioned cells
+    assert np.allclose(got, ref, rtol=2e-3, atol=1e-6 * ref.max())
+
+
+def test_accumulates_and_returns(tsc):
+    rng = np.random.default_rng(123)
+    box, ngrid = 123.0, 10
+    pos = rng.random((100, 3), dtype='f4') * box
+    dens = tsc.tsc_parallel(pos, ngrid, box)
+    assert dens.shape == (ngrid, ngrid, ngrid) and dens.dtype == np.float32
+    pre = np.full((ngrid, ngrid, ngrid), 2.0, dtype=np.float32)
+    assert tsc.tsc_parallel(pos, pre, box) is None
+    np.testing.assert_allclose(pre, dens + 2.0, rtol=1e-6)
+    # tuple shape and device tensors
+    import torch
+
+    d2 = tsc.tsc_parallel(torch.from_numpy(pos).cuda(), (10, 10, 10), box)
+    assert d2.is_cuda
+    np.testing.assert_allclose(d2.cpu().numpy(), dens, rtol=1e-6, atol=1e-7)
+    g = torch.zeros((10, 10, 10), device='cuda')
+    assert tsc.tsc_parallel(torch.from_numpy(pos).cuda(), g, box) is None
+    np.testing.assert_allclose(g.cpu().numpy(), dens, rtol=1e-6, atol=1e-7)
+
+
+def test_npartition_errors(tsc):
+    pos = np.zeros((4, 3), dtype=np.float32)
+    with pytest.raises(ValueError):
+        tsc.tsc_parallel(pos, 30, 1.0, nthread=4, npartition=14)  # > n//3 and != n//2
+    with pytest.raises(ValueError):
+        tsc.tsc_parallel(pos, 30, 1.0, nthread=4, npartition=9)  # odd
+    tsc.tsc_parallel(pos, 32, 1.0, nthread=4, npartition=16)  # == n//2 is allowed (tsc.py:141)
+
+
+@pytest.mark.parametrize('seed', [123, 456])
+@pytest.mark.parametrize('npartition', [1, 16, 1000])
+@pytest.mark.parametrize('sort', [False, True])
+def test_partition(tsc, seed, npartition, sort):
+    """tests/test_tsc.py:162-208 of the reference, plus sort=True."""
+    rng = np.random.default_rng(seed)
+    box, N, coord = 123.0, 10000, 0
+    pos = rng.random((N, 3), dtype='f4') * box
+    weights = rng.random((N,), dtype='f4')
+    ppart, starts, wpart = tsc.partition_parallel(pos, npartition, box, weights=weights, coord=coord, sort=sort)
+    keys = (pos[:, coord] * np.float32(npartition / box)).astype(np.int32)
+    keys = np.minimum(keys, npartition - 1)
+    iord = keys.argsort(kind='stable')
+    spos, sw = pos[iord], weights[iord]
+    np_starts = np.r_[0, np.bincount(keys, minlength=npartition).cumsum()].astype(np.int64)
+    assert starts.dtype == np.int64 and np.array_equal(np_starts, starts)
+    for i in range(npartition):
+        a, b = starts[i], starts[i + 1]
+        # same multiset of (pos, weight) rows per stripe
+        got = np.c_[ppart[a:b], wpart[a:b]]
+        want = np.c_[spos[a:b], sw[a:b]]
+        got = got[np.lexsort(got.T[::-1])]
+        want = want[np.lexsort(want.T[::-1])]
+        assert np.array_equal(got, want)
+        if sort:
+            assert np.all(np.diff(ppart[a:b, coord]) >= 0)
