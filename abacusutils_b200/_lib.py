@@ -53,6 +53,10 @@ SIGNATURES = {
     'abk_ctx_sync': (_i32, [_vp]),
     'abk_ctx_launch_count': (_i64, [_vp]),
     'abk_ctx_set_tile_capacity': (_i32, [_vp, _i32]),
+    'abk_ctx_profile_enable': (_i32, [_vp, _i32]),
+    'abk_ctx_profile_collect': (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    'abk_kernel_count': (_i32, []),
+    'abk_kernel_name': (C.c_char_p, [_i32]),
     'abk_wrap_inplace': (_i32, [_vp, _vp, _i64, _dbl, _vp]),
     'abk_partition_scratch_bytes': (_i32, [_i64, _i32, _psz]),
     'abk_partition': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _sz]),
@@ -157,6 +161,18 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.abk_ctx_launch_count(self.ctx))
+
+    def profile(self, on):
+        check(self.lib.abk_ctx_profile_enable(self.ctx, int(bool(on))))
+
+    def profile_collect(self):
+        """{kernel name: (total ms, launches)} since the last collect (synchronises the stream)."""
+        nk = self.lib.abk_kernel_count()
+        ms = (C.c_double * nk)()
+        cnt = (C.c_int64 * nk)()
+        self.bind_stream()
+        check(self.lib.abk_ctx_profile_collect(self.ctx, ms, cnt))
+        return {self.lib.abk_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(nk) if cnt[i]}
 
     def empty(self, shape, dtype):
         return _torch().empty(shape, dtype=dtype, device=self.device)

@@ -7,6 +7,32 @@
 
 #include "abk.h"
 
+// kernel ids for the optional per-kernel CUDA-event timing (abk_ctx_profile_*)
+enum abk_kernel_id {
+    ABK_K_WRAP = 0,
+    ABK_K_PART_HIST,
+    ABK_K_PART_SCATTER,
+    ABK_K_SCAN,
+    ABK_K_BUCKET_HIST,
+    ABK_K_BUCKET_SCATTER,
+    ABK_K_TILE_DEPOSIT,
+    ABK_K_NAIVE_DEPOSIT,
+    ABK_K_NORMALIZE,
+    ABK_K_FFT,
+    ABK_K_FINISH,
+    ABK_K_RAW_POWER,
+    ABK_K_POWER_BIN,
+    ABK_K_ADD_PLANES,
+    ABK_K_TRANSPOSE_PACK,
+    ABK_K_MISC,
+    ABK_K_COUNT
+};
+
+struct abk_prof_rec {
+    int id;
+    cudaEvent_t a, b;
+};
+
 struct abk_ctx {
     int device;
     cudaStream_t stream;
@@ -16,7 +42,25 @@ struct abk_ctx {
     int tile_capacity;  // 0 = auto
     // small device scratch owned by the context (work counters, flags)
     unsigned long long *d_scalars;
+    // profiling state
+    int prof_on;
+    abk_prof_rec *prof_recs;
+    int prof_n, prof_cap;
+    cudaEvent_t *prof_pool;
+    int prof_pool_n, prof_pool_cap;
 };
+
+void abk_prof_begin(abk_ctx *ctx, int id);
+void abk_prof_end(abk_ctx *ctx);
+
+// launch wrapper: optional event pair around the launch, launch counter, error check
+#define ABK_LAUNCH(ctx, id, ...)                 \
+    do {                                         \
+        if ((ctx)->prof_on) abk_prof_begin((ctx), (id)); \
+        __VA_ARGS__;                             \
+        if ((ctx)->prof_on) abk_prof_end((ctx)); \
+        ABK_CHECK_LAUNCH(ctx);                   \
+    } while (0)
 
 void abk_set_error(const char *fmt, ...);
 

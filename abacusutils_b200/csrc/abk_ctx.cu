@@ -1,5 +1,6 @@
 // Context, error reporting and small device utilities of libabk.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "abk_common.cuh"
@@ -39,6 +40,11 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->launches = 0;
     c->tile_capacity = 0;
     c->d_scalars = nullptr;
+    c->prof_on = 0;
+    c->prof_recs = nullptr;
+    c->prof_n = c->prof_cap = 0;
+    c->prof_pool = nullptr;
+    c->prof_pool_n = c->prof_pool_cap = 0;
     ABK_CHECK_CUDA(cudaMalloc(&c->d_scalars, 64 * sizeof(unsigned long long)));
     ABK_CHECK_CUDA(cudaMemset(c->d_scalars, 0, 64 * sizeof(unsigned long long)));
     *out = c;
@@ -51,6 +57,74 @@ extern "C" int abk_ctx_destroy(abk_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     delete ctx;
+    return ABK_OK;
+}
+
+// ---- per-kernel timing with CUDA events on the launch stream ------------------------------------
+static const char *const k_names[ABK_K_COUNT] = {
+    "wrap_inplace", "partition_hist", "partition_scatter", "scan", "tsc_bucket_hist", "tsc_bucket_scatter",
+    "tsc_tile_deposit", "tsc_naive_deposit", "normalize_field", "cufft", "field_fft_finish", "raw_power",
+    "power_bin", "add_planes", "transpose_pack", "misc"};
+
+static cudaEvent_t prof_get_event(abk_ctx *ctx)
+{
+    if (ctx->prof_pool_n > 0) return ctx->prof_pool[--ctx->prof_pool_n];
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void abk_prof_begin(abk_ctx *ctx, int id)
+{
+    if (ctx->prof_n == ctx->prof_cap) {
+        const int cap = ctx->prof_cap ? 2 * ctx->prof_cap : 256;
+        ctx->prof_recs = (abk_prof_rec *)realloc(ctx->prof_recs, sizeof(abk_prof_rec) * cap);
+        ctx->prof_cap = cap;
+    }
+    abk_prof_rec &r = ctx->prof_recs[ctx->prof_n++];
+    r.id = id;
+    r.a = prof_get_event(ctx);
+    r.b = prof_get_event(ctx);
+    cudaEventRecord(r.a, ctx->stream);
+}
+
+void abk_prof_end(abk_ctx *ctx)
+{
+    cudaEventRecord(ctx->prof_recs[ctx->prof_n - 1].b, ctx->stream);
+}
+
+extern "C" int abk_ctx_profile_enable(abk_ctx *ctx, int on)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ctx->prof_on = on ? 1 : 0;
+    return ABK_OK;
+}
+
+extern "C" int abk_kernel_count(void) { return ABK_K_COUNT; }
+extern "C" const char *abk_kernel_name(int id) { return (id >= 0 && id < ABK_K_COUNT) ? k_names[id] : ""; }
+
+// Synchronises the stream, adds the elapsed time of every recorded launch to ms_h[id] and its
+// count to n_h[id] (arrays of abk_kernel_count() entries, NOT zeroed here), and clears the records.
+extern "C" int abk_ctx_profile_collect(abk_ctx *ctx, double *ms_h, int64_t *n_h)
+{
+    ABK_REQUIRE(ctx && ms_h && n_h, "abk_ctx_profile_collect: null argument");
+    ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->prof_n; i++) {
+        abk_prof_rec &r = ctx->prof_recs[i];
+        float ms = 0.0f;
+        ABK_CHECK_CUDA(cudaEventSynchronize(r.b));
+        ABK_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_h[r.id] += ms;
+        n_h[r.id] += 1;
+        if (ctx->prof_pool_n + 2 > ctx->prof_pool_cap) {
+            const int cap = ctx->prof_pool_cap ? 2 * ctx->prof_pool_cap : 512;
+            ctx->prof_pool = (cudaEvent_t *)realloc(ctx->prof_pool, sizeof(cudaEvent_t) * cap);
+            ctx->prof_pool_cap = cap;
+        }
+        ctx->prof_pool[ctx->prof_pool_n++] = r.a;
+        ctx->prof_pool[ctx->prof_pool_n++] = r.b;
+    }
+    ctx->prof_n = 0;
     return ABK_OK;
 }
 
@@ -153,14 +227,12 @@ int abk_inclusive_scan_u32(abk_ctx *ctx, uint32_t *data, int64_t n, void *tmp)
     if (n <= 0) return ABK_OK;
     const int64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     uint32_t *sums = (nblocks > 1) ? (uint32_t *)tmp : nullptr;
-    scan_block_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_SCAN, scan_block_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums));
     if (nblocks > 1) {
         char *next = (char *)tmp + abk_align_up((size_t)nblocks * sizeof(uint32_t), 256);
         int rc = abk_inclusive_scan_u32(ctx, sums, nblocks, next);
         if (rc) return rc;
-        scan_add_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums);
-        ABK_CHECK_LAUNCH(ctx);
+        ABK_LAUNCH(ctx, ABK_K_SCAN, scan_add_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, ctx->stream>>>(data, n, sums));
     }
     return ABK_OK;
 }

@@ -118,7 +118,9 @@ extern "C" int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, voi
     ABK_REQUIRE(ctx && plan && plan->kind == 0, "abk_rfft3_exec: not a 3-D plan");
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;
+    if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
     ABK_CHECK_CUFFT(cufftExecR2C(plan->fwd, (cufftReal *)grid, (cufftComplex *)grid));
+    if (ctx->prof_on) abk_prof_end(ctx);
     ctx->launches += 1;  // cuFFT launches several kernels; counted as one library call
     return ABK_OK;
 }
@@ -153,8 +155,10 @@ extern "C" int abk_fft_exec_generic(abk_ctx *ctx, abk_fft_plan *plan, void *data
     ABK_REQUIRE(ctx && plan, "abk_fft_exec_generic: null argument");
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;
+    if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
     if (plan->kind == 2) ABK_CHECK_CUFFT(cufftExecC2C(plan->fwd, (cufftComplex *)data, (cufftComplex *)data, CUFFT_FORWARD));
     else ABK_CHECK_CUFFT(cufftExecR2C(plan->fwd, (cufftReal *)data, (cufftComplex *)data));
+    if (ctx->prof_on) abk_prof_end(ctx);
     ctx->launches += 1;
     return ABK_OK;
 }

@@ -357,12 +357,13 @@ extern "C" int abk_normalize_field(abk_ctx *ctx, float *grid, int64_t nx, int64_
     const float norm = (float)(size_total / tot_weight);  // power_spectrum.py:893
     const int64_t nrows = nx * ny;
     if ((ldz % 2 == 0) && (((uintptr_t)grid & 7) == 0)) {
-        normalize_kernel_v2<<<grid_for(ctx, nrows * (ldz / 2), 256, 16), 256, 0, ctx->stream>>>((float2 *)grid, nrows, nz,
-                                                                                                ldz / 2, norm);
+        ABK_LAUNCH(ctx, ABK_K_NORMALIZE,
+                   normalize_kernel_v2<<<grid_for(ctx, nrows * (ldz / 2), 256, 16), 256, 0, ctx->stream>>>(
+                       (float2 *)grid, nrows, nz, ldz / 2, norm));
     } else {
-        normalize_kernel<<<grid_for(ctx, nrows * ldz, 256, 16), 256, 0, ctx->stream>>>(grid, nrows, nz, ldz, norm);
+        ABK_LAUNCH(ctx, ABK_K_NORMALIZE,
+                   normalize_kernel<<<grid_for(ctx, nrows * ldz, 256, 16), 256, 0, ctx->stream>>>(grid, nrows, nz, ldz, norm));
     }
-    ABK_CHECK_LAUNCH(ctx);
     return ABK_OK;
 }
 
@@ -380,8 +381,8 @@ extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void 
     F.inv_n = 1.0f / (float)mesh_h->n;
     const int64_t nrows = (int64_t)(mesh_h->i1 - mesh_h->i0) * (mesh_h->j1 - mesh_h->j0);
     if (nrows == 0) return ABK_OK;
-    finish_kernel<<<grid_for(ctx, nrows * 32, 256, 8), 256, 0, ctx->stream>>>((float2 *)f, F, *mesh_h);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_FINISH,
+               finish_kernel<<<grid_for(ctx, nrows * 32, 256, 8), 256, 0, ctx->stream>>>((float2 *)f, F, *mesh_h));
     return ABK_OK;
 }
 
@@ -389,8 +390,7 @@ extern "C" int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float
 {
     ABK_REQUIRE(ctx && f1 && out && size >= 0, "abk_raw_power: bad arguments");
     if (size == 0) return ABK_OK;
-    raw_power_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>((const float2 *)f1, (const float2 *)f2, out, size);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_RAW_POWER, raw_power_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>((const float2 *)f1, (const float2 *)f2, out, size));
     return ABK_OK;
 }
 
@@ -450,14 +450,13 @@ extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
         ABK_CHECK_CUDA(cudaFuncSetAttribute(power_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int64_t blocks = (nrows + warps - 1) / warps;
         if (blocks > ctx->num_sms) blocks = ctx->num_sms;
-        power_bin_kernel<true><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(A);
+        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, power_bin_kernel<true><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(A));
     } else {
         ABK_CHECK_CUDA(cudaFuncSetAttribute(power_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hdr_bytes));
         int64_t blocks = (nrows + 15) / 16;
         if (blocks > (int64_t)ctx->num_sms * 2) blocks = (int64_t)ctx->num_sms * 2;
-        power_bin_kernel<false><<<(unsigned)blocks, 512, hdr_bytes, ctx->stream>>>(A);
+        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, power_bin_kernel<false><<<(unsigned)blocks, 512, hdr_bytes, ctx->stream>>>(A));
     }
-    ABK_CHECK_LAUNCH(ctx);
     return ABK_OK;
 }
 
@@ -466,8 +465,8 @@ extern "C" int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_
 {
     ABK_REQUIRE(ctx && dst && src && nplanes >= 0 && ny > 0 && nz > 0 && ldz >= nz, "abk_add_planes: bad arguments");
     if (nplanes == 0) return ABK_OK;
-    add_planes_kernel<<<grid_for(ctx, nplanes * ny * ldz, 256, 16), 256, 0, ctx->stream>>>(dst, src, nplanes * ny, nz, ldz);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_ADD_PLANES,
+               add_planes_kernel<<<grid_for(ctx, nplanes * ny * ldz, 256, 16), 256, 0, ctx->stream>>>(dst, src, nplanes * ny, nz, ldz));
     return ABK_OK;
 }
 
@@ -480,8 +479,7 @@ extern "C" int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf,
     if (nxl == 0) return ABK_OK;
     SplitTable js;
     for (int r = 0; r <= nranks; r++) js.v[r] = jsplit_h[r];
-    transpose_pack_kernel<<<grid_for(ctx, nxl * ny * 32, 256, 8), 256, 0, ctx->stream>>>(
-        (const float2 *)slab, (float2 *)sendbuf, nxl, ny, nzc, nranks, js);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_TRANSPOSE_PACK, transpose_pack_kernel<<<grid_for(ctx, nxl * ny * 32, 256, 8), 256, 0, ctx->stream>>>(
+        (const float2 *)slab, (float2 *)sendbuf, nxl, ny, nzc, nranks, js));
     return ABK_OK;
 }

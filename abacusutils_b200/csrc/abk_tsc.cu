@@ -380,9 +380,8 @@ extern "C" int abk_wrap_inplace(abk_ctx *ctx, float *pos, int64_t N, double box,
 {
     ABK_REQUIRE(ctx && (pos || N == 0) && N >= 0, "abk_wrap_inplace: bad arguments");
     if (N == 0) return ABK_OK;
-    wrap_inplace_kernel<<<grid_for(ctx, 3 * N, 256, 16), 256, 0, ctx->stream>>>(pos, 3 * N, box,
-                                                                                 (unsigned long long *)n_changed_dev);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_WRAP, wrap_inplace_kernel<<<grid_for(ctx, 3 * N, 256, 16), 256, 0, ctx->stream>>>(pos, 3 * N, box,
+                                                                                 (unsigned long long *)n_changed_dev));
     return ABK_OK;
 }
 
@@ -411,15 +410,12 @@ extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int
     const float inv_pwidth = (float)((double)npart / box);
     if (N > 0) {
         const int blocks = grid_for(ctx, N, 256, 16);
-        partition_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, nullptr, nullptr);
-        ABK_CHECK_LAUNCH(ctx);
+        ABK_LAUNCH(ctx, ABK_K_PART_HIST, partition_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, nullptr, nullptr));
         int rc = abk_inclusive_scan_u32(ctx, counts, npart, tmp);
         if (rc) return rc;
-        partition_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, out_pos, out_w);
-        ABK_CHECK_LAUNCH(ctx);
+        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, partition_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, out_pos, out_w));
     }
-    starts_to_i64_kernel<<<(npart + 256) / 256, 256, 0, ctx->stream>>>(counts, npart, N, out_starts);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_MISC, starts_to_i64_kernel<<<(npart + 256) / 256, 256, 0, ctx->stream>>>(counts, npart, N, out_starts));
     return ABK_OK;
 }
 
@@ -453,15 +449,13 @@ static int bucket_impl(abk_ctx *ctx, const float *pos, const float *w, int64_t N
     if (N > 0) {
         const int vec_ok = (((uintptr_t)pos & 15) == 0) && (!w || ((uintptr_t)w & 15) == 0);
         const int blocks = grid_for(ctx, (N + 3) / 4, 256, 16);
-        tsc_bucket_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped);
-        ABK_CHECK_LAUNCH(ctx);
+        ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped));
         int rc = abk_inclusive_scan_u32(ctx, tile_starts, g.ntiles, scratch);
         if (rc) return rc;
         // sentinel tile_starts[ntiles] = number of bucketed particles = inclusive total
         ABK_CHECK_CUDA(cudaMemcpyAsync(tile_starts + g.ntiles, tile_starts + g.ntiles - 1, 4, cudaMemcpyDeviceToDevice,
                                        ctx->stream));
-        tsc_bucket_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped);
-        ABK_CHECK_LAUNCH(ctx);
+        ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, tsc_bucket_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped));
     }
     return ABK_OK;
 }
@@ -532,8 +526,7 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     const size_t smem = deposit_smem_bytes(cap);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
     ABK_CHECK_CUDA(cudaFuncSetAttribute(tsc_tile_deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tsc_tile_deposit_kernel<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, tsc_tile_deposit_kernel<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
     return ABK_OK;
 }
 
@@ -597,7 +590,6 @@ extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float
     TscParams P;
     int rc = make_params(P, nx, ny, nz, box, offset, wrap, 0, nx);
     if (rc) return rc;
-    tsc_naive_kernel<<<grid_for(ctx, N, 256, 16), 256, 0, ctx->stream>>>(pos, w, N, grid, P, ldz);
-    ABK_CHECK_LAUNCH(ctx);
+    ABK_LAUNCH(ctx, ABK_K_NAIVE_DEPOSIT, tsc_naive_kernel<<<grid_for(ctx, N, 256, 16), 256, 0, ctx->stream>>>(pos, w, N, grid, P, ldz));
     return ABK_OK;
 }

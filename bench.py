@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the B200 density-field power-spectrum path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+    calc_power on 1e9 uniform random particles, Lbox=2000, nmesh=1024, TSC, compensated + interlaced,
+    100 linear k bins to k_Nyquist x 10 mu bins, poles 0/2/4.
+A "step" is one full calc_power pass.  `value` times it with the particles already resident in
+HBM; `e2e` times the same public call (abacusutils_b200.analysis.power_spectrum.calc_power) with the
+particles in pinned HOST memory, so the host->device copies and the device->host read of the
+binned result are inside the timed region.  Per-kernel times come from CUDA events recorded by
+libabk on its launch stream inside the timed region (abk_ctx_profile_*).
+
+--impl reference times the CPU implementation of the same path (the oracle port of the reference's
+Numba kernels, C + OpenMP on all host threads + scipy.fft) on a bounded sample of the same
+workload and reports the extrapolated full-workload number.  The unmodified reference cannot travel
+to the GPU box (pure-Python package living under /root/reference, no wheel), see DESIGN.md.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'calc_power ms (1e9 part, nmesh 1024)'
+CFG = dict(N=1_000_000_000, L=2000.0, nmesh=1024, kbins=100, mubins=10, poles=[0, 2, 4], seed=3)
+WORKLOAD = ('configs[2]: calc_power, 1e9 uniform random particles, Lbox=2000, nmesh=1024, TSC, compensated + '
+            'interlaced, 100 k x 10 mu bins, poles 0/2/4')
+
+
+def peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        # "under load": samples in the upper half of the power range seen
+        thr = 0.5 * (max(pw) + min(pw)) if pw else 0
+        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        return {'sm_mhz': float(np.median(load)), 'sm_max_mhz': float(max(smax)), 'reasons': sorted(reasons),
+                'samples': len(sm), 'power_w_max': max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(level, cfg, nthread=None):
+    """Run the CPU oracle on 1/8^level of the workload volume at equal particle density and identical
+    options (nmesh/2^level, N/8^level, L/2^level); returns (seconds, description)."""
+    from oracle import abk_oracle as O
+
+    O.build()
+    f = 2**level
+    nmesh = cfg['nmesh'] // f
+    N = cfg['N'] // f**3
+    L = cfg['L'] / f
+    rng = np.random.default_rng(cfg['seed'])
+    pos = rng.random((N, 3), dtype=np.float32) * np.float32(L)
+    nt = nthread or O.MAX_THREADS
+    t0 = time.perf_counter()
+    O.calc_power(pos, L, kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=nmesh, compensated=True, interlaced=True,
+                 poles=cfg['poles'], nthread=nt)
+    dt = time.perf_counter() - t0
+    return dt, f'1/{f**3} of the volume at equal density: N={N}, nmesh={nmesh}, L={L:g}, same options; time x {f**3}', nt
+
+
+def pick_cpu_level(cfg, budget_s):
+    """Largest sample (smallest level) whose estimated time fits the budget, from a quick calibration."""
+    max_level = 0
+    while cfg['nmesh'] // 2**(max_level + 1) >= 64:
+        max_level += 1
+    cal_level = max(max_level, 0)
+    dt, _, _ = cpu_sample(cal_level, cfg)  # also warms page cache / OpenMP
+    dt, _, _ = cpu_sample(cal_level, cfg)
+    level = cal_level
+    while level > 1 and dt * 8 ** (cal_level - (level - 1)) <= budget_s:
+        level -= 1
+    return level
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cfg = dict(CFG)
+    if args.nparticles:
+        cfg['N'] = args.nparticles
+    if args.nmesh:
+        cfg['nmesh'] = args.nmesh
+    nsteps = args.steps + args.warmup
+    budget = min(30.0, 200.0 / max(nsteps, 1))
+    level = pick_cpu_level(cfg, budget)
+    times = []
+    desc = ''
+    nt = 1
+    for i in range(nsteps):
+        dt, desc, nt = cpu_sample(level, cfg)
+        if i >= args.warmup:
+            times.append(dt)
+    scale = 8**level
+    ms_full = float(np.mean(times)) * scale * 1e3
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': ms_full, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_full, 'higher_is_better': False, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD if not (args.nparticles or args.nmesh) else f'override N={cfg["N"]} nmesh={cfg["nmesh"]}'},
+        'cpu_baseline': {'value': ms_full, 'unit': 'ms', 'cores': nt, 'kind': 'port', 'sample': desc,
+                         'sample_seconds': float(np.mean(times))},
+        'e2e': {'value': ms_full, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'mpart_per_s': cfg['N'] / ms_full / 1e3,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(name, cfg, nseg, n_used_entries):
+    """Algorithmic bytes PER LAUNCH of each kernel (DESIGN.md 'Kernels and rooflines')."""
+    N, n = cfg['N'], cfg['nmesh']
+    nzc = n // 2 + 1
+    w = 0
+    return {
+        'tsc_bucket_hist': N / nseg * 12,
+        'tsc_bucket_scatter': N / nseg * (12 + 4 * w + 16),
+        'tsc_tile_deposit': N * 16 + 4 * n**3,
+        'normalize_field': 8 * n**3,
+        'cufft': 4 * n**3 + 8 * n * n * nzc,
+        'power_bin': n_used_entries * 8 * 2,
+    }.get(name)
+
+
+def used_entries(n, L, kmax):
+    """Number of (i,j,k) mesh entries with 0 <= |k| < k_max (what the binning kernel must read)."""
+    dk = 2 * np.pi / L
+    lim = np.float32((kmax / dk) ** 2)
+    i = np.fft.fftfreq(n, 1.0 / n).astype(np.int64)
+    ij2 = (i[:, None] ** 2 + i[None, :] ** 2).ravel()
+    k2 = np.arange(n // 2 + 1, dtype=np.int64) ** 2
+    # count k with ij2 + k2 < lim, per (i,j)
+    rem = lim - ij2.astype(np.float64)
+    cnt = np.searchsorted(k2.astype(np.float64), rem, side='left')
+    return int(np.clip(cnt, 0, n // 2 + 1).sum())
+
+
+def run_gpu_arm(args):
+    import torch
+
+    from abacusutils_b200._lib import Engine
+    from abacusutils_b200.analysis.power_spectrum import calc_power
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg = dict(CFG)
+    if args.nparticles:
+        cfg['N'] = args.nparticles
+    if args.nmesh:
+        cfg['nmesh'] = args.nmesh
+    if world > 1:
+        from abacusutils_b200 import dist as abk_dist
+
+        return abk_dist.bench_main(args, cfg, METRIC, WORKLOAD, ClockSampler, peaks)
+
+    torch.cuda.set_device(local_rank)
+    eng = Engine.get(local_rank)
+    N, L, n = cfg['N'], cfg['L'], cfg['nmesh']
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(cfg['seed'])
+    pos = torch.rand((N, 3), device='cuda', dtype=torch.float32, generator=gen)
+    pos *= L
+    kw = dict(kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=n, compensated=True, interlaced=True, poles=cfg['poles'])
+
+    def step(p):
+        return calc_power(p, L, **kw)
+
+    for _ in range(args.warmup):
+        res = step(pos)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.profile(True)
+    eng.profile_collect()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step(pos)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.profile_collect()
+    eng.profile(False)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+
+    # ---- end to end: host (pinned) particles, copies inside the timed region --------------------------
+    e2e = None
+    try:
+        host = torch.empty((N, 3), dtype=torch.float32, pin_memory=True)
+        pinned = True
+    except Exception:
+        host = torch.empty((N, 3), dtype=torch.float32)
+        pinned = False
+    host.copy_(pos)
+    torch.cuda.synchronize()
+    del pos
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(1):
+        res_h = step(host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_h = step(host)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    d2h = sum(np.asarray(res_h[k]).nbytes for k in ('power', 'N_mode', 'k_avg', 'poles', 'N_mode_poles'))
+    e2e = {'value': e2e_ms, 'unit': 'ms', 'h2d_bytes_per_step': int(N * 12), 'd2h_bytes_per_step': int(d2h),
+           'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
+    del host
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peak, peak_src = peaks()
+    nseg = max(1, prof.get('tsc_bucket_hist', (0, 2 * args.steps))[1] // (2 * args.steps))
+    n_used = used_entries(n, L, np.pi * n / L)
+    stages = {}
+    for name, (tot_ms, cnt) in prof.items():
+        b = algorithmic_bytes(name, cfg, nseg, n_used)
+        stages[name] = {'ms_per_step': tot_ms / args.steps, 'launches_per_step': cnt / args.steps,
+                        'avg_launch_ms': tot_ms / cnt,
+                        'achieved_gbs': (b / (tot_ms / cnt * 1e-3) / 1e9) if b else None}
+    top = max(stages, key=lambda k: stages[k]['ms_per_step'])
+    roof = {'bound': 'hbm', 'kernel': top, 'achieved': stages[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+            'frac': (stages[top]['achieved_gbs'] / peak) if stages[top]['achieved_gbs'] else None, 'traffic': None,
+            'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms}
+
+    # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        level = pick_cpu_level(cfg, 25.0)
+        dt, desc, nt = cpu_sample(level, cfg)
+        cpu = {'value': dt * 8**level * 1e3, 'unit': 'ms', 'cores': nt, 'kind': 'port', 'sample': desc,
+               'sample_seconds': dt}
+
+    dep_ms = sum(stages[k]['ms_per_step'] for k in ('tsc_bucket_hist', 'tsc_bucket_scatter', 'scan', 'tsc_tile_deposit')
+                 if k in stages)
+    line = {
+        'metric': METRIC, 'value': ms, 'unit': 'ms', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD if not (args.nparticles or args.nmesh) else f'override N={N} nmesh={n}',
+                   'l2': 'inputs (12 GB particles, 4.3 GB grids) are larger than the 126 MB L2'},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        'stages': stages, 'mpart_per_s': N / ms / 1e3,
+        'tsc_gpart_per_s': (2 * N / (dep_ms * 1e-3) / 1e9) if dep_ms else None,
+        'N_mode_total': int(np.asarray(res['N_mode']).sum()),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--nparticles', type=int, default=0, help='override the particle count (testing only)')
+    ap.add_argument('--nmesh', type=int, default=0, help='override nmesh (testing only)')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -56,6 +56,14 @@ int abk_ctx_set_stream(abk_ctx *ctx, void *stream);
 int abk_ctx_sync(abk_ctx *ctx);
 /* number of kernels this library has launched on this context (bench.py "gpu_launches") */
 int64_t abk_ctx_launch_count(abk_ctx *ctx);
+/* Optional per-kernel timing: when enabled, every kernel launch is bracketed by a CUDA event pair
+ * on the launch stream.  abk_ctx_profile_collect synchronises the stream and ADDS, per kernel id,
+ * the elapsed milliseconds to ms_h[id] and the number of launches to n_h[id] (host arrays of
+ * abk_kernel_count() entries), then forgets the records.  abk_kernel_name(id) names an id. */
+int abk_ctx_profile_enable(abk_ctx *ctx, int on);
+int abk_ctx_profile_collect(abk_ctx *ctx, double *ms_h, int64_t *n_h);
+int abk_kernel_count(void);
+const char *abk_kernel_name(int id);
 /* tuning knobs (0 = library default): tile-kernel particle capacity per pass */
 int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity);
 
