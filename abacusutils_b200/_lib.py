@@ -37,7 +37,8 @@ class BinRequest(C.Structure):
                 ('real_in', C.c_void_p), ('W', C.c_void_p), ('scale', C.c_float), ('finish', C.c_int32),
                 ('kedges2', C.c_void_p), ('muedges2', C.c_void_p), ('Nk', C.c_int32), ('Nmu', C.c_int32),
                 ('Np', C.c_int32), ('pole_coef', C.c_void_p), ('pole_ell', C.c_int32 * ABK_MAX_POLES), ('counts', C.c_void_p),
-                ('sum_p', C.c_void_p), ('sum_k', C.c_void_p), ('sum_poles', C.c_void_p)]
+                ('sum_p', C.c_void_p), ('sum_k', C.c_void_p), ('sum_poles', C.c_void_p), ('scratch', C.c_void_p),
+                ('scratch_bytes', C.c_size_t)]
 
 
 _vp, _i32, _i64, _dbl, _flt, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t
@@ -80,6 +81,7 @@ SIGNATURES = {
     'abk_fft_exec_generic': (_i32, [_vp, _vp, _vp, _vp, _sz]),
     'abk_field_fft_finish': (_i32, [_vp, C.POINTER(KMesh), _vp, _vp, _vp, _flt]),
     'abk_raw_power': (_i32, [_vp, _vp, _vp, _vp, _i64]),
+    'abk_power_bin_scratch_bytes': (_i32, [_i32, _i32, _i32, _psz]),
     'abk_power_bin': (_i32, [_vp, C.POINTER(BinRequest)]),
     'abk_add_planes': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64]),
     'abk_transpose_pack': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, C.POINTER(_i64)]),

@@ -93,12 +93,7 @@ __global__ void __launch_bounds__(256) finish_kernel(float2 *__restrict__ f, Fin
 }
 
 // ------------------------------------------------------------------------------------------
-// (k,mu) binning.  One warp walks one (i,j) row with lanes on consecutive k (coalesced 256-byte
-// loads).  Within a row the bin index is monotone in k (power_spectrum.py:166-170), so lanes of
-// equal bin form contiguous runs: a segmented shuffle reduction leaves each run's sums in its head
-// lane, and the head lanes (distinct bins) update a WARP-PRIVATE shared-memory table with plain
-// read-modify-writes: no atomics in the main loop (a float shared atomic is a CAS loop on sm_100a).
-// Tables are flushed to the global double / u64 sums once per warp.
+// (k,mu) binning: arguments shared by the kernels below.
 struct BinArgs {
     abk_kmesh M;
     const float2 *f1, *f2;
@@ -114,41 +109,51 @@ struct BinArgs {
     double *sum_p, *sum_k, *sum_poles;
 };
 
-template <typename T>
-__device__ __forceinline__ T seg_reduce(T v, int key, int lane)
+// ------------------------------------------------------------------------------------------
+// (k,mu) binning kernel.
+//
+// A warp owns a column task (x-plane i, 32 consecutive k) and walks j.  Along j a lane's |k| moves
+// by less than one grid unit per step, so its (k,mu) bin changes only every few modes: each lane
+// keeps the running sums of its CURRENT bin in registers (no cross-lane traffic at all) and, when
+// the bin changes, sends them to the global float64/u64 sums with fire-and-forget reductions
+// (REDG.ADD.F64 / .U64, native on sm_100a).  The sums are replicated NREP times (CTA -> replica)
+// to spread same-address contention in L2 and folded by a tiny second kernel.  Bins are tracked
+// incrementally (a step changes the bin index by at most a few), so there is no binary search in
+// the loop.  Loads stay fully coalesced: lanes hold consecutive k of the same (i,j) row.
+constexpr int BIN_NREP = 16;
+constexpr int BIN_UNROLL = 4;
+
+template <int NPN>
+struct LaneAcc {
+    int key;  // bk * Nmu + bmu of the running bin, -1 = empty
+    int bk;
+    unsigned cnt;
+    float p, k;
+    float pl[NPN > 0 ? NPN : 1];
+};
+
+template <int NPN>
+__device__ __forceinline__ void lane_flush(const BinArgs &A, const LaneAcc<NPN> &acc, size_t rep_off_bins,
+                                           size_t rep_off_poles, const int *s_pidx)
 {
+    if (acc.key < 0) return;
+    atomicAdd(A.counts + rep_off_bins + acc.key, (unsigned long long)acc.cnt);
+    atomicAdd(A.sum_p + rep_off_bins + acc.key, (double)acc.p);
+    atomicAdd(A.sum_k + rep_off_bins + acc.key, (double)acc.k);
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const T o = __shfl_down_sync(0xffffffffu, v, off);
-        const int ko = __shfl_down_sync(0xffffffffu, key, off);
-        if (lane + off < 32 && ko == key) v += o;
-    }
-    return v;
+    for (int q = 0; q < NPN; q++)
+        if (q < A.Npn) atomicAdd(A.sum_poles + rep_off_poles + (size_t)s_pidx[q] * A.Nk + acc.bk, (double)acc.pl[q]);
 }
 
-// number of table entries e[1..N] strictly below x  (== np.searchsorted(e[1:], x, 'left'))
-__device__ __forceinline__ int count_below(const float *__restrict__ e, int N, float x)
-{
-    int lo = 0, hi = N;  // answer in [0, N]
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (e[1 + mid] < x) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(512) power_bin_kernel(BinArgs A)
+template <int NPN>
+__global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__restrict__ task_counter, int nrep)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int Nb = A.Nk * A.Nmu;
     float *s_ke = reinterpret_cast<float *>(smem_raw);
     float *s_me = s_ke + (A.Nk + 1);
-    float *s_coef = s_me + (A.Nmu + 1);                     // Npn * NCOEF
-    int *s_pidx = reinterpret_cast<int *>(s_coef + A.Npn * ABK_POLE_NCOEF);  // Npn: row in sum_poles
-    const int hdr = (A.Nk + 1) + (A.Nmu + 1) + A.Npn * ABK_POLE_NCOEF + A.Npn;
-    const int hdr_al = (hdr + 3) & ~3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float *s_coef = s_me + (A.Nmu + 1);
+    int *s_pidx = reinterpret_cast<int *>(s_coef + A.Npn * ABK_POLE_NCOEF);
+    const int lane = threadIdx.x & 31;
 
     for (int t = threadIdx.x; t <= A.Nk; t += blockDim.x) s_ke[t] = A.kedges2[t];
     for (int t = threadIdx.x; t <= A.Nmu; t += blockDim.x) s_me[t] = A.muedges2[t];
@@ -161,120 +166,170 @@ __global__ void __launch_bounds__(512) power_bin_kernel(BinArgs A)
                 q++;
             }
     }
-    // warp-private tables
-    const int tbl_words = 3 * Nb + A.Npn * A.Nk;
-    uint32_t *t_cnt = nullptr;
-    float *t_p = nullptr, *t_k = nullptr, *t_pl = nullptr;
-    if (SMEM_TABLES) {
-        uint32_t *base = reinterpret_cast<uint32_t *>(smem_raw) + hdr_al + (size_t)warp * tbl_words;
-        t_cnt = base;
-        t_p = reinterpret_cast<float *>(base + Nb);
-        t_k = t_p + Nb;
-        t_pl = t_k + Nb;
-        for (int t = lane; t < tbl_words; t += 32) base[t] = 0u;
-    }
     __syncthreads();
 
     const abk_kmesh M = A.M;
-    const int nj = M.j1 - M.j0;
-    const int64_t nrows = (int64_t)(M.i1 - M.i0) * nj;
-    const float e_lo = s_ke[0], e_hi = s_ke[A.Nk];
+    const int Nk = A.Nk, Nmu = A.Nmu;
+    const int nj = M.j1 - M.j0, ni = M.i1 - M.i0;
+    const int nchunks = (M.nzc + 31) / 32;
+    const unsigned ntasks = (unsigned)ni * nchunks;
+    const float e_lo = s_ke[0], e_hi = s_ke[Nk];
+    const int rep = (nrep > 1) ? (int)(blockIdx.x % nrep) : 0;
+    const size_t rep_off_bins = (size_t)rep * Nk * Nmu, rep_off_poles = (size_t)rep * A.Np * Nk;
 
-    for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < nrows; row += (int64_t)gridDim.x * nwarps) {
-        const int il = (int)(row / nj), jl = (int)(row % nj);
-        const int i = M.i0 + il, j = M.j0 + jl;
-        const int ii = fold(i, M.n), jj = fold(j, M.n);
-        const int ij2 = ii * ii + jj * jj;
-        const float wij = (A.finish && A.F1.W) ? A.F1.W[i] * A.F1.W[j] : 1.0f;
-        const int64_t base = il * M.stride_i + jl * M.stride_j;
-        // the row ends where kmag2 >= last edge (power_spectrum.py:249-250): skip the tail chunks
-        for (int k0 = 0; k0 < M.nzc; k0 += 32) {
-            if ((float)(ij2 + k0 * k0) >= e_hi) break;  // warp-uniform
-            const int k = k0 + lane;
-            int key = -1, bk = -1;
-            float val = 0.0f, kmag2 = 0.0f, mu2 = 0.0f;
-            if (k < M.nzc) {
-                kmag2 = (float)(ij2 + k * k);
-                if (kmag2 >= e_lo && kmag2 < e_hi) {
+    for (;;) {
+        unsigned task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
+        const int il = task / nchunks, k0 = (task % nchunks) * 32;
+        const int i = M.i0 + il, ii = fold(i, M.n);
+        const int k = k0 + lane;
+        const bool k_ok = k < M.nzc;
+        const int ik2 = ii * ii + k * k;
+        const int ik2_min = ii * ii + k0 * k0;  // smallest |k|^2 of this column at jj = 0
+        if ((float)ik2_min >= e_hi) continue;   // the whole column lies beyond the last edge
+        const float k2f = (float)(k * k);
+        const float Wi = (A.finish && A.F1.W) ? A.F1.W[i] : 1.0f;
+        const float Wk = (A.finish && A.F1.W && k_ok) ? A.F1.W[k] : 1.0f;
+        const float mult = (k == 0) ? 1.0f : 2.0f;
+        const unsigned cmult = (k == 0) ? 1u : 2u;
+
+        LaneAcc<NPN> acc;
+        acc.key = -1; acc.bk = 0; acc.cnt = 0; acc.p = 0.0f; acc.k = 0.0f;
+#pragma unroll
+        for (int q = 0; q < (NPN > 0 ? NPN : 1); q++) acc.pl[q] = 0.0f;
+        int bk = 0, bmu = 0;
+
+        for (int jl0 = 0; jl0 < nj; jl0 += BIN_UNROLL) {
+            // ---- issue the loads of BIN_UNROLL rows first ------------------------------------------
+            float2 va[BIN_UNROLL], vas[BIN_UNROLL], vb[BIN_UNROLL], vbs[BIN_UNROLL];
+            float kmag2[BIN_UNROLL];
+            bool use[BIN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < BIN_UNROLL; u++) {
+                const int jl = jl0 + u;
+                const int jj = fold(M.j0 + jl, M.n);
+                kmag2[u] = (float)(ik2 + jj * jj);
+                use[u] = k_ok && jl < nj && kmag2[u] >= e_lo && kmag2[u] < e_hi;
+                va[u] = vas[u] = vb[u] = vbs[u] = make_float2(0.0f, 0.0f);
+                if (use[u]) {
+                    const int64_t idx = il * M.stride_i + jl * M.stride_j + k;
                     if (A.real_in) {
-                        val = __ldcs(A.real_in + base + k);
+                        va[u].x = __ldcs(A.real_in + idx);
                     } else {
-                        float2 a = __ldcs(A.f1 + base + k);
-                        if (A.finish) a = finish_mode(a, A.F1, base + k, ii, jj, k, wij);
+                        va[u] = __ldcs(A.f1 + idx);
+                        if (A.finish && A.F1.fs) vas[u] = __ldcs(A.F1.fs + idx);
                         if (A.f2) {
-                            float2 b = __ldcs(A.f2 + base + k);
-                            if (A.finish) b = finish_mode(b, A.F2, base + k, ii, jj, k, wij);
-                            val = a.x * b.x + a.y * b.y;
-                        } else {
-                            val = a.x * a.x + a.y * a.y;
+                            vb[u] = __ldcs(A.f2 + idx);
+                            if (A.finish && A.F2.fs) vbs[u] = __ldcs(A.F2.fs + idx);
                         }
                     }
-                    mu2 = kmag2 > 0.0f ? __fdiv_rn((float)(k * k), kmag2) : 0.0f;
-                    bk = count_below(s_ke, A.Nk, kmag2);
-                    int bmu = count_below(s_me, A.Nmu, mu2);
-                    if (bmu > A.Nmu - 1) bmu = A.Nmu - 1;
-                    key = bk * A.Nmu + bmu;
                 }
             }
-            if (__ballot_sync(0xffffffffu, key >= 0) == 0u) continue;
-            const float mult = (k == 0) ? 1.0f : 2.0f;
-            const float pv = mult * val;
-            const uint32_t c_run = seg_reduce<uint32_t>(key >= 0 ? (k == 0 ? 1u : 2u) : 0u, key, lane);
-            const float p_run = seg_reduce<float>(pv, key, lane);
-            const float k_run = seg_reduce<float>(mult * sqrtf(kmag2), key, lane);
-            const int key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-            const bool head = (key >= 0) && (lane == 0 || key_prev != key);
-            if (head) {
-                if (SMEM_TABLES) {
-                    t_cnt[key] += c_run;
-                    t_p[key] += p_run;
-                    t_k[key] += k_run;
-                } else {
-                    atomicAdd(A.counts + key, (unsigned long long)c_run);
-                    atomicAdd(A.sum_p + key, (double)p_run);
-                    atomicAdd(A.sum_k + key, (double)k_run);
-                }
-            }
-            if (A.Npn > 0) {
-                const int bk_prev = __shfl_up_sync(0xffffffffu, bk, 1);
-                const bool head_k = (bk >= 0) && (lane == 0 || bk_prev != bk);
-                const float s = A.even_only ? mu2 : sqrtf(mu2);
-                for (int q = 0; q < A.Npn; q++) {
-                    const float *c = s_coef + q * ABK_POLE_NCOEF;
-                    float pw;
-                    if (A.even_only) {  // polynomial in x = mu^2: coefficients of s^0, s^2, ... s^10
-                        pw = c[10];
-                        pw = fmaf(pw, s, c[8]); pw = fmaf(pw, s, c[6]); pw = fmaf(pw, s, c[4]);
-                        pw = fmaf(pw, s, c[2]); pw = fmaf(pw, s, c[0]);
-                    } else {
-                        pw = c[10];
+            // ---- per-row arithmetic -------------------------------------------------------------------
 #pragma unroll
-                        for (int m = 9; m >= 0; m--) pw = fmaf(pw, s, c[m]);
+            for (int u = 0; u < BIN_UNROLL; u++) {
+                if (!use[u]) continue;
+                const int jl = jl0 + u;
+                const int j = M.j0 + jl, jj = fold(j, M.n);
+                float val;
+                if (A.real_in) {
+                    val = va[u].x;
+                } else {
+                    float2 a = va[u], b = vb[u];
+                    if (A.finish) {
+                        float sn = 0.0f, cs = 1.0f;
+                        if (A.F1.fs) {
+                            sincospif((float)(ii + jj + k) * A.F1.inv_n, &sn, &cs);
+                            a.x += vas[u].x * cs - vas[u].y * sn;
+                            a.y += vas[u].x * sn + vas[u].y * cs;
+                        }
+                        a.x *= A.F1.scale;
+                        a.y *= A.F1.scale;
+                        float ww = 1.0f;
+                        if (A.F1.W) {
+                            ww = (Wi * A.F1.W[j]) * Wk;
+                            a.x = __fdiv_rn(a.x, ww);
+                            a.y = __fdiv_rn(a.y, ww);
+                        }
+                        if (A.f2) {
+                            if (A.F2.fs) {
+                                b.x += vbs[u].x * cs - vbs[u].y * sn;
+                                b.y += vbs[u].x * sn + vbs[u].y * cs;
+                            }
+                            b.x *= A.F2.scale;
+                            b.y *= A.F2.scale;
+                            if (A.F2.W) {
+                                b.x = __fdiv_rn(b.x, ww);
+                                b.y = __fdiv_rn(b.y, ww);
+                            }
+                        }
                     }
-                    const float pl_run = seg_reduce<float>(bk >= 0 ? pv * pw : 0.0f, bk, lane);
-                    if (head_k) {
-                        if (SMEM_TABLES) t_pl[q * A.Nk + bk] += pl_run;
-                        else atomicAdd(A.sum_poles + (size_t)s_pidx[q] * A.Nk + bk, (double)pl_run);
+                    val = A.f2 ? (a.x * b.x + a.y * b.y) : (a.x * a.x + a.y * a.y);
+                }
+                const float km2 = kmag2[u];
+                const float mu2 = km2 > 0.0f ? __fdiv_rn(k2f, km2) : 0.0f;
+                // incremental bin tracking: bk = #{b in 1..Nk : e[b] < km2}
+                while (bk < Nk - 1 && km2 > s_ke[bk + 1]) bk++;
+                while (bk > 0 && !(km2 > s_ke[bk])) bk--;
+                while (bmu < Nmu - 1 && mu2 > s_me[bmu + 1]) bmu++;
+                while (bmu > 0 && !(mu2 > s_me[bmu])) bmu--;
+                const int key = bk * Nmu + bmu;
+                if (key != acc.key) {
+                    lane_flush<NPN>(A, acc, rep_off_bins, rep_off_poles, s_pidx);
+                    acc.key = key; acc.bk = bk; acc.cnt = 0; acc.p = 0.0f; acc.k = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < (NPN > 0 ? NPN : 1); q++) acc.pl[q] = 0.0f;
+                }
+                const float pv = mult * val;
+                acc.cnt += cmult;
+                acc.p += pv;
+                acc.k = fmaf(mult, sqrtf(km2), acc.k);
+                if (NPN > 0) {
+                    const float sarg = A.even_only ? mu2 : sqrtf(mu2);
+#pragma unroll
+                    for (int q = 0; q < NPN; q++) {
+                        if (q >= A.Npn) break;
+                        const float *c = s_coef + q * ABK_POLE_NCOEF;
+                        float pw;
+                        if (A.even_only) {
+                            pw = c[10];
+                            pw = fmaf(pw, sarg, c[8]); pw = fmaf(pw, sarg, c[6]); pw = fmaf(pw, sarg, c[4]);
+                            pw = fmaf(pw, sarg, c[2]); pw = fmaf(pw, sarg, c[0]);
+                        } else {
+                            pw = c[10];
+#pragma unroll
+                            for (int m = 9; m >= 0; m--) pw = fmaf(pw, sarg, c[m]);
+                        }
+                        acc.pl[q] = fmaf(pv, pw, acc.pl[q]);
                     }
                 }
             }
         }
+        lane_flush<NPN>(A, acc, rep_off_bins, rep_off_poles, s_pidx);
     }
+}
 
-    if (SMEM_TABLES) {
-        __syncwarp();
-        for (int t = lane; t < Nb; t += 32) {
-            const uint32_t c = t_cnt[t];
-            if (c) {
-                atomicAdd(A.counts + t, (unsigned long long)c);
-                atomicAdd(A.sum_p + t, (double)t_p[t]);
-                atomicAdd(A.sum_k + t, (double)t_k[t]);
-            }
-        }
-        for (int t = lane; t < A.Npn * A.Nk; t += 32) {
-            const float v = t_pl[t];
-            if (v != 0.0f) atomicAdd(A.sum_poles + (size_t)s_pidx[t / A.Nk] * A.Nk + (t % A.Nk), (double)v);
-        }
+// fold the NREP replicas into the caller's sums (accumulating)
+__global__ void __launch_bounds__(256) fold_replicas_kernel(const unsigned long long *__restrict__ rc,
+                                                            const double *__restrict__ rp, const double *__restrict__ rk,
+                                                            const double *__restrict__ rpl, int nrep, int64_t Nb,
+                                                            int64_t Npl, unsigned long long *__restrict__ counts,
+                                                            double *__restrict__ sum_p, double *__restrict__ sum_k,
+                                                            double *__restrict__ sum_poles)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < Nb) {
+        unsigned long long c = 0;
+        double p = 0.0, k = 0.0;
+        for (int r = 0; r < nrep; r++) { c += rc[r * Nb + t]; p += rp[r * Nb + t]; k += rk[r * Nb + t]; }
+        counts[t] += c; sum_p[t] += p; sum_k[t] += k;
+    }
+    if (t < Npl) {
+        double v = 0.0;
+        for (int r = 0; r < nrep; r++) v += rpl[r * Npl + t];
+        sum_poles[t] += v;
     }
 }
 
@@ -436,27 +491,49 @@ extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
 
     const int64_t nrows = (int64_t)(A.M.i1 - A.M.i0) * (A.M.j1 - A.M.j0);
     if (nrows == 0) return ABK_OK;
-    const int64_t Nb = (int64_t)A.Nk * A.Nmu;
+    const int64_t Nb = (int64_t)A.Nk * A.Nmu, Npl = (int64_t)A.Np * A.Nk;
     const int hdr = (A.Nk + 1) + (A.Nmu + 1) + A.Npn * ABK_POLE_NCOEF + A.Npn;
     const size_t hdr_bytes = (size_t)((hdr + 3) & ~3) * 4;
-    const size_t tbl_bytes = (size_t)(3 * Nb + (int64_t)A.Npn * A.Nk) * 4;
-    const size_t budget = (size_t)ctx->smem_optin - 1024;
-    int warps = 0;
-    if (hdr_bytes < budget) warps = (int)((budget - hdr_bytes) / tbl_bytes);
-    if (warps > 16) warps = 16;
-    ABK_REQUIRE(hdr_bytes + 64 < budget, "abk_power_bin: edge tables (%zu B) do not fit in shared memory", hdr_bytes);
-    if (warps >= 4) {
-        const size_t smem = hdr_bytes + (size_t)warps * tbl_bytes;
-        ABK_CHECK_CUDA(cudaFuncSetAttribute(power_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int64_t blocks = (nrows + warps - 1) / warps;
-        if (blocks > ctx->num_sms) blocks = ctx->num_sms;
-        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, power_bin_kernel<true><<<(unsigned)blocks, warps * 32, smem, ctx->stream>>>(A));
-    } else {
-        ABK_CHECK_CUDA(cudaFuncSetAttribute(power_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hdr_bytes));
-        int64_t blocks = (nrows + 15) / 16;
-        if (blocks > (int64_t)ctx->num_sms * 2) blocks = (int64_t)ctx->num_sms * 2;
-        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, power_bin_kernel<false><<<(unsigned)blocks, 512, hdr_bytes, ctx->stream>>>(A));
+    ABK_REQUIRE(hdr_bytes + 1024 < (size_t)ctx->smem_optin, "abk_power_bin: edge tables (%zu B) do not fit in shared memory",
+                hdr_bytes);
+
+    // replicated sums in the caller's scratch (optional): [counts | sum_p | sum_k | sum_poles] x nrep
+    int nrep = 1;
+    const size_t rep_bytes = (size_t)(3 * Nb + Npl) * 8;
+    if (R->scratch && R->scratch_bytes >= rep_bytes * BIN_NREP) nrep = BIN_NREP;
+    unsigned long long *caller_counts = A.counts;
+    double *caller_p = A.sum_p, *caller_k = A.sum_k, *caller_pl = A.sum_poles;
+    if (nrep > 1) {
+        ABK_CHECK_CUDA(cudaMemsetAsync(R->scratch, 0, rep_bytes * nrep, ctx->stream));
+        char *base = (char *)R->scratch;
+        A.counts = (unsigned long long *)base;
+        A.sum_p = (double *)(base + (size_t)nrep * Nb * 8);
+        A.sum_k = (double *)(base + (size_t)2 * nrep * Nb * 8);
+        A.sum_poles = (double *)(base + (size_t)3 * nrep * Nb * 8);
     }
+    unsigned *task_counter = (unsigned *)(ctx->d_scalars + 2);
+    ABK_CHECK_CUDA(cudaMemsetAsync(task_counter, 0, sizeof(unsigned), ctx->stream));
+    const int blocks = ctx->num_sms * 4;
+    void (*kern)(BinArgs, unsigned *, int) = nullptr;
+    if (A.Npn == 0) kern = power_bin2_kernel<0>;
+    else if (A.Npn <= 2) kern = power_bin2_kernel<2>;
+    else if (A.Npn <= 4) kern = power_bin2_kernel<4>;
+    else kern = power_bin2_kernel<ABK_MAX_POLES>;
+    ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hdr_bytes));
+    ABK_LAUNCH(ctx, ABK_K_POWER_BIN, kern<<<blocks, 256, hdr_bytes, ctx->stream>>>(A, task_counter, nrep));
+    if (nrep > 1) {
+        const int64_t m = Nb > Npl ? Nb : Npl;
+        ABK_LAUNCH(ctx, ABK_K_MISC,
+                   fold_replicas_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(
+                       A.counts, A.sum_p, A.sum_k, A.sum_poles, nrep, Nb, Npl, caller_counts, caller_p, caller_k, caller_pl));
+    }
+    return ABK_OK;
+}
+
+extern "C" int abk_power_bin_scratch_bytes(int Nk, int Nmu, int Np, size_t *bytes)
+{
+    ABK_REQUIRE(bytes && Nk >= 1 && Nmu >= 1 && Np >= 0, "abk_power_bin_scratch_bytes: bad arguments");
+    *bytes = (size_t)(3 * (int64_t)Nk * Nmu + (int64_t)Np * Nk) * 8 * BIN_NREP;
     return ABK_OK;
 }
 

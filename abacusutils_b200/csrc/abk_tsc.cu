@@ -26,7 +26,7 @@ namespace {
 
 struct TscParams {
     float inv_hx, inv_hy, inv_hz;  // f32(g/box), tsc.py:408-411
-    float off;                     // f32(offset), tsc.py:413
+    float off;                     // f32(offset), tsc.py:413: the offset of THIS deposit / bucketing
     double box;
     int nx, ny, nz;                // global grid
     int nxe;                       // x-extent of the tiled region (== nx single GPU; slab mode: local planes)
@@ -66,7 +66,8 @@ __device__ __forceinline__ bool tile_of(const TscParams &P, float x, float y, fl
     return true;
 }
 
-// Loads particle i (AoS float[N][3]); VEC4 path handles 4 particles per thread with 3 x 128-bit loads.
+// Four particles per thread: 3 x 128-bit loads of positions (AoS float[N][3]), then all four tile
+// atomics are issued back to back (independent, so their L2 round trips overlap), then the stores.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict__ pos, const float *__restrict__ w,
                                                          int64_t N, TscParams P, uint32_t *__restrict__ counts,
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
             c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
             c[8] = d.x; c[9] = d.y; c[10] = d.z; c[11] = d.w;
         } else {
-            for (int q = 0; q < 3 * cnt; q++) c[q] = __ldcs(pos + 3 * base + q);
+#pragma unroll
+            for (int q = 0; q < 12; q++) c[q] = (q < 3 * cnt) ? __ldcs(pos + 3 * base + q) : 0.0f;
         }
         float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         if (SCATTER && w) {
@@ -93,33 +95,53 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
                 const float4 t = __ldcs(reinterpret_cast<const float4 *>(w + base));
                 wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
             } else {
-                for (int q = 0; q < cnt; q++) wv[q] = __ldcs(w + base + q);
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (q < cnt) wv[q] = __ldcs(w + base + q);
             }
         }
+        uint32_t tile[4];
+        bool ok[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            if (q >= cnt) break;
-            float x = c[3 * q], y = c[3 * q + 1], z = c[3 * q + 2];
-            if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
-            uint32_t tile;
-            if (!tile_of(P, x, y, z, tile)) {
-                if (!SCATTER) atomicAdd(n_dropped, 1ull);
-                continue;
+            if (P.wrap) {
+                c[3 * q] = wrap_coord(c[3 * q], P.box);
+                c[3 * q + 1] = wrap_coord(c[3 * q + 1], P.box);
+                c[3 * q + 2] = wrap_coord(c[3 * q + 2], P.box);
             }
-            if (!SCATTER) {
-                atomicAdd(&counts[tile], 1u);
-            } else {
-                // cursors count DOWN from the inclusive scan, so they end as the exclusive scan
-                const uint32_t slot = atomicSub(&counts[tile], 1u) - 1u;
-                records[slot] = make_float4(x, y, z, wv[q]);
+            ok[q] = (q < cnt) && tile_of(P, c[3 * q], c[3 * q + 1], c[3 * q + 2], tile[q]);
+        }
+        if (!SCATTER) {
+            unsigned dropped = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (ok[q]) atomicAdd(&counts[tile[q]], 1u);
+                else if (q < cnt) dropped++;
             }
+            if (dropped) atomicAdd(n_dropped, (unsigned long long)dropped);
+        } else {
+            // cursors count DOWN from the inclusive scan, so they end as the exclusive scan
+            uint32_t slot[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) slot[q] = ok[q] ? atomicSub(&counts[tile[q]], 1u) - 1u : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (ok[q]) records[slot[q]] = make_float4(c[3 * q], c[3 * q + 1], c[3 * q + 2], wv[q]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
+// Tile deposit.  Geometry of the shared-memory working set of one CTA (= one tile of 8 x 8 x 32 cells):
+//   slab[w]   : warp w (= y-row w of the tile) owns a PRIVATE float slab [TX+2 planes][3 rows][TZ+2],
+//               the image of its row's clouds on rows w-1, w, w+1 (+1-cell halo in x and z).  Private
+//               slabs make the main loop free of block barriers and of atomics.
+//   head[c]   : first particle of cell c's list (index into srec) or NIL
+//   srec[2v]  : (wx-, wx0, wx+, dz)            precomputed in the lane<->particle load pass, so the
+//   srec[2v+1]: (wy- W, wy0 W, wy+ W, next)     divergent lane<->cell loop is 2 LDS.128 + 43 FP ops
 constexpr int OUT_X = ABK_TX + 2, OUT_Y = ABK_TY + 2, OUT_Z = ABK_TZ + 2;
 constexpr int OUT_N = OUT_X * OUT_Y * OUT_Z;
+constexpr int SLAB_PLANE = 3 * OUT_Z;
+constexpr int SLAB_WORDS = OUT_X * SLAB_PLANE;
 constexpr int NCELL = ABK_TX * ABK_TY * ABK_TZ;
 constexpr int DEP_THREADS = ABK_TY * 32;
 constexpr uint32_t NIL = 0xffffffffu;
@@ -132,7 +154,7 @@ struct SegList {
 
 static size_t deposit_smem_bytes(int cap)
 {
-    return (size_t)OUT_N * 4 + (size_t)NCELL * 4 + (size_t)cap * 16 + (size_t)cap * 2 + 64;
+    return (size_t)ABK_TY * SLAB_WORDS * 4 + (size_t)NCELL * 4 + (size_t)cap * 32 + 64;
 }
 
 // tsc.py:442-451: the three 1-D TSC weights for cells i-1, i, i+1 given d = i - p
@@ -144,34 +166,60 @@ __device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
     wp = 0.5f * b * b;
 }
 
-__device__ __forceinline__ void emit_plane(float *__restrict__ out, const float (&S)[3][3], int x, int wy, int lane)
+// Add one finished x-plane of this lane's register window to the warp's private slab.
+// S[b][c]: contribution of cell (row w, z = lane) to row w-1+b, cell z-1+c.  Lane z receives the
+// c=+1 term of lane z-1 and the c=-1 term of lane z+1; the two halo cells are lanes 0 / 31's.
+__device__ __forceinline__ void emit_plane(float *__restrict__ slab, const float (&S)[3][3], int x, int lane)
 {
-    // S[b][c]: this lane's (cell cz = lane) contribution to row wy-1+b, cell cz-1+c of plane x.
-    // Lane cz receives c=+1 from lane cz-1 and c=-1 from lane cz+1.
-    float *plane = out + (x + 1) * (OUT_Y * OUT_Z);
+    float *plane = slab + (x + 1) * SLAB_PLANE;
 #pragma unroll
     for (int b = 0; b < 3; b++) {
         const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
         const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
-        float v = S[b][1];
-        if (lane > 0) v += up;
-        if (lane < 31) v += dn;
-        float *row = plane + (wy + b) * OUT_Z;
+        const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
+        float *row = plane + b * OUT_Z;
         row[lane + 1] += v;
         if (lane == 0) row[0] += S[b][0];
         if (lane == 31) row[OUT_Z - 1] += S[b][2];
-        __syncthreads();  // rows wy+b of different warps are distinct within a phase, not across phases
     }
 }
 
-__global__ void __launch_bounds__(DEP_THREADS, 3)
+// 27 global reductions for a particle whose (shifted) centre cell lies outside the tile it was
+// bucketed in (only possible when the deposit offset differs from the bucketing offset).
+__device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscParams &P, int64_t ldz, int slab,
+                                            int cx, int cy, int cz, float dx, float dy, float dz, float W)
+{
+    const int64_t sx = (int64_t)P.ny * ldz;
+    float wx[3], wy[3], wz[3];
+    tsc_w(dx, wx[0], wx[1], wx[2]);
+    tsc_w(dy, wy[0], wy[1], wy[2]);
+    tsc_w(dz, wz[0], wz[1], wz[2]);
+    for (int a = 0; a < 3; a++) {
+        int64_t gx;
+        if (slab) {
+            int lx = cx - P.x_lo;
+            if (lx < 0) lx += P.nx;
+            gx = lx + a;  // plane 0 of a slab grid is the ghost plane x_lo-1
+        } else {
+            gx = abk_wrap_cell(cx + a - 1, P.nx);
+        }
+        for (int b = 0; b < 3; b++) {
+            const int gy = abk_wrap_cell(cy + b - 1, P.ny);
+            for (int c = 0; c < 3; c++) {
+                const int gz = abk_wrap_cell(cz + c - 1, P.nz);
+                atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gz, wx[a] * wy[b] * wz[c] * W);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DEP_THREADS, 2)
 tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *out = reinterpret_cast<float *>(smem_raw);
-    uint32_t *head = reinterpret_cast<uint32_t *>(out + OUT_N);
-    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);  // (OUT_N + NCELL)*4 is a multiple of 16
-    uint16_t *next = reinterpret_cast<uint16_t *>(srec + cap);
+    float *slabs = reinterpret_cast<float *>(smem_raw);
+    uint32_t *head = reinterpret_cast<uint32_t *>(slabs + ABK_TY * SLAB_WORDS);
+    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);
     __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
     __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
 
@@ -191,13 +239,14 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
 
-    for (int i = tid; i < OUT_N; i += DEP_THREADS) out[i] = 0.0f;
+    for (int i = tid; i < ABK_TY * SLAB_WORDS; i += DEP_THREADS) slabs[i] = 0.0f;
+    float *myslab = slabs + wy * SLAB_WORDS;
 
     for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
         const int m = (int)min((uint32_t)cap, total - chunk0);
         for (int c = tid; c < NCELL; c += DEP_THREADS) head[c] = NIL;
         __syncthreads();
-        // ---- build per-cell lists -----------------------------------------------------------
+        // ---- lane <-> particle: weights once per particle, per-cell lists ------------------------
         for (int v = tid; v < m; v += DEP_THREADS) {
             uint32_t u = chunk0 + v;
             int s = 0;
@@ -210,12 +259,24 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
             cell_of(r.z, P.off, P.inv_hz, P.nz, cz, dz);
             int lx = cx - P.x_lo;
             if (lx < 0) lx += P.nx;
-            const int c = ((lx - x0) * ABK_TY + (cy - y0)) * ABK_TZ + (cz - z0);
-            srec[v] = make_float4(dx, dy, dz, r.w);
-            next[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+            lx -= x0;
+            int ly = cy - y0, lz = cz - z0;
+            if (ly < 0) ly += P.ny;  // the shifted cell may have wrapped around the box edge
+            if (lz < 0) lz += P.nz;
+            if ((unsigned)lx < (unsigned)ABK_TX && (unsigned)ly < (unsigned)ABK_TY && (unsigned)lz < (unsigned)ABK_TZ) {
+                float wxm, wx0, wxp, wym, wy0, wyp;
+                tsc_w(dx, wxm, wx0, wxp);
+                tsc_w(dy, wym, wy0, wyp);
+                const int c = (lx * ABK_TY + ly) * ABK_TZ + lz;
+                srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
+                const uint32_t old = atomicExch(&head[c], (uint32_t)v);
+                srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
+            } else {
+                deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+            }
         }
         __syncthreads();
-        // ---- accumulate: lane owns cell (cx, wy, lane); rolling window over x ------------------
+        // ---- lane <-> cell (row wy, z = lane); rolling 3-plane register window along x ---------------
         float S0[3][3], S1[3][3], S2[3][3];
 #pragma unroll
         for (int b = 0; b < 3; b++)
@@ -226,40 +287,43 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
         for (int cx = 0; cx < ABK_TX; cx++) {
             uint32_t i = head[(cx * ABK_TY + wy) * ABK_TZ + lane];
             while (i != NIL) {
-                const float4 r = srec[i];
-                const uint16_t nxt = next[i];
-                i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
-                float wxm, wx0, wxp, wym, wy0, wyp, wzm, wz0, wzp;
-                tsc_w(r.x, wxm, wx0, wxp);
-                tsc_w(r.y, wym, wy0, wyp);
-                tsc_w(r.z, wzm, wz0, wzp);
-                const float wyv[3] = {wym, wy0, wyp}, wzv[3] = {wzm, wz0, wzp};
+                const float4 A = srec[2 * i], B = srec[2 * i + 1];
+                i = __float_as_uint(B.w);
+                float wz[3];
+                tsc_w(A.w, wz[0], wz[1], wz[2]);
+                const float wyW[3] = {B.x, B.y, B.z};
 #pragma unroll
                 for (int b = 0; b < 3; b++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        const float t = wyv[b] * wzv[c] * r.w;
-                        S0[b][c] = fmaf(wxm, t, S0[b][c]);
-                        S1[b][c] = fmaf(wx0, t, S1[b][c]);
-                        S2[b][c] = fmaf(wxp, t, S2[b][c]);
+                        const float t = wyW[b] * wz[c];
+                        S0[b][c] = fmaf(A.x, t, S0[b][c]);
+                        S1[b][c] = fmaf(A.y, t, S1[b][c]);
+                        S2[b][c] = fmaf(A.z, t, S2[b][c]);
                     }
             }
-            emit_plane(out, S0, cx - 1, wy, lane);
+            emit_plane(myslab, S0, cx - 1, lane);
 #pragma unroll
             for (int b = 0; b < 3; b++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
         }
-        emit_plane(out, S0, ABK_TX - 1, wy, lane);
-        emit_plane(out, S1, ABK_TX, wy, lane);
+        emit_plane(myslab, S0, ABK_TX - 1, lane);
+        emit_plane(myslab, S1, ABK_TX, lane);
+        __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
     }
 
-    // ---- flush tile + halo ---------------------------------------------------------------------
+    // ---- merge the 8 private slabs and flush tile + halo with float reductions ---------------------
     const int64_t sx = (int64_t)P.ny * ldz;
     for (int i = tid; i < OUT_N; i += DEP_THREADS) {
-        const float v = out[i];
-        if (v == 0.0f) continue;
         const int oz = i % OUT_Z, oy = (i / OUT_Z) % OUT_Y, ox = i / (OUT_Z * OUT_Y);
+        float v = 0.0f;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            const int w = oy - b;
+            if (w >= 0 && w < ABK_TY) v += slabs[w * SLAB_WORDS + ox * SLAB_PLANE + b * OUT_Z + oz];
+        }
+        if (v == 0.0f) continue;
         int64_t gx;
         if (slab) gx = x0 + ox;  // grid plane 0 is the ghost plane x_lo-1
         else gx = abk_wrap_cell(x0 + ox - 1, P.nx);
@@ -493,12 +557,14 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
 static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles)
 {
     if (ctx->tile_capacity) return ctx->tile_capacity;
-    // mean occupancy + 5 sigma (Poisson), rounded up to 256, so a uniform catalogue needs one pass
+    // mean occupancy + 5 sigma (Poisson), so a uniform catalogue needs one pass per tile; capped so
+    // that two CTAs stay resident per SM (denser tiles simply take several passes)
     const double mean = ntiles > 0 ? (double)n_total / (double)ntiles : 0.0;
-    double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
-    int cap = (int)((want + 255.0) / 256.0) * 256;
-    if (cap < 512) cap = 512;
-    if (cap > 8192) cap = 8192;
+    const double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
+    int cap = (int)((want + 63.0) / 64.0) * 64;
+    const int two_per_sm = (int)(((size_t)(ctx->smem_optin + 1024) / 2 - 1024 - deposit_smem_bytes(0)) / 32) / 64 * 64;
+    if (cap > two_per_sm) cap = two_per_sm;
+    if (cap < 256) cap = 256;
     return cap;
 }
 

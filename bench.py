@@ -261,28 +261,29 @@ def run_gpu_arm(args):
 
     # ---- end to end: host (pinned) particles, copies inside the timed region --------------------------
     e2e = None
-    try:
-        host = torch.empty((N, 3), dtype=torch.float32, pin_memory=True)
-        pinned = True
-    except Exception:
-        host = torch.empty((N, 3), dtype=torch.float32)
-        pinned = False
-    host.copy_(pos)
-    torch.cuda.synchronize()
-    del pos
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1):
-        res_h = step(host)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res_h = step(host)
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-    d2h = sum(np.asarray(res_h[k]).nbytes for k in ('power', 'N_mode', 'k_avg', 'poles', 'N_mode_poles'))
-    e2e = {'value': e2e_ms, 'unit': 'ms', 'h2d_bytes_per_step': int(N * 12), 'd2h_bytes_per_step': int(d2h),
-           'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
-    del host
+    if not args.no_e2e:
+        try:
+            host = torch.empty((N, 3), dtype=torch.float32, pin_memory=True)
+            pinned = True
+        except Exception:
+            host = torch.empty((N, 3), dtype=torch.float32)
+            pinned = False
+        host.copy_(pos)
+        torch.cuda.synchronize()
+        del pos
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(1):
+            res_h = step(host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res_h = step(host)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+        d2h = sum(np.asarray(res_h[k]).nbytes for k in ('power', 'N_mode', 'k_avg', 'poles', 'N_mode_poles'))
+        e2e = {'value': e2e_ms, 'unit': 'ms', 'h2d_bytes_per_step': int(N * 12), 'd2h_bytes_per_step': int(d2h),
+               'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
+        del host
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peak, peak_src = peaks()
@@ -333,6 +334,7 @@ def main():
     ap.add_argument('--nparticles', type=int, default=0, help='override the particle count (testing only)')
     ap.add_argument('--nmesh', type=int, default=0, help='override nmesh (testing only)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)

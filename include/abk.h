@@ -113,8 +113,10 @@ int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t 
  * flushes the tile (+1-cell halo) to the grid with float reductions.  The grid is accumulated
  * into, never zeroed (tsc.py:45-50).
  *   nseg segments: records_seg_h[s] / tile_starts_seg_h[s] (host arrays of device pointers) as
- *   produced by abk_tsc_bucket with the SAME grid shape, box and offset; seg_counts_h[s] = N of
- *   segment s (sizes the shared-memory particle capacity).
+ *   produced by abk_tsc_bucket with the SAME grid shape and box; seg_counts_h[s] = N of segment s
+ *   (sizes the shared-memory particle capacity).  `offset` may differ from the bucketing offset
+ *   (interlacing: bucket once at offset 0, deposit at 0 and at half a cell): a particle whose cell
+ *   at `offset` lies outside the tile it was bucketed in is deposited with 27 direct reductions.
  *   Single GPU: x_lo = 0, nxe = nx, the grid holds nx planes and x wraps periodically.
  *   Slab mode : the grid holds nxe+2 planes: plane 0 is the ghost plane x_lo-1, planes 1..nxe are
  *   x_lo..x_lo+nxe-1, plane nxe+1 is the ghost plane x_lo+nxe (no wrap in x). */
@@ -225,8 +227,14 @@ typedef struct abk_bin_request {
     int32_t pole_ell[ABK_MAX_POLES];
     unsigned long long *counts;
     double *sum_p, *sum_k, *sum_poles;
+    /* optional device scratch of abk_power_bin_scratch_bytes(): lets the kernel spread its
+     * reductions over replicated sum tables (less same-address contention); NULL = reduce straight
+     * into the outputs */
+    void *scratch;
+    size_t scratch_bytes;
 } abk_bin_request;
 
+int abk_power_bin_scratch_bytes(int Nk, int Nmu, int Np, size_t *bytes);
 int abk_power_bin(abk_ctx *ctx, const abk_bin_request *req_h);
 
 /* ---- multi-GPU helpers (x-slab sharded mesh) ------------------------------------------------ */
