@@ -147,7 +147,8 @@ extern "C" int64_t abk_ctx_launch_count(abk_ctx *ctx) { return ctx ? ctx->launch
 extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
 {
     ABK_REQUIRE(ctx != nullptr, "null context");
-    ABK_REQUIRE(capacity == 0 || (capacity >= 256 && capacity <= 12288), "tile capacity %d out of range", capacity);
+    const int cap = capacity & 0xffff;  // bits 16..18: deposit kernel variant (experiments), 0 = default
+    ABK_REQUIRE(cap == 0 || (cap >= 256 && cap <= 12288), "tile capacity %d out of range", cap);
     ctx->tile_capacity = capacity;
     return ABK_OK;
 }

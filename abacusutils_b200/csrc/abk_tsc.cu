@@ -152,9 +152,15 @@ struct SegList {
     const uint32_t *starts[ABK_MAX_SEGMENTS];
 };
 
-static size_t deposit_smem_bytes(int cap)
+// PRE : 32-byte records with precomputed x/y weights (fewer instructions in the divergent loop)
+//       vs 16-byte (dx,dy,dz,W) records + u16 links (less shared memory -> more resident CTAs)
+// PRIV: private per-warp slabs (no barriers in the main loop) vs one shared output tile with a
+//       block barrier after every row phase
+static size_t deposit_smem_bytes(int cap, bool pre, bool priv)
 {
-    return (size_t)ABK_TY * SLAB_WORDS * 4 + (size_t)NCELL * 4 + (size_t)cap * 32 + 64;
+    const size_t out = priv ? (size_t)ABK_TY * SLAB_WORDS * 4 : (size_t)OUT_N * 4;
+    const size_t rec = pre ? (size_t)cap * 32 : (size_t)cap * 16 + (size_t)cap * 2;
+    return out + (size_t)NCELL * 4 + rec + 64;
 }
 
 // tsc.py:442-451: the three 1-D TSC weights for cells i-1, i, i+1 given d = i - p
@@ -169,7 +175,8 @@ __device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
 // Add one finished x-plane of this lane's register window to the warp's private slab.
 // S[b][c]: contribution of cell (row w, z = lane) to row w-1+b, cell z-1+c.  Lane z receives the
 // c=+1 term of lane z-1 and the c=-1 term of lane z+1; the two halo cells are lanes 0 / 31's.
-__device__ __forceinline__ void emit_plane(float *__restrict__ slab, const float (&S)[3][3], int x, int lane)
+__device__ __forceinline__ void emit_plane(float *__restrict__ slab, const float (&S)[3][3], int x, int lane,
+                                           bool first)
 {
     float *plane = slab + (x + 1) * SLAB_PLANE;
 #pragma unroll
@@ -178,9 +185,15 @@ __device__ __forceinline__ void emit_plane(float *__restrict__ slab, const float
         const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
         const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
         float *row = plane + b * OUT_Z;
-        row[lane + 1] += v;
-        if (lane == 0) row[0] += S[b][0];
-        if (lane == 31) row[OUT_Z - 1] += S[b][2];
+        if (first) {  // the first pass over a tile writes every slab entry exactly once: no zero-fill, no RMW
+            row[lane + 1] = v;
+            if (lane == 0) row[0] = S[b][0];
+            if (lane == 31) row[OUT_Z - 1] = S[b][2];
+        } else {
+            row[lane + 1] += v;
+            if (lane == 0) row[0] += S[b][0];
+            if (lane == 31) row[OUT_Z - 1] += S[b][2];
+        }
     }
 }
 
@@ -213,13 +226,34 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
     }
 }
 
-__global__ void __launch_bounds__(DEP_THREADS, 2)
+// shared-tile variant of emit_plane: rows of different warps are distinct within a phase (b), not
+// across phases, hence the block barrier after each phase
+__device__ __forceinline__ void emit_plane_shared(float *__restrict__ out, const float (&S)[3][3], int x, int wy, int lane)
+{
+    float *plane = out + (x + 1) * (OUT_Y * OUT_Z);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
+        const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
+        const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
+        float *row = plane + (wy + b) * OUT_Z;
+        row[lane + 1] += v;
+        if (lane == 0) row[0] += S[b][0];
+        if (lane == 31) row[OUT_Z - 1] += S[b][2];
+        __syncthreads();
+    }
+}
+
+template <bool PRE, bool PRIV>
+__global__ void __launch_bounds__(DEP_THREADS, PRE ? 2 : (PRIV ? 3 : 4))
 tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *slabs = reinterpret_cast<float *>(smem_raw);
-    uint32_t *head = reinterpret_cast<uint32_t *>(slabs + ABK_TY * SLAB_WORDS);
-    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);
+    constexpr int OUT_WORDS = PRIV ? ABK_TY * SLAB_WORDS : OUT_N;
+    float *outbuf = reinterpret_cast<float *>(smem_raw);
+    uint32_t *head = reinterpret_cast<uint32_t *>(outbuf + OUT_WORDS);
+    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);  // (OUT_WORDS + NCELL) * 4 is a multiple of 16
+    uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);  // !PRE only
     __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
     __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
 
@@ -239,40 +273,60 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
 
-    for (int i = tid; i < ABK_TY * SLAB_WORDS; i += DEP_THREADS) slabs[i] = 0.0f;
-    float *myslab = slabs + wy * SLAB_WORDS;
+    float *myslab = outbuf + wy * SLAB_WORDS;  // PRIV only
+    if (!PRIV)
+        for (int i = tid; i < OUT_N; i += DEP_THREADS) outbuf[i] = 0.0f;
 
     for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
         const int m = (int)min((uint32_t)cap, total - chunk0);
+        const bool first = (chunk0 == 0);
         for (int c = tid; c < NCELL; c += DEP_THREADS) head[c] = NIL;
         __syncthreads();
-        // ---- lane <-> particle: weights once per particle, per-cell lists ------------------------
-        for (int v = tid; v < m; v += DEP_THREADS) {
-            uint32_t u = chunk0 + v;
-            int s = 0;
-            while (u >= seg_cnt[s]) { u -= seg_cnt[s]; s++; }
-            const float4 r = __ldcs(seg_rec[s] + seg_beg[s] + u);
-            int cx, cy, cz;
-            float dx, dy, dz;
-            cell_of(r.x, P.off, P.inv_hx, P.nx, cx, dx);
-            cell_of(r.y, P.off, P.inv_hy, P.ny, cy, dy);
-            cell_of(r.z, P.off, P.inv_hz, P.nz, cz, dz);
-            int lx = cx - P.x_lo;
-            if (lx < 0) lx += P.nx;
-            lx -= x0;
-            int ly = cy - y0, lz = cz - z0;
-            if (ly < 0) ly += P.ny;  // the shifted cell may have wrapped around the box edge
-            if (lz < 0) lz += P.nz;
-            if ((unsigned)lx < (unsigned)ABK_TX && (unsigned)ly < (unsigned)ABK_TY && (unsigned)lz < (unsigned)ABK_TZ) {
-                float wxm, wx0, wxp, wym, wy0, wyp;
-                tsc_w(dx, wxm, wx0, wxp);
-                tsc_w(dy, wym, wy0, wyp);
-                const int c = (lx * ABK_TY + ly) * ABK_TZ + lz;
-                srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
-                const uint32_t old = atomicExch(&head[c], (uint32_t)v);
-                srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
-            } else {
-                deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+        // ---- lane <-> particle: per-cell lists (and, PRE, the x/y weights once per particle) -------
+        for (int v0 = tid; v0 < m; v0 += 4 * DEP_THREADS) {
+            float4 rr[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // issue the (streaming) record loads of four particles first
+                const int v = v0 + q * DEP_THREADS;
+                if (v < m) {
+                    uint32_t u = chunk0 + v;
+                    int s = 0;
+                    while (u >= seg_cnt[s]) { u -= seg_cnt[s]; s++; }
+                    rr[q] = __ldcs(seg_rec[s] + seg_beg[s] + u);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int v = v0 + q * DEP_THREADS;
+                if (v >= m) break;
+                const float4 r = rr[q];
+                int cx, cy, cz;
+                float dx, dy, dz;
+                cell_of(r.x, P.off, P.inv_hx, P.nx, cx, dx);
+                cell_of(r.y, P.off, P.inv_hy, P.ny, cy, dy);
+                cell_of(r.z, P.off, P.inv_hz, P.nz, cz, dz);
+                int lx = cx - P.x_lo;
+                if (lx < 0) lx += P.nx;
+                lx -= x0;
+                int ly = cy - y0, lz = cz - z0;
+                if (ly < 0) ly += P.ny;  // the shifted cell may have wrapped around the box edge
+                if (lz < 0) lz += P.nz;
+                if ((unsigned)lx < (unsigned)ABK_TX && (unsigned)ly < (unsigned)ABK_TY && (unsigned)lz < (unsigned)ABK_TZ) {
+                    const int c = (lx * ABK_TY + ly) * ABK_TZ + lz;
+                    if (PRE) {
+                        float wxm, wx0, wxp, wym, wy0, wyp;
+                        tsc_w(dx, wxm, wx0, wxp);
+                        tsc_w(dy, wym, wy0, wyp);
+                        srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
+                        const uint32_t old = atomicExch(&head[c], (uint32_t)v);
+                        srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
+                    } else {
+                        srec[v] = make_float4(dx, dy, dz, r.w);
+                        next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+                    }
+                } else {
+                    deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+                }
             }
         }
         __syncthreads();
@@ -287,49 +341,83 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
         for (int cx = 0; cx < ABK_TX; cx++) {
             uint32_t i = head[(cx * ABK_TY + wy) * ABK_TZ + lane];
             while (i != NIL) {
-                const float4 A = srec[2 * i], B = srec[2 * i + 1];
-                i = __float_as_uint(B.w);
-                float wz[3];
-                tsc_w(A.w, wz[0], wz[1], wz[2]);
-                const float wyW[3] = {B.x, B.y, B.z};
+                float wx[3], wyW[3], wz[3];
+                if (PRE) {
+                    const float4 A = srec[2 * i], B = srec[2 * i + 1];
+                    i = __float_as_uint(B.w);
+                    wx[0] = A.x; wx[1] = A.y; wx[2] = A.z;
+                    wyW[0] = B.x; wyW[1] = B.y; wyW[2] = B.z;
+                    tsc_w(A.w, wz[0], wz[1], wz[2]);
+                } else {
+                    const float4 r = srec[i];
+                    const uint16_t nxt = next16[i];
+                    i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
+                    tsc_w(r.x, wx[0], wx[1], wx[2]);
+                    tsc_w(r.y, wyW[0], wyW[1], wyW[2]);
+                    tsc_w(r.z, wz[0], wz[1], wz[2]);
+                    wyW[0] *= r.w; wyW[1] *= r.w; wyW[2] *= r.w;
+                }
 #pragma unroll
                 for (int b = 0; b < 3; b++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const float t = wyW[b] * wz[c];
-                        S0[b][c] = fmaf(A.x, t, S0[b][c]);
-                        S1[b][c] = fmaf(A.y, t, S1[b][c]);
-                        S2[b][c] = fmaf(A.z, t, S2[b][c]);
+                        S0[b][c] = fmaf(wx[0], t, S0[b][c]);
+                        S1[b][c] = fmaf(wx[1], t, S1[b][c]);
+                        S2[b][c] = fmaf(wx[2], t, S2[b][c]);
                     }
             }
-            emit_plane(myslab, S0, cx - 1, lane);
+            if (PRIV) emit_plane(myslab, S0, cx - 1, lane, first);
+            else emit_plane_shared(outbuf, S0, cx - 1, wy, lane);
 #pragma unroll
             for (int b = 0; b < 3; b++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
         }
-        emit_plane(myslab, S0, ABK_TX - 1, lane);
-        emit_plane(myslab, S1, ABK_TX, lane);
-        __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
+        if (PRIV) {
+            emit_plane(myslab, S0, ABK_TX - 1, lane, first);
+            emit_plane(myslab, S1, ABK_TX, lane, first);
+            __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
+        } else {
+            emit_plane_shared(outbuf, S0, ABK_TX - 1, wy, lane);
+            emit_plane_shared(outbuf, S1, ABK_TX, wy, lane);
+        }
     }
 
-    // ---- merge the 8 private slabs and flush tile + halo with float reductions ---------------------
+    // ---- flush tile + halo with float reductions -----------------------------------------------------
+    // Warp w owns output rows oy = w (and oy = 8 + w for w < 2) of every x-plane; lanes on z, so the
+    // reductions of one instruction hit 32 consecutive floats.  Everything that does not depend on
+    // the plane (row pointers of the <= 3 contributing slabs, wrapped y/z indices) is hoisted.
     const int64_t sx = (int64_t)P.ny * ldz;
-    for (int i = tid; i < OUT_N; i += DEP_THREADS) {
-        const int oz = i % OUT_Z, oy = (i / OUT_Z) % OUT_Y, ox = i / (OUT_Z * OUT_Y);
-        float v = 0.0f;
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-            const int w = oy - b;
-            if (w >= 0 && w < ABK_TY) v += slabs[w * SLAB_WORDS + ox * SLAB_PLANE + b * OUT_Z + oz];
-        }
-        if (v == 0.0f) continue;
-        int64_t gx;
-        if (slab) gx = x0 + ox;  // grid plane 0 is the ghost plane x_lo-1
-        else gx = abk_wrap_cell(x0 + ox - 1, P.nx);
+    const int gz = abk_wrap_cell(z0 + lane, P.nz);
+    const int ozh = lane ? OUT_Z - 1 : 0;
+    const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
+    for (int oy = wy; oy < OUT_Y; oy += ABK_TY) {
         const int gy = abk_wrap_cell(y0 + oy - 1, P.ny);
-        const int gz = abk_wrap_cell(z0 + oz - 1, P.nz);
-        atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gz, v);
+        // PRIV: contributing (warp, row) pairs: w = oy - b for b = 0..2 with 0 <= w < 8
+        const bool ok0 = oy < ABK_TY, ok1 = oy >= 1 && oy - 1 < ABK_TY, ok2 = oy >= 2;
+        const float *p0 = outbuf + (ok0 ? oy : 0) * SLAB_WORDS;
+        const float *p1 = outbuf + (ok1 ? oy - 1 : 0) * SLAB_WORDS + OUT_Z;
+        const float *p2 = outbuf + (ok2 ? oy - 2 : 0) * SLAB_WORDS + 2 * OUT_Z;
+        int gx = slab ? x0 : abk_wrap_cell(x0 - 1, P.nx);
+        for (int ox = 0; ox < OUT_X; ox++) {
+            float v = 0.0f, vh = 0.0f;
+            if (PRIV) {
+                const int o = ox * SLAB_PLANE;
+                if (ok0) { v += p0[o + lane + 1]; if (lane < 2) vh += p0[o + ozh]; }
+                if (ok1) { v += p1[o + lane + 1]; if (lane < 2) vh += p1[o + ozh]; }
+                if (ok2) { v += p2[o + lane + 1]; if (lane < 2) vh += p2[o + ozh]; }
+            } else {
+                const float *r = outbuf + (ox * OUT_Y + oy) * OUT_Z;
+                v = r[lane + 1];
+                if (lane < 2) vh = r[ozh];
+            }
+            float *dst = grid + gx * sx + (int64_t)gy * ldz;
+            if (v != 0.0f) atomicAdd(dst + gz, v);
+            if (lane < 2 && vh != 0.0f) atomicAdd(dst + gzh, vh);
+            gx++;
+            if (!slab && gx >= P.nx) gx -= P.nx;
+        }
     }
 }
 
@@ -554,16 +642,21 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
     return ABK_OK;
 }
 
-static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles)
+// kernel variant: bit 0 = PRE, bit 1 = PRIV (abk_ctx_set_tile_capacity's high bits select it for experiments)
+static int g_deposit_variant = -1;
+
+static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int per_sm)
 {
-    if (ctx->tile_capacity) return ctx->tile_capacity;
+    if (ctx->tile_capacity & 0xffff) return ctx->tile_capacity & 0xffff;
     // mean occupancy + 5 sigma (Poisson), so a uniform catalogue needs one pass per tile; capped so
-    // that two CTAs stay resident per SM (denser tiles simply take several passes)
+    // that `per_sm` CTAs stay resident per SM (denser tiles simply take several passes)
     const double mean = ntiles > 0 ? (double)n_total / (double)ntiles : 0.0;
     const double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
     int cap = (int)((want + 63.0) / 64.0) * 64;
-    const int two_per_sm = (int)(((size_t)(ctx->smem_optin + 1024) / 2 - 1024 - deposit_smem_bytes(0)) / 32) / 64 * 64;
-    if (cap > two_per_sm) cap = two_per_sm;
+    const size_t per_cta = (size_t)(ctx->smem_optin + 1024) / per_sm - 1024;
+    const size_t fixed = deposit_smem_bytes(0, pre, priv);
+    const int fit = (int)((per_cta - fixed) / (pre ? 32 : 18)) / 64 * 64;
+    if (cap > fit) cap = fit;
     if (cap < 256) cap = 256;
     return cap;
 }
@@ -588,11 +681,19 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
         segs.starts[s] = tile_starts_seg_h[s];
         n_total += seg_counts_h ? seg_counts_h[s] : 0;
     }
-    const int cap = pick_capacity(ctx, n_total, g.ntiles);
-    const size_t smem = deposit_smem_bytes(cap);
+    int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
+    const bool pre = variant ? ((variant - 1) & 1) : false;
+    const bool priv = variant ? (((variant - 1) >> 1) & 1) : false;
+    const int per_sm = pre ? 2 : (priv ? 3 : 4);
+    const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, per_sm);
+    const size_t smem = deposit_smem_bytes(cap, pre, priv);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
-    ABK_CHECK_CUDA(cudaFuncSetAttribute(tsc_tile_deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, tsc_tile_deposit_kernel<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
+    void (*kern)(SegList, float *, TscParams, int64_t, int, int) =
+        pre ? (priv ? tsc_tile_deposit_kernel<true, true> : tsc_tile_deposit_kernel<true, false>)
+            : (priv ? tsc_tile_deposit_kernel<false, true> : tsc_tile_deposit_kernel<false, false>);
+    ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
+    (void)g_deposit_variant;
     return ABK_OK;
 }
 

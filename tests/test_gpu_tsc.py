@@ -205,3 +205,39 @@ def test_partition(tsc, seed, npartition, sort):
         assert np.array_equal(got, want)
         if sort:
             assert np.all(np.diff(ppart[a:b, coord]) >= 0)
+
+
+def test_deposit_with_foreign_bucket_offset(oracle):
+    """abk_tsc_deposit_tiles accepts records bucketed at another offset (particles whose cell leaves
+    their tile take the direct-reduction path); result must equal the plain deposit at that offset."""
+    import ctypes as C
+
+    import torch
+
+    from abacusutils_b200._lib import Engine, check, ptr
+
+    rng = np.random.default_rng(99)
+    N, box, n = 150000, 300.0, 48
+    pos = rng.random((N, 3), dtype='f4') * np.float32(box)
+    w = rng.random(N, dtype='f4')
+    eng = Engine.get()
+    eng.bind_stream()
+    lib = eng.lib
+    pd, wd = eng.to_device(pos), eng.to_device(w)
+    ntiles = C.c_int64()
+    check(lib.abk_tsc_num_tiles(n, n, n, C.byref(ntiles)))
+    nb = C.c_size_t()
+    check(lib.abk_tsc_bucket_scratch_bytes(N, n, n, n, C.byref(nb)))
+    scr = torch.empty(nb.value, dtype=torch.uint8, device='cuda')
+    rec = torch.empty(N * 16, dtype=torch.uint8, device='cuda')
+    st = torch.empty(ntiles.value + 1, dtype=torch.int32, device='cuda')
+    check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), N, n, n, n, box, 0.0, 1, ptr(rec), ptr(st), ptr(scr), scr.numel()))
+    for off in (0.5 * box / n, -0.3 * box / n, 2.2 * box / n):
+        grid = torch.zeros((n, n, n), device='cuda')
+        recs = (C.c_void_p * 1)(rec.data_ptr())
+        sts = (C.c_void_p * 1)(st.data_ptr())
+        cnts = (C.c_int64 * 1)(N)
+        check(lib.abk_tsc_deposit_tiles(eng.ctx, 1, recs, sts, cnts, ptr(grid), n, n, n, n, box, off, 0, n))
+        ref = np.zeros((n, n, n), dtype=np.float32)
+        oracle.tsc_scatter_serial(pos, ref, box, weights=w, offset=off)
+        assert np.allclose(grid.cpu().numpy(), ref, rtol=1e-5, atol=1e-5), off
