@@ -233,7 +233,7 @@ class _Painter:
             recs = VP(*[records[o].data_ptr() + a * 16 for a, _ in chunks])
             sts = VP(*[starts[o].data_ptr() + s * starts_stride * 4 for s in range(nseg)])
             check(lib.abk_tsc_deposit_tiles(eng.ctx, nseg, recs, sts, counts, ptr(grids[o]), n, n, n, ldz, self.L,
-                                            float(off), 0, n))
+                                            float(off), 0, 0, n))
         return grids
 
     def normalize_fft(self, grid, tot_weight):

@@ -68,7 +68,7 @@ __device__ __forceinline__ bool tile_of(const TscParams &P, float x, float y, fl
 
 // Four particles per thread: 3 x 128-bit loads of positions (AoS float[N][3]), then all four tile
 // atomics are issued back to back (independent, so their L2 round trips overlap), then the stores.
-template <bool SCATTER>
+template <bool SCATTER, bool REC4>
 __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict__ pos, const float *__restrict__ w,
                                                          int64_t N, TscParams P, uint32_t *__restrict__ counts,
                                                          float4 *__restrict__ records, int vec_ok,
@@ -79,8 +79,17 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
          g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t base = g * 4;
         float c[12];
+        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         const int cnt = (int)min((int64_t)4, N - base);
-        if (vec_ok && cnt == 4) {
+        if (REC4) {  // input already is (x,y,z,w) records (routed particles of a sharded run)
+            const float4 *p4 = reinterpret_cast<const float4 *>(pos) + base;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 1.f);
+                if (q < cnt) r = __ldcs(p4 + q);
+                c[3 * q] = r.x; c[3 * q + 1] = r.y; c[3 * q + 2] = r.z; wv[q] = r.w;
+            }
+        } else if (vec_ok && cnt == 4) {
             const float4 *p4 = reinterpret_cast<const float4 *>(pos + 3 * base);
             const float4 a = __ldcs(p4), b = __ldcs(p4 + 1), d = __ldcs(p4 + 2);
             c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
@@ -89,8 +98,7 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
 #pragma unroll
             for (int q = 0; q < 12; q++) c[q] = (q < 3 * cnt) ? __ldcs(pos + 3 * base + q) : 0.0f;
         }
-        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-        if (SCATTER && w) {
+        if (!REC4 && SCATTER && w) {
             if (vec_ok && cnt == 4) {
                 const float4 t = __ldcs(reinterpret_cast<const float4 *>(w + base));
                 wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
@@ -467,6 +475,49 @@ __global__ void __launch_bounds__(256) wrap_inplace_kernel(float *__restrict__ p
     if (n_changed && changed) atomicAdd(n_changed, changed);
 }
 
+// ---- particle routing for an x-slab sharded mesh -------------------------------------------------------
+// owner(p) = rank r with xsplit[r] <= cell_x(p) < xsplit[r+1], cell_x = rint(x * f32(nx/box)) mod nx (the
+// centre cell of the UNSHIFTED cloud; the half-cell-shifted cloud is handled with one more ghost plane).
+// Warp-aggregated counting sort into (x,y,z,w) records grouped by owner.
+struct RouteSplit { int v[65]; };
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) route_kernel(const float *__restrict__ pos, const float *__restrict__ w, int64_t N,
+                                                    float inv_hx, int nx, double box, int wrap, int nranks, RouteSplit xs,
+                                                    unsigned long long *__restrict__ counts, float4 *__restrict__ out)
+{
+    __shared__ int s_xs[65];
+    for (int t = threadIdx.x; t <= nranks; t += blockDim.x) s_xs[t] = xs.v[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t nround = (N + 31) / 32 * 32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += (int64_t)gridDim.x * blockDim.x) {
+        int owner = -1;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < N) {
+            x = pos[3 * i]; y = pos[3 * i + 1]; z = pos[3 * i + 2];
+            if (wrap) { x = wrap_coord(x, box); y = wrap_coord(y, box); z = wrap_coord(z, box); }
+            int cx;
+            float d;
+            cell_of(x, 0.0f, inv_hx, nx, cx, d);
+            int lo = 0, hi = nranks - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_xs[mid] <= cx) lo = mid; else hi = mid - 1;
+            }
+            owner = lo;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        if (owner < 0) continue;
+        const int leader = __ffs(peers) - 1;
+        const int rank_in = __popc(peers & ((1u << lane) - 1u));
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&counts[owner], (unsigned long long)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (SCATTER) out[base + rank_in] = make_float4(x, y, z, w ? w[i] : 1.0f);
+    }
+}
+
 // ---- partition_parallel (tsc.py:259-384) ---------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) partition_kernel(const float *__restrict__ pos, const float *__restrict__ w,
@@ -571,6 +622,37 @@ extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int
     return ABK_OK;
 }
 
+extern "C" int abk_route_particles(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, double box,
+                                   int wrap, int nranks, const int32_t *xsplit_h, void *records_out,
+                                   int64_t *counts_h)
+{
+    ABK_REQUIRE(ctx && (pos || N == 0) && N >= 0 && nranks >= 1 && nranks <= 64 && xsplit_h && counts_h,
+                "abk_route_particles: bad arguments");
+    ABK_REQUIRE(xsplit_h[0] == 0 && xsplit_h[nranks] == nx, "abk_route_particles: xsplit must run from 0 to nx");
+    RouteSplit xs;
+    for (int r = 0; r <= nranks; r++) xs.v[r] = xsplit_h[r];
+    unsigned long long *counts = ctx->d_scalars + 8;  // 2 x 64 slots would not fit: use 8..39 / 40..
+    ABK_REQUIRE(nranks <= 24, "abk_route_particles: at most 24 ranks per node supported");
+    unsigned long long *cursors = ctx->d_scalars + 8 + 24;
+    ABK_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 48, ctx->stream));
+    const float inv_hx = (float)(nx / box);
+    unsigned long long h[24];
+    if (N > 0) {
+        const int blocks = grid_for(ctx, N, 256, 16);
+        ABK_LAUNCH(ctx, ABK_K_PART_HIST, route_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, inv_hx, nx, box, wrap, nranks, xs, counts, nullptr));
+    }
+    ABK_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(unsigned long long) * nranks, cudaMemcpyDeviceToHost, ctx->stream));
+    ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned long long run = 0, start[24];
+    for (int r = 0; r < nranks; r++) { counts_h[r] = (int64_t)h[r]; start[r] = run; run += h[r]; }
+    if (N > 0 && records_out) {
+        ABK_CHECK_CUDA(cudaMemcpyAsync(cursors, start, sizeof(unsigned long long) * nranks, cudaMemcpyHostToDevice, ctx->stream));
+        const int blocks = grid_for(ctx, N, 256, 16);
+        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, route_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, inv_hx, nx, box, wrap, nranks, xs, cursors, (float4 *)records_out));
+    }
+    return ABK_OK;
+}
+
 extern "C" int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles)
 {
     ABK_REQUIRE(ntiles && nx > 0 && ny > 0 && nz > 0, "abk_tsc_num_tiles: bad arguments");
@@ -586,7 +668,7 @@ extern "C" int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, s
 }
 
 static int bucket_impl(abk_ctx *ctx, const float *pos, const float *w, int64_t N, const TscParams &P, void *records,
-                       uint32_t *tile_starts, void *scratch, size_t scratch_bytes)
+                       uint32_t *tile_starts, void *scratch, size_t scratch_bytes, bool rec4 = false)
 {
     const abk_tile_geom g = abk_make_geom(P.nxe, P.ny, P.nz);
     ABK_REQUIRE(g.ntiles < ((int64_t)1 << 31), "too many tiles (%lld)", (long long)g.ntiles);
@@ -601,13 +683,15 @@ static int bucket_impl(abk_ctx *ctx, const float *pos, const float *w, int64_t N
     if (N > 0) {
         const int vec_ok = (((uintptr_t)pos & 15) == 0) && (!w || ((uintptr_t)w & 15) == 0);
         const int blocks = grid_for(ctx, (N + 3) / 4, 256, 16);
-        ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped));
+        if (rec4) ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false, true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped));
+        else ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false, false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, nullptr, vec_ok, dropped));
         int rc = abk_inclusive_scan_u32(ctx, tile_starts, g.ntiles, scratch);
         if (rc) return rc;
         // sentinel tile_starts[ntiles] = number of bucketed particles = inclusive total
         ABK_CHECK_CUDA(cudaMemcpyAsync(tile_starts + g.ntiles, tile_starts + g.ntiles - 1, 4, cudaMemcpyDeviceToDevice,
                                        ctx->stream));
-        ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, tsc_bucket_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped));
+        if (rec4) ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, tsc_bucket_kernel<true, true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped));
+        else ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, tsc_bucket_kernel<true, false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, tile_starts, (float4 *)records, vec_ok, dropped));
     }
     return ABK_OK;
 }
@@ -623,9 +707,9 @@ extern "C" int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, in
     return bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
 }
 
-extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
-                                   double box, double offset, int wrap, int x_lo, int nxe, void *records,
-                                   uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
+extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int in_records, int nx,
+                                   int ny, int nz, double box, double offset, int wrap, int x_lo, int nxe,
+                                   void *records, uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
                                    unsigned long long *n_dropped_h)
 {
     ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket_slab: null argument");
@@ -633,7 +717,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
     int rc = make_params(P, nx, ny, nz, box, offset, wrap, x_lo, nxe);
     if (rc) return rc;
     ABK_CHECK_CUDA(cudaMemsetAsync(ctx->d_scalars + 1, 0, 8, ctx->stream));
-    rc = bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
+    rc = bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes, in_records != 0);
     if (rc) return rc;
     if (n_dropped_h) {
         ABK_CHECK_CUDA(cudaMemcpyAsync(n_dropped_h, ctx->d_scalars + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -642,8 +726,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
     return ABK_OK;
 }
 
-// kernel variant: bit 0 = PRE, bit 1 = PRIV (abk_ctx_set_tile_capacity's high bits select it for experiments)
-static int g_deposit_variant = -1;
+// kernel variant (PRE, PRIV): abk_ctx_set_tile_capacity's bits 16..18 select it for experiments
 
 static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int per_sm)
 {
@@ -664,14 +747,14 @@ static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bo
 extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
                                      const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h,
                                      float *grid, int nx, int ny, int nz, int64_t ldz, double box, double offset,
-                                     int x_lo, int nxe)
+                                     int slab, int x_lo, int nxe)
 {
     ABK_REQUIRE(ctx && grid && nseg >= 1 && nseg <= ABK_MAX_SEGMENTS, "abk_tsc_deposit_tiles: bad arguments");
+    ABK_REQUIRE(slab || (x_lo == 0 && nxe == nx), "abk_tsc_deposit_tiles: a periodic (non-slab) grid needs x_lo=0, nxe=nx");
     ABK_REQUIRE(ldz >= nz, "ldz %lld < nz %d", (long long)ldz, nz);
     TscParams P;
     int rc = make_params(P, nx, ny, nz, box, offset, 0, x_lo, nxe);
     if (rc) return rc;
-    const int slab = !(x_lo == 0 && nxe == nx);
     const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
     SegList segs;
     segs.nseg = nseg;
@@ -693,7 +776,6 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
             : (priv ? tsc_tile_deposit_kernel<false, true> : tsc_tile_deposit_kernel<false, false>);
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
-    (void)g_deposit_variant;
     return ABK_OK;
 }
 
@@ -746,7 +828,7 @@ extern "C" int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, i
         starts_h[s] = starts;
         cnt_h[s] = n;
     }
-    return abk_tsc_deposit_tiles(ctx, nseg, rec_h, starts_h, cnt_h, grid, nx, ny, nz, ldz, box, offset, 0, nx);
+    return abk_tsc_deposit_tiles(ctx, nseg, rec_h, starts_h, cnt_h, grid, nx, ny, nz, ldz, box, offset, 0, 0, nx);
 }
 
 extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx,

@@ -1,0 +1,470 @@
+"""
+Multi-GPU power spectrum: the mesh is sharded by x-planes over the ranks of a torch.distributed
+process group (one process per GPU, NCCL over NVLink/NVSwitch).  The reference has no distributed path
+(/root/reference/docs/tutorials/analysis/tsc.ipynb:21 "can't readily scale to multiple nodes"); this
+module extends ``calc_power`` to a sharded mesh with the four exchanges SURVEY.md 8(e) lists:
+
+  1. particle routing   -- all-to-all of (x,y,z,w) records to the rank owning the centre cell's x-plane
+  2. ghost planes       -- each rank deposits into its planes plus 1 ghost plane below and 2 above (the
+                           half-cell-shifted cloud reaches one plane further), sends them to its ring
+                           neighbours, which add them (abk_add_planes)
+  3. FFT transpose      -- local 2-D R2C over (y,z), slab -> pencil all-to-all (packed by
+                           abk_transpose_pack), local 1-D C2C along x; the spectrum stays in the pencil
+                           layout [x][y_local][kz]: the binning kernel takes the layout as strides
+  4. bin all-reduce     -- float64 / int64 sums of the (k,mu) bins and multipoles
+
+``calc_power(pos_local, ...)`` has the reference's signature; ``pos_local`` is THIS rank's share of the
+catalogue (any particles, they are routed).  Every rank returns the same table.
+
+The data-movement helpers take the process group and plain tensors, so the host logic is exercised on
+CPU with the gloo backend (tests/test_dist_cpu.py) -- the kernels themselves need a GPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+import time
+
+import numpy as np
+
+from ._lib import BinRequest, Engine, KMesh, check, ptr
+from .analysis import power_spectrum as ps
+from .analysis.tsc import padded_ldz
+
+
+# ------------------------------------------------------------------------------------------- plan
+class SlabPlan:
+    """x-plane ownership (slabs) and y-row ownership (pencils) of an n^3 mesh over `world` ranks.
+    Uneven splits are allowed (n need not be a multiple of world); every rank needs >= 2 planes."""
+
+    def __init__(self, n, world):
+        if world < 1 or n // world < 2:
+            raise ValueError(f'mesh size {n} is too small for {world} ranks (need >= 2 planes per rank)')
+        self.n = int(n)
+        self.world = int(world)
+        self.nzc = n // 2 + 1
+        self.xsplit = [r * n // world for r in range(world + 1)]
+        self.jsplit = list(self.xsplit)
+
+    def x_range(self, r):
+        return self.xsplit[r], self.xsplit[r + 1]
+
+    def nxl(self, r):
+        return self.xsplit[r + 1] - self.xsplit[r]
+
+    def nyl(self, r):
+        return self.jsplit[r + 1] - self.jsplit[r]
+
+    def owner_of_plane(self, ix):
+        return int(np.searchsorted(self.xsplit, ix % self.n, side='right') - 1)
+
+    def transpose_splits(self, r):
+        """(input_split_sizes, output_split_sizes) in complex elements for rank r's slab->pencil all-to-all."""
+        nxl, nyl, nzc = self.nxl(r), self.nyl(r), self.nzc
+        send = [nxl * self.nyl(q) * nzc for q in range(self.world)]
+        recv = [self.nxl(q) * nyl * nzc for q in range(self.world)]
+        return send, recv
+
+
+# ------------------------------------------------------------------------------------------- exchanges
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def exchange_counts(send_counts, group=None, device=None):
+    """all-to-all of per-destination counts -> per-source counts (lists of ints)."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    t = torch.tensor(list(send_counts), dtype=torch.int64, device=device)
+    out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(out, t, group=group)
+    return [int(v) for v in out.tolist()]
+
+
+def exchange_rows(rows, send_counts, recv_counts, group=None):
+    """Variable all-to-all of the rows of a 2-D tensor grouped by destination rank."""
+    import torch
+
+    dist = _dist()
+    out = torch.empty((int(sum(recv_counts)), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(out, rows, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
+                           group=group)
+    return out
+
+
+def exchange_ghost_planes(grid, nxl, add_planes, group=None):
+    """Ring exchange of the ghost planes of a slab grid laid out as
+        plane 0          : ghost  x_lo - 1        -> added to the LEFT neighbour's last owned plane
+        planes 1..nxl    : owned
+        planes nxl+1,+2  : ghosts x_lo+nxl, +1    -> added to the RIGHT neighbour's first two owned planes
+    `add_planes(dst_view, src)` performs dst += src (abk_add_planes on the GPU)."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo = grid[0:1]
+    hi = grid[nxl + 1:nxl + 3]
+    if world == 1:
+        add_planes(grid[nxl:nxl + 1], lo.clone())
+        add_planes(grid[1:3], hi.clone())
+        return
+    left, right = (rank - 1) % world, (rank + 1) % world
+    from_right = torch.empty_like(lo)   # the right neighbour's low ghost lands on my last owned plane
+    from_left = torch.empty_like(hi)    # the left neighbour's high ghosts land on my first two planes
+    gl = dist.get_global_rank(group, left) if group is not None else left
+    gr = dist.get_global_rank(group, right) if group is not None else right
+    ops = [dist.P2POp(dist.isend, lo.contiguous(), gl, group=group), dist.P2POp(dist.isend, hi.contiguous(), gr, group=group),
+           dist.P2POp(dist.irecv, from_right, gr, group=group), dist.P2POp(dist.irecv, from_left, gl, group=group)]
+    if world == 2:
+        # both neighbours are the same peer: order the two messages explicitly with tags via two rounds
+        ops = [dist.P2POp(dist.isend, lo.contiguous(), gl, group=group), dist.P2POp(dist.irecv, from_right, gr, group=group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        ops = [dist.P2POp(dist.isend, hi.contiguous(), gr, group=group), dist.P2POp(dist.irecv, from_left, gl, group=group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    add_planes(grid[nxl:nxl + 1], from_right)
+    add_planes(grid[1:3], from_left)
+
+
+def transpose_slab_to_pencil(packed, plan, rank, group=None):
+    """packed: complex64 1-D tensor holding, destination by destination, the blocks [nxl][nyl_q][nzc]
+    (abk_transpose_pack).  Returns the pencil [n][nyl][nzc] of this rank."""
+    import torch
+
+    dist = _dist()
+    send, recv = plan.transpose_splits(rank)
+    out = torch.empty(plan.n * plan.nyl(rank) * plan.nzc, dtype=packed.dtype, device=packed.device)
+    a, b = torch.view_as_real(packed), torch.view_as_real(out)
+    dist.all_to_all_single(b, a, output_split_sizes=recv, input_split_sizes=send, group=group)
+    return out.view(plan.n, plan.nyl(rank), plan.nzc)
+
+
+# ------------------------------------------------------------------------------------------- pipeline
+class DistEngine:
+    def __init__(self, group=None):
+        import torch
+
+        dist = _dist()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.eng = Engine.get(torch.cuda.current_device())
+        self.device = self.eng.device
+
+    # -- 1. routing -----------------------------------------------------------------------------------
+    def route(self, pos, w, plan, Lbox):
+        """Returns the (M,4) float32 records of the particles whose centre cell this rank owns."""
+        import torch
+
+        eng = self.eng
+        eng.bind_stream()
+        pos_d = eng.to_device(pos, torch.float32)
+        w_d = None if w is None else eng.to_device(w, torch.float32)
+        N = int(pos_d.shape[0])
+        xs = (C.c_int32 * (self.world + 1))(*plan.xsplit)
+        counts = (C.c_int64 * self.world)()
+        out = eng.scratch('route_out', max(N, 1) * 16)
+        check(eng.lib.abk_route_particles(eng.ctx, ptr(pos_d), ptr(w_d), N, plan.n, float(Lbox), 1, self.world, xs,
+                                          ptr(out), counts))
+        send_counts = [int(c) for c in counts]
+        rows = out[: N * 16].view(torch.float32).view(N, 4)
+        if self.world == 1:
+            return rows
+        recv_counts = exchange_counts(send_counts, self.group, self.device)
+        return exchange_rows(rows, send_counts, recv_counts, self.group)
+
+    # -- 2. deposit + ghosts ----------------------------------------------------------------------------
+    def paint_slab(self, records, plan, Lbox, offsets):
+        """Deposit this rank's records for every offset into slab grids [(nxl+3), n, ldz] and fold the ghosts."""
+        import torch
+
+        eng, n = self.eng, plan.n
+        lib = eng.lib
+        x_lo, x_hi = plan.x_range(self.rank)
+        nxl = x_hi - x_lo
+        ldz = padded_ldz(n)
+        M = int(records.shape[0])
+        grids = []
+        for off in offsets:
+            shifted = off != 0.0
+            nxe = nxl + (1 if shifted else 0)
+            grid = eng.zeros((nxl + 3, n, ldz), torch.float32)
+            if M > 0:
+                ntiles = C.c_int64()
+                check(lib.abk_tsc_num_tiles(nxe, n, n, C.byref(ntiles)))
+                nb = C.c_size_t()
+                check(lib.abk_tsc_bucket_scratch_bytes(M, nxe, n, n, C.byref(nb)))
+                scan_tmp = eng.scratch('bucket_scan', nb.value)
+                rec = eng.scratch('records_slab', M * 16)
+                starts = eng.scratch('starts_slab', (ntiles.value + 1) * 4)
+                dropped = C.c_ulonglong(0)
+                eng.bind_stream()
+                for a in range(0, M, 1 << 30):
+                    if a:
+                        raise NotImplementedError('more than 2^30 particles per rank')
+                check(lib.abk_tsc_bucket_slab(eng.ctx, ptr(records), None, M, 1, n, n, n, float(Lbox), float(off), 0,
+                                              x_lo, nxe, ptr(rec), ptr(starts), ptr(scan_tmp), scan_tmp.numel(),
+                                              C.byref(dropped)))
+                if dropped.value:
+                    raise RuntimeError(f'rank {self.rank}: {dropped.value} routed particles fall outside the slab')
+                recs = (C.c_void_p * 1)(rec.data_ptr())
+                sts = (C.c_void_p * 1)(starts.data_ptr())
+                cnts = (C.c_int64 * 1)(M)
+                check(lib.abk_tsc_deposit_tiles(eng.ctx, 1, recs, sts, cnts, ptr(grid), n, n, n, ldz, float(Lbox),
+                                                float(off), 1, x_lo, nxe))
+
+            def add_planes(dst, src):
+                eng.bind_stream()
+                check(lib.abk_add_planes(eng.ctx, ptr(dst), ptr(src.contiguous()), dst.shape[0], n, n, ldz))
+
+            exchange_ghost_planes(grid, nxl, add_planes, self.group)
+            grids.append(grid)
+        return grids
+
+    # -- 3. distributed FFT -------------------------------------------------------------------------------
+    def _plan(self, kind, *dims):
+        eng = self.eng
+        key = (kind,) + dims
+        if key not in eng._plans:
+            h, wb = C.c_void_p(), C.c_size_t()
+            fn = eng.lib.abk_fft_yz_plan_create if kind == 'yz' else eng.lib.abk_fft_x_plan_create
+            check(fn(eng.ctx, *dims, C.byref(h), C.byref(wb)))
+            eng._plans[key] = (h, int(wb.value))
+        return eng._plans[key]
+
+    def _exec(self, plan_h, wb, data_ptr):
+        eng = self.eng
+        work = eng.scratch('fftwork', wb)
+        eng.bind_stream()
+        check(eng.lib.abk_fft_exec_generic(eng.ctx, plan_h, C.c_void_p(data_ptr), ptr(work), work.numel()))
+
+    def fft_slab(self, grid, plan, n_total):
+        """Normalise the owned planes, 2-D FFT, transpose, 1-D FFT.  Returns the pencil [n][nyl][nzc] complex64."""
+        import torch
+
+        eng, n = self.eng, plan.n
+        nxl, nyl, nzc = plan.nxl(self.rank), plan.nyl(self.rank), plan.nzc
+        ldz = padded_ldz(n)
+        owned = grid[1:nxl + 1]
+        eng.bind_stream()
+        check(eng.lib.abk_normalize_field(eng.ctx, ptr(owned), nxl, n, n, ldz, float(n) ** 3, float(n_total)))
+        h, wb = self._plan('yz', nxl, n, n)
+        self._exec(h, wb, owned.data_ptr())
+        packed = eng.empty((nxl * n * nzc,), torch.complex64)
+        js = (C.c_int64 * (self.world + 1))(*plan.jsplit)
+        check(eng.lib.abk_transpose_pack(eng.ctx, ptr(owned), ptr(packed), nxl, n, nzc, self.world, js))
+        if self.world == 1:
+            pencil = packed.view(n, nyl, nzc)
+        else:
+            pencil = transpose_slab_to_pencil(packed, plan, self.rank, self.group)
+        h, wb = self._plan('x', n, nyl, nzc)
+        self._exec(h, wb, pencil.data_ptr())
+        return pencil
+
+    # -- 4. binning + all-reduce ---------------------------------------------------------------------------
+    def bin_pencils(self, plan, Lbox, kedges, muedges, poles, f1, f1s, f2, f2s, W_d, scale):
+        import torch
+
+        eng, n = self.eng, plan.n
+        dist = _dist()
+        kedges = np.asarray(kedges, dtype=np.float64)
+        muedges = np.asarray(muedges, dtype=np.float64)
+        poles = np.asarray(poles, dtype=np.int64).reshape(-1)
+        Nk, Nmu, Np = len(kedges) - 1, len(muedges) - 1, len(poles)
+        dk = 2.0 * np.pi / Lbox
+        kedges2 = ((kedges / dk) ** 2).astype(np.float32)
+        muedges2 = (muedges**2).astype(np.float32)
+        Nb = Nk * Nmu
+        tables = np.concatenate([kedges2, muedges2, ps.legendre_coefficients(poles).reshape(-1)]).astype(np.float32)
+        tables_d = eng.to_device(tables, torch.float32)
+        sums = eng.zeros((3 * Nb + Np * Nk,), torch.float64)
+        j0, j1 = plan.jsplit[self.rank], plan.jsplit[self.rank + 1]
+        nyl, nzc = j1 - j0, plan.nzc
+        req = BinRequest()
+        req.mesh = KMesh(n=n, nzc=nzc, i0=0, i1=n, j0=j0, j1=j1, stride_i=nyl * nzc, stride_j=nzc)
+        for name, t in (('f1', f1), ('f1s', f1s), ('f2', f2), ('f2s', f2s), ('W', W_d)):
+            setattr(req, name, None if t is None else t.data_ptr())
+        req.real_in = None
+        req.scale = float(scale)
+        req.finish = 1
+        base = tables_d.data_ptr()
+        req.kedges2 = base
+        req.muedges2 = base + 4 * (Nk + 1)
+        req.pole_coef = base + 4 * (Nk + 1 + Nmu + 1)
+        for ip in range(Np):
+            req.pole_ell[ip] = int(poles[ip])
+        req.Nk, req.Nmu, req.Np = Nk, Nmu, Np
+        sb = sums.data_ptr()
+        req.counts, req.sum_p, req.sum_k, req.sum_poles = sb, sb + 8 * Nb, sb + 16 * Nb, sb + 24 * Nb
+        nb = C.c_size_t()
+        check(eng.lib.abk_power_bin_scratch_bytes(Nk, Nmu, Np, C.byref(nb)))
+        rep = eng.scratch('bin_replicas', nb.value)
+        req.scratch, req.scratch_bytes = rep.data_ptr(), rep.numel()
+        eng.bind_stream()
+        check(eng.lib.abk_power_bin(eng.ctx, C.byref(req)))
+        if self.world > 1:
+            # counts are exact integers: reduce them as int64, the float sums as float64
+            cnt = sums[:Nb].view(torch.int64)
+            dist.all_reduce(cnt, group=self.group)
+            dist.all_reduce(sums[Nb:], group=self.group)
+        return ps._finalize_bins(sums, Nk, Nmu, poles, dk)
+
+
+def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste='TSC', nmesh=128, compensated=True,
+               interlaced=True, w=None, pos2=None, w2=None, poles=None, squeeze_mu_axis=True, nthread=1,
+               dtype=np.float32, group=None):
+    """Sharded ``calc_power`` (same parameters and result table as the single-GPU / reference function,
+    power_spectrum.py:1131-1319).  ``pos``/``w`` (and ``pos2``/``w2``) are this rank's share of the catalogue."""
+    import torch
+
+    dist = _dist()
+    de = DistEngine(group)
+    eng = de.eng
+    n = int(nmesh)
+    plan = SlabPlan(n, de.world)
+    ps._check_paste(paste)
+    if kbins is None:
+        kbins = nmesh
+    if k_max is None:
+        k_max = np.pi * nmesh / Lbox
+    return_mubins = mubins is not None
+    if mubins is None:
+        mubins = 1
+
+    def total(npart):
+        t = torch.tensor([npart], dtype=torch.int64, device=de.device)
+        if de.world > 1:
+            dist.all_reduce(t, group=group)
+        return int(t.item())
+
+    def field(p, wt):
+        ntot = total(len(p))
+        rec = de.route(p, wt, plan, Lbox)
+        offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
+        grids = de.paint_slab(rec, plan, Lbox, offsets)
+        return [de.fft_slab(g, plan, ntot) for g in grids], ntot
+
+    g1, N1 = field(pos, w)
+    g2, N2 = (field(pos2, w2) if pos2 is not None else (None, None))
+    meta = dict(Lbox=Lbox, logk=logk, paste=paste, nmesh=nmesh, compensated=compensated, interlaced=interlaced,
+                poles=poles, nthread=nthread, N_pos=N1, is_weighted=w is not None, field_dtype=dtype,
+                squeeze_mu_axis=squeeze_mu_axis, n_ranks=de.world)
+    if pos2 is not None:
+        meta['N_pos2'] = N2
+        meta['is_weighted2'] = w2 is not None
+    W = ps.get_W_compensated(Lbox, n, paste, interlaced) if compensated else None
+    W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
+    poles_arr = np.asarray(poles or [], dtype=np.int64)
+    kbins, mubins = ps.get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)
+    scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
+    binned = de.bin_pencils(plan, float(Lbox), kbins, mubins, poles_arr, g1[0], g1[1] if interlaced else None,
+                            None if g2 is None else g2[0], g2[1] if (g2 is not None and interlaced) else None, W_d,
+                            scale)
+    P = ps._package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
+    kbins, mubins = np.asarray(kbins), np.asarray(mubins)
+    res = dict(k_min=kbins[:-1], k_max=kbins[1:], k_mid=(kbins[1:] + kbins[:-1]) * 0.5, k_avg=P['k_avg'],
+               power=P['power'], N_mode=P['N_mode'])
+    if len(poles_arr) > 0:
+        res.update(poles=P['binned_poles'].T, N_mode_poles=P['N_mode_poles'])
+    if return_mubins:
+        mu_binc = (mubins[1:] + mubins[:-1]) * 0.5
+        res.update(mu_min=np.broadcast_to(mubins[:-1], res['power'].shape),
+                   mu_max=np.broadcast_to(mubins[1:], res['power'].shape),
+                   mu_mid=np.broadcast_to(mu_binc, res['power'].shape))
+    return ps._make_table(res, meta)
+
+
+# ------------------------------------------------------------------------------------------- bench (N > 1)
+def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
+    """bench.py's multi-GPU arm: strong scaling of the configs[2] workload over the ranks of one node."""
+    import os
+
+    import torch
+
+    dist = _dist()
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    eng = Engine.get(local_rank)
+    N, L, n = cfg['N'], cfg['L'], cfg['nmesh']
+    n_local = N // world + (1 if rank < N % world else 0)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(cfg['seed'] + 1000 * rank)
+    pos = torch.rand((n_local, 3), device='cuda', dtype=torch.float32, generator=gen)
+    pos *= L
+    kw = dict(kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=n, compensated=True, interlaced=True, poles=cfg['poles'])
+
+    def step(p):
+        return calc_power(p, L, **kw)
+
+    for _ in range(args.warmup):
+        res = step(pos)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step(pos)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device='cuda', dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True)
+            pinned = True
+        except Exception:
+            host = torch.empty((n_local, 3), dtype=torch.float32)
+            pinned = False
+        host.copy_(pos)
+        torch.cuda.synchronize()
+        del pos
+        step(host)
+        e2e_steps = max(1, min(args.steps, 3))
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res_h = step(host)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        d2h = sum(np.asarray(res_h[k]).nbytes for k in ('power', 'N_mode', 'k_avg', 'poles', 'N_mode_poles'))
+        e2e = {'value': float(t.item()), 'unit': 'ms', 'h2d_bytes_per_step': int(N * 12), 'd2h_bytes_per_step': int(d2h),
+               'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {
+            'metric': metric, 'value': float(ms.item()), 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': float(ms.item()), 'higher_is_better': False, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'parallelism': f'x-slab mesh sharding over {world} GPUs',
+                       'l2': 'inputs are larger than the 126 MB L2'},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * world),
+            'roofline': {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                         'peak_source': peak_src, 'note': 'per-kernel roofline is reported by the N=1 run'},
+            'cpu_baseline': None, 'mpart_per_s': N / float(ms.item()) / 1e3,
+            'N_mode_total': int(np.asarray(res['N_mode']).sum()),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -102,10 +102,21 @@ int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, int64_t N, in
 /* Slab mode (mesh sharded over GPUs by x-planes): only particles whose centre cell lies in planes
  * [x_lo, x_lo+nxe) (mod nx) are bucketed; tiles cover that x-range.  The number of particles that
  * fell outside is returned in *n_dropped_h (host; the call then synchronises the stream). */
-int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
-                        double box, double offset, int wrap, int x_lo, int nxe, void *records,
+int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int in_records, int nx, int ny,
+                        int nz, double box, double offset, int wrap, int x_lo, int nxe, void *records,
                         uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
                         unsigned long long *n_dropped_h);
+/* in_records != 0: `pos` points to float4 (x,y,z,w) records (as produced by abk_route_particles)
+ * instead of float[N][3] (+ w).
+ *
+ * Routing for a mesh sharded by x-planes: the owner of a particle is the rank whose plane range
+ * [xsplit_h[r], xsplit_h[r+1]) contains the centre cell of its unshifted cloud,
+ * rint(x * f32(nx/box)) mod nx.  Writes (x,y,z,w) records grouped by owner into records_out
+ * (float4[N]; may be NULL to only count) and the per-owner counts into counts_h (host,
+ * int64[nranks]); synchronises the stream.  The one-shot periodic wrap (tsc.py:219-226) is applied to
+ * the routed copies when `wrap` is set. */
+int abk_route_particles(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, double box, int wrap,
+                        int nranks, const int32_t *xsplit_h, void *records_out, int64_t *counts_h);
 
 /* tsc.py:394-507 `_tsc_scatter` (+ :229-256): 27-point TSC deposit of bucketed particles.
  * One CTA per tile builds per-cell particle lists in shared memory, accumulates each cell's
@@ -117,12 +128,14 @@ int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *w, int64_t 
  *   (sizes the shared-memory particle capacity).  `offset` may differ from the bucketing offset
  *   (interlacing: bucket once at offset 0, deposit at 0 and at half a cell): a particle whose cell
  *   at `offset` lies outside the tile it was bucketed in is deposited with 27 direct reductions.
- *   Single GPU: x_lo = 0, nxe = nx, the grid holds nx planes and x wraps periodically.
- *   Slab mode : the grid holds nxe+2 planes: plane 0 is the ghost plane x_lo-1, planes 1..nxe are
- *   x_lo..x_lo+nxe-1, plane nxe+1 is the ghost plane x_lo+nxe (no wrap in x). */
+ *   slab == 0 : x_lo = 0, nxe = nx, the grid holds nx planes and x wraps periodically.
+ *   slab != 0 : the records are those of abk_tsc_bucket_slab(x_lo, nxe); the grid holds nxe+2 planes:
+ *   plane 0 is the ghost plane x_lo-1, planes 1..nxe are x_lo..x_lo+nxe-1, plane nxe+1 is the ghost
+ *   plane x_lo+nxe (no wrap in x). */
 int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
                           const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h, float *grid,
-                          int nx, int ny, int nz, int64_t ldz, double box, double offset, int x_lo, int nxe);
+                          int nx, int ny, int nz, int64_t ldz, double box, double offset, int slab, int x_lo,
+                          int nxe);
 
 /* Convenience: bucket one segment and deposit it (what tsc_parallel does for device inputs).
  * scratch must hold abk_tsc_deposit_scratch_bytes(). */
