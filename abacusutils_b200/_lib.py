@@ -69,7 +69,7 @@ SIGNATURES = {
     'abk_route_particles': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, C.POINTER(C.c_int32), _vp,
                                    C.POINTER(_i64)]),
     'abk_tsc_deposit_tiles': (_i32, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _vp, _i32, _i32, _i32,
-                                     _i64, _dbl, _dbl, _i32, _i32, _i32]),
+                                     _i64, _dbl, _dbl, _dbl, _i32, _i32, _i32]),
     'abk_tsc_deposit_scratch_bytes': (_i32, [_i64, _i32, _i32, _i32, _psz]),
     'abk_tsc_deposit': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _dbl, _dbl, _i32, _vp, _sz]),
     'abk_tsc_deposit_naive': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _dbl, _dbl, _i32]),
@@ -83,6 +83,7 @@ SIGNATURES = {
     'abk_fft_exec_generic': (_i32, [_vp, _vp, _vp, _vp, _sz]),
     'abk_field_fft_finish': (_i32, [_vp, C.POINTER(KMesh), _vp, _vp, _vp, _flt]),
     'abk_raw_power': (_i32, [_vp, _vp, _vp, _vp, _i64]),
+    'abk_real_to_complex': (_i32, [_vp, _vp, _vp, _i64]),
     'abk_power_bin_scratch_bytes': (_i32, [_i32, _i32, _i32, _psz]),
     'abk_power_bin': (_i32, [_vp, C.POINTER(BinRequest)]),
     'abk_add_planes': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64]),

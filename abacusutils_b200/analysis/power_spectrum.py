@@ -181,12 +181,11 @@ class _Painter:
         check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
         scan_tmp = eng.scratch('bucket_scan', nb.value)
         starts_stride = (ntiles + 1 + 63) // 64 * 64
-        # One bucketing per offset.  (The tile kernel also accepts records bucketed at another offset --
-        # a particle whose cell leaves its tile is then deposited with 27 direct reductions -- but for the
-        # half-cell interlacing shift 13% of the particles would take that slow path; measured on B200 a
-        # second histogram+scatter is cheaper.)
-        records = [eng.scratch(f'records{tag}{o}', N * 16) for o in range(len(offsets))]
-        starts = [eng.scratch(f'starts{tag}{o}', nseg * starts_stride * 4) for o in range(len(offsets))]
+        # Particles are bucketed ONCE, by the tile of their cell at the first offset.  The deposit of the
+        # half-cell-shifted grid reuses the records: its tile kernel covers one more cell in x and y,
+        # which holds every particle whose cell moved by 0 or +1 (abk_tsc_deposit_tiles, bucket_offset).
+        records = eng.scratch(f'records{tag}', N * 16)
+        starts = eng.scratch(f'starts{tag}', nseg * starts_stride * 4)
 
         host = kind == 'host'
         if host:
@@ -218,22 +217,22 @@ class _Painter:
                 wd = None if wsrc is None else wsrc[a:b]
                 if not pd.is_contiguous():
                     pd = pd.contiguous()
-            for o, off in enumerate(offsets):
-                rec_ptr = records[o].data_ptr() + a * 16
-                st_ptr = starts[o].data_ptr() + s * starts_stride * 4
-                check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(off), int(bool(wrap)),
-                                         C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp), scan_tmp.numel()))
+            rec_ptr = records.data_ptr() + a * 16
+            st_ptr = starts.data_ptr() + s * starts_stride * 4
+            check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[0]),
+                                     int(bool(wrap)), C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp),
+                                     scan_tmp.numel()))
             if host:
                 done[slot].record(compute)
 
         VP = C.c_void_p * nseg
         I64 = C.c_int64 * nseg
         counts = I64(*[b - a for a, b in chunks])
+        recs = VP(*[records.data_ptr() + a * 16 for a, _ in chunks])
+        sts = VP(*[starts.data_ptr() + s * starts_stride * 4 for s in range(nseg)])
         for o, off in enumerate(offsets):
-            recs = VP(*[records[o].data_ptr() + a * 16 for a, _ in chunks])
-            sts = VP(*[starts[o].data_ptr() + s * starts_stride * 4 for s in range(nseg)])
             check(lib.abk_tsc_deposit_tiles(eng.ctx, nseg, recs, sts, counts, ptr(grids[o]), n, n, n, ldz, self.L,
-                                            float(off), 0, 0, n))
+                                            float(off), float(offsets[0]), 0, 0, n))
         return grids
 
     def normalize_fft(self, grid, tot_weight):
@@ -600,9 +599,45 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     return _make_table(res, meta)
 
 
-def pk_to_xi(*args, **kwargs):
-    """xi(r) multipoles (power_spectrum.py:620-660) -- next on the roadmap, not yet on the GPU."""
-    raise NotImplementedError('pk_to_xi is not implemented on the GPU path yet')
+def pk_to_xi(Pk, Lbox, r_bins, poles=[0, 2, 4]):
+    r"""
+    Transform a 3-D power spectrum (rfftn layout, real, shape (N, N, N//2+1)) into correlation-function
+    multipoles (reference: power_spectrum.py:620-660): ``Xi = irfftn(Pk)``, then ``bin_kmu(fourier=False)``
+    over separations ``r = |index| * Lbox/N`` with a single mu bin.
+
+    Returns ``(r_binc, binned_poles * N**3  (Np, Nr) float32, Npoles (Nr,) int64)``.
+    """
+    import torch
+
+    on_device = is_torch_tensor(Pk) and Pk.is_cuda
+    eng = Engine.get(Pk.device if on_device else None)
+    r_bins = np.asarray(r_bins)
+    pk_d = eng.to_device(Pk, torch.float32)
+    n = int(pk_d.shape[0])
+    if tuple(pk_d.shape) != (n, n, n // 2 + 1):
+        raise ValueError(f'Pk must have shape (N, N, N//2+1), got {tuple(pk_d.shape)}')
+    ldz = padded_ldz(n)
+    buf = eng.empty((n, n, ldz), torch.float32)
+    eng.bind_stream()
+    check(eng.lib.abk_real_to_complex(eng.ctx, ptr(pk_d), ptr(buf), pk_d.numel()))
+    plan, wb = eng.rfft3_plan(n, n, n)
+    # the C2R plan is created on first use and may want a larger work area than the R2C one
+    work = eng.scratch('fftwork', max(wb, 2 * buf.numel() * 4))
+    check(eng.lib.abk_irfft3_exec(eng.ctx, plan, ptr(buf), ptr(work), work.numel()))
+    r_binc = (r_bins[1:] + r_bins[:-1]) * 0.5
+    poles = np.asarray(poles)
+    muedges = np.array([0.0, 1.0])
+    sw, counts, sp, counts_poles, sk = _bin_device(eng, n, float(Lbox), r_bins, muedges, poles, False, real_in=buf,
+                                                   row_len=ldz)
+    # the C2R transform is unnormalised: Xi = out / N^3 (scipy's irfftn normalises), power_spectrum.py:645
+    binned_poles = (sp / float(n) ** 3).astype(np.float32)
+    binned_poles *= n**3  # power_spectrum.py:659
+    return r_binc, binned_poles, counts_poles
+
+
+def get_delta_mu2(delta, n1d, dtype_c=np.complex64, dtype_f=np.float32):
+    """``delta(k) * mu^2`` (reference: power_spectrum.py:577-617) -- next on the roadmap, not yet on the GPU."""
+    raise NotImplementedError('get_delta_mu2 is not implemented on the GPU path yet')
 
 
 _ = (warnings, tsc_parallel)

@@ -383,6 +383,14 @@ __global__ void __launch_bounds__(256) raw_power_kernel(const float2 *__restrict
     }
 }
 
+// real (n,n,nzc) float32 -> complex64 with zero imaginary part (input of the C2R transform in pk_to_xi)
+__global__ void __launch_bounds__(256) real_to_complex_kernel(const float *__restrict__ in, float2 *__restrict__ out,
+                                                              int64_t size)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < size; t += (int64_t)gridDim.x * blockDim.x)
+        out[t] = make_float2(in[t], 0.0f);
+}
+
 int grid_for(const abk_ctx *ctx, int64_t work_items, int threads, int per_sm)
 {
     int64_t blocks = (work_items + threads - 1) / threads;
@@ -446,6 +454,14 @@ extern "C" int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float
     ABK_REQUIRE(ctx && f1 && out && size >= 0, "abk_raw_power: bad arguments");
     if (size == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_RAW_POWER, raw_power_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>((const float2 *)f1, (const float2 *)f2, out, size));
+    return ABK_OK;
+}
+
+extern "C" int abk_real_to_complex(abk_ctx *ctx, const float *in, void *out, int64_t size)
+{
+    ABK_REQUIRE(ctx && in && out && size >= 0, "abk_real_to_complex: bad arguments");
+    if (size == 0) return ABK_OK;
+    ABK_LAUNCH(ctx, ABK_K_MISC, real_to_complex_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>(in, (float2 *)out, size));
     return ABK_OK;
 }
 

@@ -146,12 +146,18 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
 //   head[c]   : first particle of cell c's list (index into srec) or NIL
 //   srec[2v]  : (wx-, wx0, wx+, dz)            precomputed in the lane<->particle load pass, so the
 //   srec[2v+1]: (wy- W, wy0 W, wy+ W, next)     divergent lane<->cell loop is 2 LDS.128 + 43 FP ops
-constexpr int OUT_X = ABK_TX + 2, OUT_Y = ABK_TY + 2, OUT_Z = ABK_TZ + 2;
-constexpr int OUT_N = OUT_X * OUT_Y * OUT_Z;
-constexpr int SLAB_PLANE = 3 * OUT_Z;
-constexpr int SLAB_WORDS = OUT_X * SLAB_PLANE;
-constexpr int NCELL = ABK_TX * ABK_TY * ABK_TZ;
-constexpr int DEP_THREADS = ABK_TY * 32;
+// EXT = 1 widens the cell domain of a tile by one cell in x and y (and treats z-overflow with direct
+// reductions): that is what the half-cell-shifted (interlaced) deposit needs when it REUSES the records
+// bucketed for the unshifted grid -- the shifted centre cell is the unshifted one or its +1 neighbour.
+template <int EXT>
+struct TileDom {
+    static constexpr int NXC = ABK_TX + EXT, NYC = ABK_TY + EXT;       // cells with particle lists
+    static constexpr int OX = NXC + 2, OY = NYC + 2, OZ = ABK_TZ + 2;  // output region incl. 1-cell halo
+    static constexpr int OUT_N = OX * OY * OZ;
+    static constexpr int SLAB_PLANE = 3 * OZ, SLAB_WORDS = OX * SLAB_PLANE;
+    static constexpr int NCELL = NXC * NYC * ABK_TZ;
+    static constexpr int NW = NYC, NT = NW * 32;  // one warp per y-row
+};
 constexpr uint32_t NIL = 0xffffffffu;
 
 struct SegList {
@@ -164,11 +170,14 @@ struct SegList {
 //       vs 16-byte (dx,dy,dz,W) records + u16 links (less shared memory -> more resident CTAs)
 // PRIV: private per-warp slabs (no barriers in the main loop) vs one shared output tile with a
 //       block barrier after every row phase
-static size_t deposit_smem_bytes(int cap, bool pre, bool priv)
+static size_t deposit_smem_bytes(int cap, bool pre, bool priv, int ext)
 {
-    const size_t out = priv ? (size_t)ABK_TY * SLAB_WORDS * 4 : (size_t)OUT_N * 4;
+    const size_t out_n = ext ? TileDom<1>::OUT_N : TileDom<0>::OUT_N;
+    const size_t slab = ext ? (size_t)TileDom<1>::NW * TileDom<1>::SLAB_WORDS : (size_t)TileDom<0>::NW * TileDom<0>::SLAB_WORDS;
+    const size_t ncell = ext ? TileDom<1>::NCELL : TileDom<0>::NCELL;
+    const size_t out = (priv ? slab : out_n) * 4;
     const size_t rec = pre ? (size_t)cap * 32 : (size_t)cap * 16 + (size_t)cap * 2;
-    return out + (size_t)NCELL * 4 + rec + 64;
+    return abk_align_up(out + ncell * 4, 16) + rec + 64;
 }
 
 // tsc.py:442-451: the three 1-D TSC weights for cells i-1, i, i+1 given d = i - p
@@ -180,33 +189,38 @@ __device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
     wp = 0.5f * b * b;
 }
 
-// Add one finished x-plane of this lane's register window to the warp's private slab.
+// Add one finished x-plane of this lane's register window to the output.
 // S[b][c]: contribution of cell (row w, z = lane) to row w-1+b, cell z-1+c.  Lane z receives the
 // c=+1 term of lane z-1 and the c=-1 term of lane z+1; the two halo cells are lanes 0 / 31's.
-__device__ __forceinline__ void emit_plane(float *__restrict__ slab, const float (&S)[3][3], int x, int lane,
+// PRIV: `dst` is the warp's private slab [plane][3 rows][OZ] and the first pass stores instead of adding.
+// shared: `dst` is the CTA's tile [plane][OY][OZ]; rows of different warps are distinct within a
+//         phase (b) but not across phases, hence the block barrier after each phase.
+template <typename D, bool PRIV>
+__device__ __forceinline__ void emit_plane(float *__restrict__ dst, const float (&S)[3][3], int x, int wy, int lane,
                                            bool first)
 {
-    float *plane = slab + (x + 1) * SLAB_PLANE;
+    float *plane = dst + (x + 1) * (PRIV ? D::SLAB_PLANE : D::OY * D::OZ);
 #pragma unroll
     for (int b = 0; b < 3; b++) {
         const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
         const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
         const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
-        float *row = plane + b * OUT_Z;
-        if (first) {  // the first pass over a tile writes every slab entry exactly once: no zero-fill, no RMW
+        float *row = plane + (PRIV ? b : wy + b) * D::OZ;
+        if (PRIV && first) {  // the first pass writes every slab entry exactly once: no zero-fill, no RMW
             row[lane + 1] = v;
             if (lane == 0) row[0] = S[b][0];
-            if (lane == 31) row[OUT_Z - 1] = S[b][2];
+            if (lane == 31) row[D::OZ - 1] = S[b][2];
         } else {
             row[lane + 1] += v;
             if (lane == 0) row[0] += S[b][0];
-            if (lane == 31) row[OUT_Z - 1] += S[b][2];
+            if (lane == 31) row[D::OZ - 1] += S[b][2];
         }
+        if (!PRIV) __syncthreads();
     }
 }
 
-// 27 global reductions for a particle whose (shifted) centre cell lies outside the tile it was
-// bucketed in (only possible when the deposit offset differs from the bucketing offset).
+// 27 global reductions for a particle whose centre cell lies outside the cell domain of the tile it
+// was bucketed in (only possible when the deposit offset differs from the bucketing offset).
 __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscParams &P, int64_t ldz, int slab,
                                             int cx, int cy, int cz, float dx, float dy, float dz, float W)
 {
@@ -234,33 +248,18 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
     }
 }
 
-// shared-tile variant of emit_plane: rows of different warps are distinct within a phase (b), not
-// across phases, hence the block barrier after each phase
-__device__ __forceinline__ void emit_plane_shared(float *__restrict__ out, const float (&S)[3][3], int x, int wy, int lane)
-{
-    float *plane = out + (x + 1) * (OUT_Y * OUT_Z);
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-        const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
-        const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
-        const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
-        float *row = plane + (wy + b) * OUT_Z;
-        row[lane + 1] += v;
-        if (lane == 0) row[0] += S[b][0];
-        if (lane == 31) row[OUT_Z - 1] += S[b][2];
-        __syncthreads();
-    }
-}
-
-template <bool PRE, bool PRIV>
-__global__ void __launch_bounds__(DEP_THREADS, PRE ? 2 : (PRIV ? 3 : 4))
+template <bool PRE, bool PRIV, int EXT>
+__global__ void __launch_bounds__(TileDom<EXT>::NT, PRE ? 2 : ((PRIV || EXT) ? 3 : 4))
 tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
 {
+    using D = TileDom<EXT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int OUT_WORDS = PRIV ? ABK_TY * SLAB_WORDS : OUT_N;
+    constexpr int OUT_WORDS = PRIV ? D::NW * D::SLAB_WORDS : D::OUT_N;
+    constexpr int HEAD_OFF = OUT_WORDS;
+    constexpr int REC_OFF_BYTES = ((OUT_WORDS + D::NCELL) * 4 + 15) / 16 * 16;
     float *outbuf = reinterpret_cast<float *>(smem_raw);
-    uint32_t *head = reinterpret_cast<uint32_t *>(outbuf + OUT_WORDS);
-    float4 *srec = reinterpret_cast<float4 *>(head + NCELL);  // (OUT_WORDS + NCELL) * 4 is a multiple of 16
+    uint32_t *head = reinterpret_cast<uint32_t *>(outbuf + HEAD_OFF);
+    float4 *srec = reinterpret_cast<float4 *>(smem_raw + REC_OFF_BYTES);
     uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);  // !PRE only
     __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
     __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
@@ -281,21 +280,21 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
 
-    float *myslab = outbuf + wy * SLAB_WORDS;  // PRIV only
+    float *myslab = outbuf + wy * D::SLAB_WORDS;  // PRIV only
     if (!PRIV)
-        for (int i = tid; i < OUT_N; i += DEP_THREADS) outbuf[i] = 0.0f;
+        for (int i = tid; i < D::OUT_N; i += D::NT) outbuf[i] = 0.0f;
 
     for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
         const int m = (int)min((uint32_t)cap, total - chunk0);
         const bool first = (chunk0 == 0);
-        for (int c = tid; c < NCELL; c += DEP_THREADS) head[c] = NIL;
+        for (int c = tid; c < D::NCELL; c += D::NT) head[c] = NIL;
         __syncthreads();
         // ---- lane <-> particle: per-cell lists (and, PRE, the x/y weights once per particle) -------
-        for (int v0 = tid; v0 < m; v0 += 4 * DEP_THREADS) {
+        for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
             float4 rr[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {  // issue the (streaming) record loads of four particles first
-                const int v = v0 + q * DEP_THREADS;
+                const int v = v0 + q * D::NT;
                 if (v < m) {
                     uint32_t u = chunk0 + v;
                     int s = 0;
@@ -305,7 +304,7 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int v = v0 + q * DEP_THREADS;
+                const int v = v0 + q * D::NT;
                 if (v >= m) break;
                 const float4 r = rr[q];
                 int cx, cy, cz;
@@ -319,8 +318,9 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                 int ly = cy - y0, lz = cz - z0;
                 if (ly < 0) ly += P.ny;  // the shifted cell may have wrapped around the box edge
                 if (lz < 0) lz += P.nz;
-                if ((unsigned)lx < (unsigned)ABK_TX && (unsigned)ly < (unsigned)ABK_TY && (unsigned)lz < (unsigned)ABK_TZ) {
-                    const int c = (lx * ABK_TY + ly) * ABK_TZ + lz;
+                if (!slab && lx < 0) lx += P.nx;
+                if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
+                    const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
                     if (PRE) {
                         float wxm, wx0, wxp, wym, wy0, wyp;
                         tsc_w(dx, wxm, wx0, wxp);
@@ -346,8 +346,8 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
             for (int c = 0; c < 3; c++) S0[b][c] = S1[b][c] = S2[b][c] = 0.0f;
 
 #pragma unroll 1
-        for (int cx = 0; cx < ABK_TX; cx++) {
-            uint32_t i = head[(cx * ABK_TY + wy) * ABK_TZ + lane];
+        for (int cx = 0; cx < D::NXC; cx++) {
+            uint32_t i = head[(cx * D::NYC + wy) * ABK_TZ + lane];
             while (i != NIL) {
                 float wx[3], wyW[3], wz[3];
                 if (PRE) {
@@ -375,48 +375,42 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                         S2[b][c] = fmaf(wx[2], t, S2[b][c]);
                     }
             }
-            if (PRIV) emit_plane(myslab, S0, cx - 1, lane, first);
-            else emit_plane_shared(outbuf, S0, cx - 1, wy, lane);
+            emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S0, cx - 1, wy, lane, first);
 #pragma unroll
             for (int b = 0; b < 3; b++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
         }
-        if (PRIV) {
-            emit_plane(myslab, S0, ABK_TX - 1, lane, first);
-            emit_plane(myslab, S1, ABK_TX, lane, first);
-            __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
-        } else {
-            emit_plane_shared(outbuf, S0, ABK_TX - 1, wy, lane);
-            emit_plane_shared(outbuf, S1, ABK_TX, wy, lane);
-        }
+        emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S0, D::NXC - 1, wy, lane, first);
+        emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S1, D::NXC, wy, lane, first);
+        if (PRIV) __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
     }
 
     // ---- flush tile + halo with float reductions -----------------------------------------------------
-    // Warp w owns output rows oy = w (and oy = 8 + w for w < 2) of every x-plane; lanes on z, so the
-    // reductions of one instruction hit 32 consecutive floats.  Everything that does not depend on
-    // the plane (row pointers of the <= 3 contributing slabs, wrapped y/z indices) is hoisted.
+    // Warp w owns output rows oy = w, w + NW, ... of every x-plane; lanes on z, so the reductions of
+    // one instruction hit 32 consecutive floats.  Everything that does not depend on the plane (row
+    // pointers of the <= 3 contributing slabs, wrapped y/z indices) is hoisted.
     const int64_t sx = (int64_t)P.ny * ldz;
     const int gz = abk_wrap_cell(z0 + lane, P.nz);
-    const int ozh = lane ? OUT_Z - 1 : 0;
+    const int ozh = lane ? D::OZ - 1 : 0;
     const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
-    for (int oy = wy; oy < OUT_Y; oy += ABK_TY) {
+    for (int oy = wy; oy < D::OY; oy += D::NW) {
         const int gy = abk_wrap_cell(y0 + oy - 1, P.ny);
-        // PRIV: contributing (warp, row) pairs: w = oy - b for b = 0..2 with 0 <= w < 8
-        const bool ok0 = oy < ABK_TY, ok1 = oy >= 1 && oy - 1 < ABK_TY, ok2 = oy >= 2;
-        const float *p0 = outbuf + (ok0 ? oy : 0) * SLAB_WORDS;
-        const float *p1 = outbuf + (ok1 ? oy - 1 : 0) * SLAB_WORDS + OUT_Z;
-        const float *p2 = outbuf + (ok2 ? oy - 2 : 0) * SLAB_WORDS + 2 * OUT_Z;
+        // PRIV: contributing (warp, row) pairs: w = oy - b for b = 0..2 with 0 <= w < NW
+        const bool ok0 = oy < D::NW, ok1 = oy >= 1 && oy - 1 < D::NW, ok2 = oy >= 2 && oy - 2 < D::NW;
+        const float *p0 = outbuf + (ok0 ? oy : 0) * D::SLAB_WORDS;
+        const float *p1 = outbuf + (ok1 ? oy - 1 : 0) * D::SLAB_WORDS + D::OZ;
+        const float *p2 = outbuf + (ok2 ? oy - 2 : 0) * D::SLAB_WORDS + 2 * D::OZ;
         int gx = slab ? x0 : abk_wrap_cell(x0 - 1, P.nx);
-        for (int ox = 0; ox < OUT_X; ox++) {
+        for (int ox = 0; ox < D::OX; ox++) {
             float v = 0.0f, vh = 0.0f;
             if (PRIV) {
-                const int o = ox * SLAB_PLANE;
+                const int o = ox * D::SLAB_PLANE;
                 if (ok0) { v += p0[o + lane + 1]; if (lane < 2) vh += p0[o + ozh]; }
                 if (ok1) { v += p1[o + lane + 1]; if (lane < 2) vh += p1[o + ozh]; }
                 if (ok2) { v += p2[o + lane + 1]; if (lane < 2) vh += p2[o + ozh]; }
             } else {
-                const float *r = outbuf + (ox * OUT_Y + oy) * OUT_Z;
+                const float *r = outbuf + (ox * D::OY + oy) * D::OZ;
                 v = r[lane + 1];
                 if (lane < 2) vh = r[ozh];
             }
@@ -728,7 +722,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
 
 // kernel variant (PRE, PRIV): abk_ctx_set_tile_capacity's bits 16..18 select it for experiments
 
-static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int per_sm)
+static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int ext, int per_sm)
 {
     if (ctx->tile_capacity & 0xffff) return ctx->tile_capacity & 0xffff;
     // mean occupancy + 5 sigma (Poisson), so a uniform catalogue needs one pass per tile; capped so
@@ -737,21 +731,33 @@ static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bo
     const double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
     int cap = (int)((want + 63.0) / 64.0) * 64;
     const size_t per_cta = (size_t)(ctx->smem_optin + 1024) / per_sm - 1024;
-    const size_t fixed = deposit_smem_bytes(0, pre, priv);
+    const size_t fixed = deposit_smem_bytes(0, pre, priv, ext);
     const int fit = (int)((per_cta - fixed) / (pre ? 32 : 18)) / 64 * 64;
     if (cap > fit) cap = fit;
     if (cap < 256) cap = 256;
     return cap;
 }
 
+typedef void (*deposit_kernel_t)(SegList, float *, TscParams, int64_t, int, int);
+
+static deposit_kernel_t pick_kernel(bool pre, bool priv, int ext)
+{
+    if (ext) {
+        if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 1> : tsc_tile_deposit_kernel<true, false, 1>;
+        return priv ? tsc_tile_deposit_kernel<false, true, 1> : tsc_tile_deposit_kernel<false, false, 1>;
+    }
+    if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 0> : tsc_tile_deposit_kernel<true, false, 0>;
+    return priv ? tsc_tile_deposit_kernel<false, true, 0> : tsc_tile_deposit_kernel<false, false, 0>;
+}
+
 extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
                                      const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h,
                                      float *grid, int nx, int ny, int nz, int64_t ldz, double box, double offset,
-                                     int slab, int x_lo, int nxe)
+                                     double bucket_offset, int slab, int x_lo, int nxe)
 {
     ABK_REQUIRE(ctx && grid && nseg >= 1 && nseg <= ABK_MAX_SEGMENTS, "abk_tsc_deposit_tiles: bad arguments");
-    ABK_REQUIRE(slab || (x_lo == 0 && nxe == nx), "abk_tsc_deposit_tiles: a periodic (non-slab) grid needs x_lo=0, nxe=nx");
     ABK_REQUIRE(ldz >= nz, "ldz %lld < nz %d", (long long)ldz, nz);
+    ABK_REQUIRE(slab || (x_lo == 0 && nxe == nx), "abk_tsc_deposit_tiles: a periodic (non-slab) grid needs x_lo=0, nxe=nx");
     TscParams P;
     int rc = make_params(P, nx, ny, nz, box, offset, 0, x_lo, nxe);
     if (rc) return rc;
@@ -764,18 +770,19 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
         segs.starts[s] = tile_starts_seg_h[s];
         n_total += seg_counts_h ? seg_counts_h[s] : 0;
     }
-    int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
+    // records bucketed at another offset: widen the tile's cell domain by one cell in x and y
+    const int ext = ((float)bucket_offset != (float)offset) ? 1 : 0;
+    const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
     const bool pre = variant ? ((variant - 1) & 1) : false;
     const bool priv = variant ? (((variant - 1) >> 1) & 1) : false;
-    const int per_sm = pre ? 2 : (priv ? 3 : 4);
-    const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, per_sm);
-    const size_t smem = deposit_smem_bytes(cap, pre, priv);
+    const int per_sm = pre ? 2 : ((priv || ext) ? 3 : 4);
+    const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, ext, per_sm);
+    const size_t smem = deposit_smem_bytes(cap, pre, priv, ext);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
-    void (*kern)(SegList, float *, TscParams, int64_t, int, int) =
-        pre ? (priv ? tsc_tile_deposit_kernel<true, true> : tsc_tile_deposit_kernel<true, false>)
-            : (priv ? tsc_tile_deposit_kernel<false, true> : tsc_tile_deposit_kernel<false, false>);
+    deposit_kernel_t kern = pick_kernel(pre, priv, ext);
+    const int threads = ext ? TileDom<1>::NT : TileDom<0>::NT;
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, DEP_THREADS, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
+    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, threads, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
     return ABK_OK;
 }
 
@@ -828,7 +835,7 @@ extern "C" int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, i
         starts_h[s] = starts;
         cnt_h[s] = n;
     }
-    return abk_tsc_deposit_tiles(ctx, nseg, rec_h, starts_h, cnt_h, grid, nx, ny, nz, ldz, box, offset, 0, 0, nx);
+    return abk_tsc_deposit_tiles(ctx, nseg, rec_h, starts_h, cnt_h, grid, nx, ny, nz, ldz, box, offset, offset, 0, 0, nx);
 }
 
 extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx,

@@ -192,33 +192,35 @@ class DistEngine:
         ldz = padded_ldz(n)
         M = int(records.shape[0])
         grids = []
+        # bucket once by the unshifted centre cell (tiles cover the nxl owned planes); the shifted deposit
+        # reuses the records with the widened tile domain (abk_tsc_deposit_tiles, bucket_offset)
+        rec = starts = None
+        if M > 0:
+            if M > 1 << 30:
+                raise NotImplementedError('more than 2^30 particles per rank')
+            ntiles = C.c_int64()
+            check(lib.abk_tsc_num_tiles(nxl, n, n, C.byref(ntiles)))
+            nb = C.c_size_t()
+            check(lib.abk_tsc_bucket_scratch_bytes(M, nxl, n, n, C.byref(nb)))
+            scan_tmp = eng.scratch('bucket_scan', nb.value)
+            rec = eng.scratch('records_slab', M * 16)
+            starts = eng.scratch('starts_slab', (ntiles.value + 1) * 4)
+            dropped = C.c_ulonglong(0)
+            eng.bind_stream()
+            check(lib.abk_tsc_bucket_slab(eng.ctx, ptr(records), None, M, 1, n, n, n, float(Lbox), float(offsets[0]), 0,
+                                          x_lo, nxl, ptr(rec), ptr(starts), ptr(scan_tmp), scan_tmp.numel(),
+                                          C.byref(dropped)))
+            if dropped.value:
+                raise RuntimeError(f'rank {self.rank}: {dropped.value} routed particles fall outside the slab')
         for off in offsets:
-            shifted = off != 0.0
-            nxe = nxl + (1 if shifted else 0)
             grid = eng.zeros((nxl + 3, n, ldz), torch.float32)
             if M > 0:
-                ntiles = C.c_int64()
-                check(lib.abk_tsc_num_tiles(nxe, n, n, C.byref(ntiles)))
-                nb = C.c_size_t()
-                check(lib.abk_tsc_bucket_scratch_bytes(M, nxe, n, n, C.byref(nb)))
-                scan_tmp = eng.scratch('bucket_scan', nb.value)
-                rec = eng.scratch('records_slab', M * 16)
-                starts = eng.scratch('starts_slab', (ntiles.value + 1) * 4)
-                dropped = C.c_ulonglong(0)
-                eng.bind_stream()
-                for a in range(0, M, 1 << 30):
-                    if a:
-                        raise NotImplementedError('more than 2^30 particles per rank')
-                check(lib.abk_tsc_bucket_slab(eng.ctx, ptr(records), None, M, 1, n, n, n, float(Lbox), float(off), 0,
-                                              x_lo, nxe, ptr(rec), ptr(starts), ptr(scan_tmp), scan_tmp.numel(),
-                                              C.byref(dropped)))
-                if dropped.value:
-                    raise RuntimeError(f'rank {self.rank}: {dropped.value} routed particles fall outside the slab')
                 recs = (C.c_void_p * 1)(rec.data_ptr())
                 sts = (C.c_void_p * 1)(starts.data_ptr())
                 cnts = (C.c_int64 * 1)(M)
+                eng.bind_stream()
                 check(lib.abk_tsc_deposit_tiles(eng.ctx, 1, recs, sts, cnts, ptr(grid), n, n, n, ldz, float(Lbox),
-                                                float(off), 1, x_lo, nxe))
+                                                float(off), float(offsets[0]), 1, x_lo, nxl))
 
             def add_planes(dst, src):
                 eng.bind_stream()

@@ -125,17 +125,19 @@ int abk_route_particles(abk_ctx *ctx, const float *pos, const float *w, int64_t 
  * into, never zeroed (tsc.py:45-50).
  *   nseg segments: records_seg_h[s] / tile_starts_seg_h[s] (host arrays of device pointers) as
  *   produced by abk_tsc_bucket with the SAME grid shape and box; seg_counts_h[s] = N of segment s
- *   (sizes the shared-memory particle capacity).  `offset` may differ from the bucketing offset
- *   (interlacing: bucket once at offset 0, deposit at 0 and at half a cell): a particle whose cell
- *   at `offset` lies outside the tile it was bucketed in is deposited with 27 direct reductions.
+ *   (sizes the shared-memory particle capacity).  `offset` may differ from `bucket_offset`, the
+ *   offset the records were bucketed with (interlacing: bucket once at offset 0, deposit at 0 and at
+ *   half a cell).  The tile kernel then covers one more cell in x and y, which holds every particle
+ *   whose cell moved by 0 or +1; anything else (z overflow, larger shifts) is deposited with 27
+ *   direct reductions.
  *   slab == 0 : x_lo = 0, nxe = nx, the grid holds nx planes and x wraps periodically.
  *   slab != 0 : the records are those of abk_tsc_bucket_slab(x_lo, nxe); the grid holds nxe+2 planes:
  *   plane 0 is the ghost plane x_lo-1, planes 1..nxe are x_lo..x_lo+nxe-1, plane nxe+1 is the ghost
  *   plane x_lo+nxe (no wrap in x). */
 int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
                           const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h, float *grid,
-                          int nx, int ny, int nz, int64_t ldz, double box, double offset, int slab, int x_lo,
-                          int nxe);
+                          int nx, int ny, int nz, int64_t ldz, double box, double offset, double bucket_offset,
+                          int slab, int x_lo, int nxe);
 
 /* Convenience: bucket one segment and deposit it (what tsc_parallel does for device inputs).
  * scratch must hold abk_tsc_deposit_scratch_bytes(). */
@@ -206,6 +208,10 @@ int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const v
 /* power_spectrum.py:707-727 `get_raw_power`: out[t] = |f1[t]|^2, or Re(conj(f1[t]) f2[t]) when f2 != NULL,
  * over `size` complex64 elements (materialised; calc_power itself uses the fused abk_power_bin). */
 int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float *out, int64_t size);
+
+/* out[t] = in[t] + 0i over `size` elements: turns a real P(k) mesh into the complex input of the C2R
+ * transform of power_spectrum.py:645 (`irfftn(Pk)` in pk_to_xi). */
+int abk_real_to_complex(abk_ctx *ctx, const float *in, void *out, int64_t size);
 
 /* Binning request: power_spectrum.py:150-300 `bin_kmu` fused with :707-727 `get_raw_power` and,
  * optionally, with the finishing step above (so calc_power never materialises delta(k) or P(k)).

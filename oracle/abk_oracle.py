@@ -320,6 +320,21 @@ def project_3d_to_poles(k_bin_edges, raw_p3d, Lbox, poles):
     return binned_poles, Npoles
 
 
+def pk_to_xi(Pk, Lbox, r_bins, poles=[0, 2, 4]):
+    """power_spectrum.py:620-660."""
+    from scipy.fft import irfftn
+
+    Xi = irfftn(Pk, workers=-1).real
+    r_bins = np.asarray(r_bins)
+    r_binc = (r_bins[1:] + r_bins[:-1]) * 0.5
+    nmesh = Xi.shape[0]
+    poles = np.asarray(poles)
+    muedges = np.array([0.0, 1.0])
+    _, _, binned_poles, Npoles, _ = bin_kmu(nmesh, Lbox, r_bins, muedges, Xi, poles=poles, fourier=False)
+    binned_poles *= nmesh**3
+    return r_binc, binned_poles, Npoles
+
+
 def calc_pk_from_deltak(field_fft, Lbox, k_bin_edges, mu_bin_edges, field2_fft=None, poles=np.empty(0, 'i8'),
                         squeeze_mu_axis=True, nthread=MAX_THREADS, acc64=False):
     """power_spectrum.py:730-805."""
@@ -376,7 +391,7 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     return Table(res, meta=meta)
 
 
-__all__ = ['tsc_parallel', 'partition_parallel', 'calc_power', 'calc_pk_from_deltak', 'project_3d_to_poles',
+__all__ = ['tsc_parallel', 'partition_parallel', 'calc_power', 'pk_to_xi', 'calc_pk_from_deltak', 'project_3d_to_poles',
            'get_k_mu_edges', 'get_W_compensated', 'get_field_fft', 'get_field', 'normalize_field',
            'get_interlaced_field_fft', 'shift_field_fft', 'get_raw_power', 'bin_kmu', 'P_n',
            'tsc_scatter_serial', 'Table', 'build']

@@ -136,3 +136,22 @@ def deltak_inputs(c):
         np.complex64)
     raw = (rng.random(shp, dtype='f4') * 10).astype(np.float32)
     return f1, f2, raw
+
+
+# ---------------------------------------------------------------- xi(r) multipoles (pk_to_xi)
+XI_CASES = {
+    'x24': dict(seed=61, n=24, L=120.0, Nr=10, r_max=50.0, poles=[0, 2, 4]),
+    'x30': dict(seed=62, n=30, L=300.0, Nr=14, r_max=150.0, poles=[0, 2]),
+}
+
+
+def xi_inputs(c):
+    """A physical P(k) mesh: |rfftn(real field)|^2, so P(-k) = P(k) holds on the k_z = 0 / Nyquist planes
+    (irfftn of a mesh without that symmetry is implementation-defined)."""
+    rng = np.random.default_rng(c['seed'])
+    n = c['n']
+    field = rng.standard_normal((n, n, n)).astype(np.float32)
+    dk = np.fft.rfftn(field.astype(np.float64)) / n**3
+    Pk = (np.abs(dk) ** 2).astype(np.float32)
+    r_bins = np.linspace(0.0, c['r_max'], c['Nr'] + 1)
+    return Pk, r_bins

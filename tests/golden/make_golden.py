@@ -134,6 +134,23 @@ def golden_reference_runs():
     print('wrote', HERE / 'reference_runs.npz', len(out), 'arrays')
 
 
+def golden_xi():
+    _, ps = ref_shim.load(num_threads=2)
+    out = {}
+    for name, c in cases.XI_CASES.items():
+        Pk, r_bins = cases.xi_inputs(c)
+        r_binc, binned_poles, Npoles = ps.pk_to_xi(Pk.copy(), c['L'], r_bins, poles=c['poles'])
+        out[f'xi/{name}/r_binc'] = r_binc
+        out[f'xi/{name}/binned_poles'] = binned_poles
+        out[f'xi/{name}/Npoles'] = Npoles
+        print('xi', name, binned_poles[0][:3])
+    np.savez_compressed(HERE / 'reference_xi.npz', **out)
+
+
 if __name__ == '__main__':
-    golden_ref_tsc()
-    golden_reference_runs()
+    if len(sys.argv) > 1 and sys.argv[1] == 'xi':
+        golden_xi()
+    else:
+        golden_ref_tsc()
+        golden_reference_runs()
+        golden_xi()

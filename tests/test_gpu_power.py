@@ -193,3 +193,33 @@ def test_config1_full_vs_oracle(ps, oracle):
     got = ps.calc_power(pos.copy(), 1000.0, **kw)
     want = oracle.calc_power(pos.copy(), 1000.0, acc64=True, **kw)
     compare_power_tables(got, want)
+
+
+@pytest.mark.parametrize('name', list(cases.XI_CASES))
+def test_pk_to_xi(ps, name):
+    """xi(r) multipoles: C2R FFT + real-space binning (fourier=False) vs the unmodified reference."""
+    g = np.load(cases.__file__.replace('cases.py', 'reference_xi.npz'))
+    c = cases.XI_CASES[name]
+    Pk, r_bins = cases.xi_inputs(c)
+    r_binc, bp, Npo = ps.pk_to_xi(Pk, c['L'], r_bins, poles=c['poles'])
+    want = g[f'xi/{name}/binned_poles']
+    np.testing.assert_allclose(r_binc, g[f'xi/{name}/r_binc'])
+    assert bp.dtype == want.dtype and bp.shape == want.shape
+    assert_int_exact(Npo, g[f'xi/{name}/Npoles'])
+    assert_close_scaled(bp, want, scale=np.abs(want).max(), rtol=1e-4, what='xi poles')
+
+
+def test_bin_kmu_configuration_space(ps, oracle):
+    """bin_kmu(fourier=False) on a real-space mesh (n,n,n): only r_z <= n/2 is visited, dk = L/n."""
+    n, L = 28, 140.0
+    rng = np.random.default_rng(5)
+    xi = rng.standard_normal((n, n, n)).astype(np.float32)
+    r_bins = np.linspace(0, 60.0, 13)
+    mu = np.linspace(0, 1, 4)
+    got = ps.bin_kmu(n, L, r_bins, mu, xi, poles=np.array([0, 2]), fourier=False)
+    want = oracle.bin_kmu(n, L, r_bins, mu, xi, poles=np.array([0, 2]), fourier=False, acc64=True)
+    assert_int_exact(got[1], want[1])
+    assert_int_exact(got[3], want[3])
+    assert_close_scaled(got[0], want[0], scale=0.05, rtol=1e-5)
+    assert_close_scaled(got[4], want[4], rtol=1e-5)
+    assert_close_scaled(got[2], want[2], scale=0.05, rtol=1e-5)

@@ -237,7 +237,7 @@ def test_deposit_with_foreign_bucket_offset(oracle):
         recs = (C.c_void_p * 1)(rec.data_ptr())
         sts = (C.c_void_p * 1)(st.data_ptr())
         cnts = (C.c_int64 * 1)(N)
-        check(lib.abk_tsc_deposit_tiles(eng.ctx, 1, recs, sts, cnts, ptr(grid), n, n, n, n, box, off, 0, 0, n))
+        check(lib.abk_tsc_deposit_tiles(eng.ctx, 1, recs, sts, cnts, ptr(grid), n, n, n, n, box, off, 0.0, 0, 0, n))
         ref = np.zeros((n, n, n), dtype=np.float32)
         oracle.tsc_scatter_serial(pos, ref, box, weights=w, offset=off)
         assert np.allclose(grid.cpu().numpy(), ref, rtol=1e-5, atol=1e-5), off
