@@ -263,6 +263,11 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);  // !PRE only
     __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
     __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
+    // particles whose cell falls just outside the tile's cell domain (z overflow of the shifted deposit):
+    // queued here and deposited warp-cooperatively, one lane per stencil point
+    constexpr int MAX_OVF = 512;
+    __shared__ uint16_t ovf_v[MAX_OVF], ovf_xyz[MAX_OVF];
+    __shared__ unsigned ovf_cnt;
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -288,6 +293,7 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
         const int m = (int)min((uint32_t)cap, total - chunk0);
         const bool first = (chunk0 == 0);
         for (int c = tid; c < D::NCELL; c += D::NT) head[c] = NIL;
+        if (tid == 0) ovf_cnt = 0;
         __syncthreads();
         // ---- lane <-> particle: per-cell lists (and, PRE, the x/y weights once per particle) -------
         for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
@@ -333,11 +339,43 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                         next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
                     }
                 } else {
-                    deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+                    unsigned slot = MAX_OVF;
+                    if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
+                    if (slot < (unsigned)MAX_OVF) {
+                        srec[PRE ? 2 * v : v] = make_float4(dx, dy, dz, r.w);
+                        ovf_v[slot] = (uint16_t)v;
+                        ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
+                    } else {
+                        deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+                    }
                 }
             }
         }
         __syncthreads();
+        // ---- queued out-of-domain particles: one warp per particle, one lane per stencil point -----------
+        {
+            const int novf = (int)min(ovf_cnt, (unsigned)MAX_OVF);
+            const int64_t sxo = (int64_t)P.ny * ldz;
+            const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+            for (int q = wy; q < novf; q += D::NW) {
+                const float4 r = srec[PRE ? 2 * ovf_v[q] : ovf_v[q]];
+                const int xyz = ovf_xyz[q];
+                const int lx = xyz >> 10, ly = (xyz >> 6) & 15, lz = xyz & 63;
+                float wx[3], wyv[3], wz[3];
+                tsc_w(r.x, wx[0], wx[1], wx[2]);
+                tsc_w(r.y, wyv[0], wyv[1], wyv[2]);
+                tsc_w(r.z, wz[0], wz[1], wz[2]);
+                if (lane < 27) {
+                    const float val = (a == 0 ? wx[0] : (a == 1 ? wx[1] : wx[2])) *
+                                      (b == 0 ? wyv[0] : (b == 1 ? wyv[1] : wyv[2])) *
+                                      (c == 0 ? wz[0] : (c == 1 ? wz[1] : wz[2])) * r.w;
+                    const int64_t gx = slab ? (int64_t)(x0 + lx + a) : (int64_t)abk_wrap_cell(x0 + lx + a - 1, P.nx);
+                    const int gy = abk_wrap_cell(y0 + ly + b - 1, P.ny);
+                    const int gz = abk_wrap_cell(z0 + lz + c - 1, P.nz);
+                    atomicAdd(grid + gx * sxo + (int64_t)gy * ldz + gz, val);
+                }
+            }
+        }
         // ---- lane <-> cell (row wy, z = lane); rolling 3-plane register window along x ---------------
         float S0[3][3], S1[3][3], S2[3][3];
 #pragma unroll
