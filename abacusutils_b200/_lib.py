@@ -54,6 +54,7 @@ SIGNATURES = {
     'abk_ctx_sync': (_i32, [_vp]),
     'abk_ctx_launch_count': (_i64, [_vp]),
     'abk_ctx_set_tile_capacity': (_i32, [_vp, _i32]),
+    'abk_ctx_set_scheme': (_i32, [_vp, _i32]),
     'abk_ctx_profile_enable': (_i32, [_vp, _i32]),
     'abk_ctx_profile_collect': (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     'abk_kernel_count': (_i32, []),
@@ -166,6 +167,10 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.abk_ctx_launch_count(self.ctx))
+
+    def set_scheme(self, paste):
+        """Select the mass-assignment scheme ('TSC' / 'CIC') of the following bucket / deposit calls."""
+        check(self.lib.abk_ctx_set_scheme(self.ctx, 1 if str(paste).upper() == 'CIC' else 0))
 
     def profile(self, on):
         check(self.lib.abk_ctx_profile_enable(self.ctx, int(bool(on))))

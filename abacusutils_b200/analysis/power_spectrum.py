@@ -138,11 +138,14 @@ class _Painter:
     transforms in place.  Host inputs are streamed in chunks on a copy stream so the bucketing of
     chunk i overlaps the host->device copy of chunk i+1; every chunk becomes one bucket segment."""
 
-    def __init__(self, eng, nmesh, Lbox):
+    def __init__(self, eng, nmesh, Lbox, paste='TSC'):
         self.eng = eng
         self.n = int(nmesh)
         self.L = float(Lbox)
         self.ldz = padded_ldz(self.n)
+        # 'CIC' is the reference's cic_serial (analysis/cic.py) -- same 27-cell update, other weights; it
+        # applies no periodic wrap to the positions (power_spectrum.py:846-853)
+        self.paste = _check_paste(paste)
 
     def chunk_plan(self, N):
         max_seg = ABK_MAX_SEGMENTS - 2
@@ -156,6 +159,9 @@ class _Painter:
 
         eng, n, ldz = self.eng, self.n, self.ldz
         lib = eng.lib
+        eng.set_scheme(self.paste)
+        if self.paste == 'CIC':
+            wrap = False
         kind, psrc = _as_source(pos, np.float32)
         N = int(psrc.shape[0])
         wsrc = None
@@ -257,9 +263,7 @@ def _complex_view(grid_padded, n):
 
 def _check_paste(paste):
     paste_u = str(paste).upper()
-    if paste_u == 'CIC':
-        raise NotImplementedError("paste='CIC' is not implemented on the GPU path yet (TSC only)")
-    if paste_u != 'TSC':
+    if paste_u not in ('TSC', 'CIC'):
         raise ValueError(f'Unknown pasting method: {paste}')
     return paste_u
 
@@ -297,10 +301,10 @@ def get_field(pos, Lbox, nmesh, paste, w=None, d=0.0, nthread=MAX_THREADS, dtype
     Normalisation uses ``len(pos)``, not ``sum(w)``, like the reference (:856)."""
     if w is not None:
         assert pos.shape[0] == len(w)
-    _check_paste(paste)
+    paste = _check_paste(paste)
     on_device = is_torch_tensor(pos) and pos.is_cuda
     eng = Engine.get(pos.device if on_device else None)
-    P = _Painter(eng, nmesh, Lbox)
+    P = _Painter(eng, nmesh, Lbox, paste)
     (grid,) = P.paint(pos, w, [d])
     n = int(nmesh)
     check(eng.lib.abk_normalize_field(eng.ctx, ptr(grid), n, n, n, P.ldz, float(n) ** 3, float(len(pos))))
@@ -329,10 +333,10 @@ def shift_field_fft(field_fft, field_shift_fft, n1d, L, d, dtype=np.float32):
         np.copyto(field_fft, f.cpu().numpy())
 
 
-def _field_fft_device(eng, pos, Lbox, nmesh, w, interlaced, tag=''):
+def _field_fft_device(eng, pos, Lbox, nmesh, w, interlaced, tag='', paste='TSC'):
     """Paint, normalise and FFT; returns the in-place padded grids [A] or [A, B(shifted)] (unscaled)."""
     n = int(nmesh)
-    P = _Painter(eng, n, Lbox)
+    P = _Painter(eng, n, Lbox, paste)
     offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
     grids = P.paint(pos, w, offsets, tag=tag)
     for g in grids:
@@ -352,7 +356,7 @@ def get_field_fft(pos, Lbox, nmesh, paste, w, W, compensated, interlaced, nthrea
     scale by 1/n^3 (0.5/n^3 and the interlacing phase when ``interlaced``), divide by the window."""
     import torch
 
-    _check_paste(paste)
+    paste = _check_paste(paste)
     if w is not None:
         assert pos.shape[0] == len(w)
     if compensated:
@@ -360,7 +364,7 @@ def get_field_fft(pos, Lbox, nmesh, paste, w, W, compensated, interlaced, nthrea
     on_device = is_torch_tensor(pos) and pos.is_cuda
     eng = Engine.get(pos.device if on_device else None)
     n = int(nmesh)
-    grids = _field_fft_device(eng, pos, Lbox, n, w, interlaced)
+    grids = _field_fft_device(eng, pos, Lbox, n, w, interlaced, paste=paste)
     W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
     mesh = _kmesh(n)
     scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
@@ -561,7 +565,7 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     if pos2 is not None:
         meta['N_pos2'] = len(pos2)
         meta['is_weighted2'] = w2 is not None
-    _check_paste(paste)
+    paste_u = _check_paste(paste)
     if w is not None:
         assert pos.shape[0] == len(w)
     if pos2 is not None and w2 is not None:
@@ -573,8 +577,8 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     W = get_W_compensated(Lbox, n, paste, interlaced) if compensated else None
     W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
 
-    g1 = _field_fft_device(eng, pos, Lbox, n, w, interlaced, tag='a')
-    g2 = _field_fft_device(eng, pos2, Lbox, n, w2, interlaced, tag='a') if pos2 is not None else None
+    g1 = _field_fft_device(eng, pos, Lbox, n, w, interlaced, tag='a', paste=paste_u)
+    g2 = _field_fft_device(eng, pos2, Lbox, n, w2, interlaced, tag='a', paste=paste_u) if pos2 is not None else None
 
     poles_arr = np.asarray(poles or [], dtype=np.int64)
     kbins, mubins = get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)

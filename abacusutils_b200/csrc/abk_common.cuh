@@ -40,6 +40,7 @@ struct abk_ctx {
     int smem_optin;  // max dynamic shared memory per block (opt-in)
     int64_t launches;
     int tile_capacity;  // 0 = auto
+    int scheme;         // mass-assignment scheme of the deposit entry points: 0 TSC, 1 CIC
     // small device scratch owned by the context (work counters, flags)
     unsigned long long *d_scalars;
     // profiling state

@@ -39,6 +39,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     c->launches = 0;
     c->tile_capacity = 0;
+    c->scheme = 0;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -143,6 +144,14 @@ extern "C" int abk_ctx_sync(abk_ctx *ctx)
 }
 
 extern "C" int64_t abk_ctx_launch_count(abk_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int abk_ctx_set_scheme(abk_ctx *ctx, int scheme)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ABK_REQUIRE(scheme == 0 || scheme == 1, "unknown mass-assignment scheme %d (0 = TSC, 1 = CIC)", scheme);
+    ctx->scheme = scheme;
+    return ABK_OK;
+}
 
 extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
 {

@@ -33,6 +33,8 @@ struct TscParams {
     int x_lo;                      // first global x-plane of the tiled region
     int nty, ntz;
     int wrap;
+    int cic;                       // 0: TSC (tsc.py), 1: CIC (cic.py:13-125)
+    double gx_d, gy_d, gz_d;       // CIC works in double: p = (x / box) * g
 };
 
 // tsc.py:219-226: one-shot wrap; compare against the double box, store float32
@@ -52,13 +54,34 @@ __device__ __forceinline__ void cell_of(float x, float off, float inv_h, int n, 
     cell = abk_wrap_cell((int)r, n);
 }
 
+// cic.py:29-42: p = ((pos + d) / boxsize) * g in double (pos + d is a float32 sum); i = round-half-even(p)
+__device__ __forceinline__ void cell_of_cic(float x, float off, double box, double g, int n, int &cell, float &d)
+{
+    const double p = ((double)__fadd_rn(x, off) / box) * g;
+    const double r = rint(p);
+    d = (float)(r - p);
+    cell = abk_wrap_cell((int)r, n);
+}
+
+__device__ __forceinline__ void cells_of(const TscParams &P, float x, float y, float z, int &cx, int &cy, int &cz,
+                                         float &dx, float &dy, float &dz)
+{
+    if (P.cic) {
+        cell_of_cic(x, P.off, P.box, P.gx_d, P.nx, cx, dx);
+        cell_of_cic(y, P.off, P.box, P.gy_d, P.ny, cy, dy);
+        cell_of_cic(z, P.off, P.box, P.gz_d, P.nz, cz, dz);
+    } else {
+        cell_of(x, P.off, P.inv_hx, P.nx, cx, dx);
+        cell_of(y, P.off, P.inv_hy, P.ny, cy, dy);
+        cell_of(z, P.off, P.inv_hz, P.nz, cz, dz);
+    }
+}
+
 __device__ __forceinline__ bool tile_of(const TscParams &P, float x, float y, float z, uint32_t &tile)
 {
     int cx, cy, cz;
-    float d;
-    cell_of(x, P.off, P.inv_hx, P.nx, cx, d);
-    cell_of(y, P.off, P.inv_hy, P.ny, cy, d);
-    cell_of(z, P.off, P.inv_hz, P.nz, cz, d);
+    float d, d2, d3;
+    cells_of(P, x, y, z, cx, cy, cz, d, d2, d3);
     int lx = cx - P.x_lo;
     if (lx < 0) lx += P.nx;
     if (lx >= P.nxe) return false;  // not owned by this slab
@@ -189,6 +212,21 @@ __device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
     wp = 0.5f * b * b;
 }
 
+// cic.py:43-67: weights of cells i-1, i, i+1 for d = i - p: (max(d,0), 1-|d|, max(-d,0))
+__device__ __forceinline__ void cic_w(float d, float &wm, float &w0, float &wp)
+{
+    wm = fmaxf(d, 0.0f);
+    w0 = 1.0f - fabsf(d);
+    wp = fmaxf(-d, 0.0f);
+}
+
+template <bool CIC>
+__device__ __forceinline__ void mas_w(float d, float &wm, float &w0, float &wp)
+{
+    if (CIC) cic_w(d, wm, w0, wp);
+    else tsc_w(d, wm, w0, wp);
+}
+
 // Add one finished x-plane of this lane's register window to the output.
 // S[b][c]: contribution of cell (row w, z = lane) to row w-1+b, cell z-1+c.  Lane z receives the
 // c=+1 term of lane z-1 and the c=-1 term of lane z+1; the two halo cells are lanes 0 / 31's.
@@ -226,9 +264,11 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
 {
     const int64_t sx = (int64_t)P.ny * ldz;
     float wx[3], wy[3], wz[3];
-    tsc_w(dx, wx[0], wx[1], wx[2]);
-    tsc_w(dy, wy[0], wy[1], wy[2]);
-    tsc_w(dz, wz[0], wz[1], wz[2]);
+    if (P.cic) {
+        cic_w(dx, wx[0], wx[1], wx[2]); cic_w(dy, wy[0], wy[1], wy[2]); cic_w(dz, wz[0], wz[1], wz[2]);
+    } else {
+        tsc_w(dx, wx[0], wx[1], wx[2]); tsc_w(dy, wy[0], wy[1], wy[2]); tsc_w(dz, wz[0], wz[1], wz[2]);
+    }
     for (int a = 0; a < 3; a++) {
         int64_t gx;
         if (slab) {
@@ -248,7 +288,7 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
     }
 }
 
-template <bool PRE, bool PRIV, int EXT>
+template <bool PRE, bool PRIV, int EXT, bool CIC>
 __global__ void __launch_bounds__(TileDom<EXT>::NT, PRE ? 2 : ((PRIV || EXT) ? 3 : 4))
 tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
 {
@@ -315,9 +355,7 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                 const float4 r = rr[q];
                 int cx, cy, cz;
                 float dx, dy, dz;
-                cell_of(r.x, P.off, P.inv_hx, P.nx, cx, dx);
-                cell_of(r.y, P.off, P.inv_hy, P.ny, cy, dy);
-                cell_of(r.z, P.off, P.inv_hz, P.nz, cz, dz);
+                cells_of(P, r.x, r.y, r.z, cx, cy, cz, dx, dy, dz);
                 int lx = cx - P.x_lo;
                 if (lx < 0) lx += P.nx;
                 lx -= x0;
@@ -329,8 +367,8 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                     const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
                     if (PRE) {
                         float wxm, wx0, wxp, wym, wy0, wyp;
-                        tsc_w(dx, wxm, wx0, wxp);
-                        tsc_w(dy, wym, wy0, wyp);
+                        mas_w<CIC>(dx, wxm, wx0, wxp);
+                        mas_w<CIC>(dy, wym, wy0, wyp);
                         srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
                         const uint32_t old = atomicExch(&head[c], (uint32_t)v);
                         srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
@@ -362,9 +400,9 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                 const int xyz = ovf_xyz[q];
                 const int lx = xyz >> 10, ly = (xyz >> 6) & 15, lz = xyz & 63;
                 float wx[3], wyv[3], wz[3];
-                tsc_w(r.x, wx[0], wx[1], wx[2]);
-                tsc_w(r.y, wyv[0], wyv[1], wyv[2]);
-                tsc_w(r.z, wz[0], wz[1], wz[2]);
+                mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
+                mas_w<CIC>(r.y, wyv[0], wyv[1], wyv[2]);
+                mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
                 if (lane < 27) {
                     const float val = (a == 0 ? wx[0] : (a == 1 ? wx[1] : wx[2])) *
                                       (b == 0 ? wyv[0] : (b == 1 ? wyv[1] : wyv[2])) *
@@ -393,14 +431,14 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                     i = __float_as_uint(B.w);
                     wx[0] = A.x; wx[1] = A.y; wx[2] = A.z;
                     wyW[0] = B.x; wyW[1] = B.y; wyW[2] = B.z;
-                    tsc_w(A.w, wz[0], wz[1], wz[2]);
+                    mas_w<CIC>(A.w, wz[0], wz[1], wz[2]);
                 } else {
                     const float4 r = srec[i];
                     const uint16_t nxt = next16[i];
                     i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
-                    tsc_w(r.x, wx[0], wx[1], wx[2]);
-                    tsc_w(r.y, wyW[0], wyW[1], wyW[2]);
-                    tsc_w(r.z, wz[0], wz[1], wz[2]);
+                    mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
+                    mas_w<CIC>(r.y, wyW[0], wyW[1], wyW[2]);
+                    mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
                     wyW[0] *= r.w; wyW[1] *= r.w; wyW[2] *= r.w;
                 }
 #pragma unroll
@@ -472,13 +510,13 @@ __global__ void __launch_bounds__(256) tsc_naive_kernel(const float *__restrict_
         const float W = w ? w[n] : 1.0f;
         int cx, cy, cz;
         float dx, dy, dz;
-        cell_of(x, P.off, P.inv_hx, P.nx, cx, dx);
-        cell_of(y, P.off, P.inv_hy, P.ny, cy, dy);
-        cell_of(z, P.off, P.inv_hz, P.nz, cz, dz);
+        cells_of(P, x, y, z, cx, cy, cz, dx, dy, dz);
         float wx[3], wy[3], wz[3];
-        tsc_w(dx, wx[0], wx[1], wx[2]);
-        tsc_w(dy, wy[0], wy[1], wy[2]);
-        tsc_w(dz, wz[0], wz[1], wz[2]);
+        if (P.cic) {
+            cic_w(dx, wx[0], wx[1], wx[2]); cic_w(dy, wy[0], wy[1], wy[2]); cic_w(dz, wz[0], wz[1], wz[2]);
+        } else {
+            tsc_w(dx, wx[0], wx[1], wx[2]); tsc_w(dy, wy[0], wy[1], wy[2]); tsc_w(dz, wz[0], wz[1], wz[2]);
+        }
         for (int a = 0; a < 3; a++) {
             const int64_t gx = abk_wrap_cell(cx + a - 1, P.nx);
             for (int b = 0; b < 3; b++) {
@@ -515,7 +553,7 @@ struct RouteSplit { int v[65]; };
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) route_kernel(const float *__restrict__ pos, const float *__restrict__ w, int64_t N,
-                                                    float inv_hx, int nx, double box, int wrap, int nranks, RouteSplit xs,
+                                                    TscParams P, int nranks, RouteSplit xs,
                                                     unsigned long long *__restrict__ counts, float4 *__restrict__ out)
 {
     __shared__ int s_xs[65];
@@ -528,10 +566,10 @@ __global__ void __launch_bounds__(256) route_kernel(const float *__restrict__ po
         float x = 0.f, y = 0.f, z = 0.f;
         if (i < N) {
             x = pos[3 * i]; y = pos[3 * i + 1]; z = pos[3 * i + 2];
-            if (wrap) { x = wrap_coord(x, box); y = wrap_coord(y, box); z = wrap_coord(z, box); }
-            int cx;
-            float d;
-            cell_of(x, 0.0f, inv_hx, nx, cx, d);
+            if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
+            int cx, cy, cz;
+            float d, d2, d3;
+            cells_of(P, x, y, z, cx, cy, cz, d, d2, d3);
             int lo = 0, hi = nranks - 1;
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
@@ -581,7 +619,7 @@ __global__ void starts_to_i64_kernel(const uint32_t *__restrict__ excl, int npar
     if (i == npart) starts[i] = N;
 }
 
-int make_params(TscParams &P, int nx, int ny, int nz, double box, double offset, int wrap, int x_lo, int nxe)
+int make_params(const abk_ctx *ctx, TscParams &P, int nx, int ny, int nz, double box, double offset, int wrap, int x_lo, int nxe)
 {
     ABK_REQUIRE(nx > 0 && ny > 0 && nz > 0, "grid shape (%d,%d,%d) must be positive", nx, ny, nz);
     ABK_REQUIRE(box > 0, "box must be positive");
@@ -596,6 +634,8 @@ int make_params(TscParams &P, int nx, int ny, int nz, double box, double offset,
     const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
     P.nty = g.nty; P.ntz = g.ntz;
     P.wrap = wrap;
+    P.cic = ctx->scheme == 1;
+    P.gx_d = nx; P.gy_d = ny; P.gz_d = nz;
     return ABK_OK;
 }
 
@@ -667,11 +707,13 @@ extern "C" int abk_route_particles(abk_ctx *ctx, const float *pos, const float *
     ABK_REQUIRE(nranks <= 24, "abk_route_particles: at most 24 ranks per node supported");
     unsigned long long *cursors = ctx->d_scalars + 8 + 24;
     ABK_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * 48, ctx->stream));
-    const float inv_hx = (float)(nx / box);
+    TscParams P;
+    int rcp = make_params(ctx, P, nx, nx, nx, box, 0.0, wrap, 0, nx);
+    if (rcp) return rcp;
     unsigned long long h[24];
     if (N > 0) {
         const int blocks = grid_for(ctx, N, 256, 16);
-        ABK_LAUNCH(ctx, ABK_K_PART_HIST, route_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, inv_hx, nx, box, wrap, nranks, xs, counts, nullptr));
+        ABK_LAUNCH(ctx, ABK_K_PART_HIST, route_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, nranks, xs, counts, nullptr));
     }
     ABK_CHECK_CUDA(cudaMemcpyAsync(h, counts, sizeof(unsigned long long) * nranks, cudaMemcpyDeviceToHost, ctx->stream));
     ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -680,7 +722,7 @@ extern "C" int abk_route_particles(abk_ctx *ctx, const float *pos, const float *
     if (N > 0 && records_out) {
         ABK_CHECK_CUDA(cudaMemcpyAsync(cursors, start, sizeof(unsigned long long) * nranks, cudaMemcpyHostToDevice, ctx->stream));
         const int blocks = grid_for(ctx, N, 256, 16);
-        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, route_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, inv_hx, nx, box, wrap, nranks, xs, cursors, (float4 *)records_out));
+        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, route_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, P, nranks, xs, cursors, (float4 *)records_out));
     }
     return ABK_OK;
 }
@@ -734,7 +776,7 @@ extern "C" int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, in
 {
     ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket: null argument");
     TscParams P;
-    int rc = make_params(P, nx, ny, nz, box, offset, wrap, 0, nx);
+    int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, 0, nx);
     if (rc) return rc;
     return bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
 }
@@ -746,7 +788,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
 {
     ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket_slab: null argument");
     TscParams P;
-    int rc = make_params(P, nx, ny, nz, box, offset, wrap, x_lo, nxe);
+    int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, x_lo, nxe);
     if (rc) return rc;
     ABK_CHECK_CUDA(cudaMemsetAsync(ctx->d_scalars + 1, 0, 8, ctx->stream));
     rc = bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes, in_records != 0);
@@ -778,14 +820,15 @@ static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bo
 
 typedef void (*deposit_kernel_t)(SegList, float *, TscParams, int64_t, int, int);
 
-static deposit_kernel_t pick_kernel(bool pre, bool priv, int ext)
+static deposit_kernel_t pick_kernel(bool pre, bool priv, int ext, bool cic)
 {
+    if (cic) return ext ? tsc_tile_deposit_kernel<false, false, 1, true> : tsc_tile_deposit_kernel<false, false, 0, true>;
     if (ext) {
-        if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 1> : tsc_tile_deposit_kernel<true, false, 1>;
-        return priv ? tsc_tile_deposit_kernel<false, true, 1> : tsc_tile_deposit_kernel<false, false, 1>;
+        if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 1, false> : tsc_tile_deposit_kernel<true, false, 1, false>;
+        return priv ? tsc_tile_deposit_kernel<false, true, 1, false> : tsc_tile_deposit_kernel<false, false, 1, false>;
     }
-    if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 0> : tsc_tile_deposit_kernel<true, false, 0>;
-    return priv ? tsc_tile_deposit_kernel<false, true, 0> : tsc_tile_deposit_kernel<false, false, 0>;
+    if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 0, false> : tsc_tile_deposit_kernel<true, false, 0, false>;
+    return priv ? tsc_tile_deposit_kernel<false, true, 0, false> : tsc_tile_deposit_kernel<false, false, 0, false>;
 }
 
 extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
@@ -797,7 +840,7 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     ABK_REQUIRE(ldz >= nz, "ldz %lld < nz %d", (long long)ldz, nz);
     ABK_REQUIRE(slab || (x_lo == 0 && nxe == nx), "abk_tsc_deposit_tiles: a periodic (non-slab) grid needs x_lo=0, nxe=nx");
     TscParams P;
-    int rc = make_params(P, nx, ny, nz, box, offset, 0, x_lo, nxe);
+    int rc = make_params(ctx, P, nx, ny, nz, box, offset, 0, x_lo, nxe);
     if (rc) return rc;
     const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
     SegList segs;
@@ -811,13 +854,14 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     // records bucketed at another offset: widen the tile's cell domain by one cell in x and y
     const int ext = ((float)bucket_offset != (float)offset) ? 1 : 0;
     const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
-    const bool pre = variant ? ((variant - 1) & 1) : false;
-    const bool priv = variant ? (((variant - 1) >> 1) & 1) : false;
+    const bool cic = ctx->scheme == 1;
+    const bool pre = (variant && !cic) ? ((variant - 1) & 1) : false;
+    const bool priv = (variant && !cic) ? (((variant - 1) >> 1) & 1) : false;
     const int per_sm = pre ? 2 : ((priv || ext) ? 3 : 4);
     const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, ext, per_sm);
     const size_t smem = deposit_smem_bytes(cap, pre, priv, ext);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
-    deposit_kernel_t kern = pick_kernel(pre, priv, ext);
+    deposit_kernel_t kern = pick_kernel(pre, priv, ext, cic);
     const int threads = ext ? TileDom<1>::NT : TileDom<0>::NT;
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, threads, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
@@ -882,7 +926,7 @@ extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float
     ABK_REQUIRE(ctx && grid && (pos || N == 0) && N >= 0, "abk_tsc_deposit_naive: bad arguments");
     if (N == 0) return ABK_OK;
     TscParams P;
-    int rc = make_params(P, nx, ny, nz, box, offset, wrap, 0, nx);
+    int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, 0, nx);
     if (rc) return rc;
     ABK_LAUNCH(ctx, ABK_K_NAIVE_DEPOSIT, tsc_naive_kernel<<<grid_for(ctx, N, 256, 16), 256, 0, ctx->stream>>>(pos, w, N, grid, P, ldz));
     return ABK_OK;

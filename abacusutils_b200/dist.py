@@ -159,19 +159,21 @@ class DistEngine:
         self.device = self.eng.device
 
     # -- 1. routing -----------------------------------------------------------------------------------
-    def route(self, pos, w, plan, Lbox):
+    def route(self, pos, w, plan, Lbox, paste='TSC'):
         """Returns the (M,4) float32 records of the particles whose centre cell this rank owns."""
         import torch
 
         eng = self.eng
         eng.bind_stream()
+        eng.set_scheme(paste)
         pos_d = eng.to_device(pos, torch.float32)
         w_d = None if w is None else eng.to_device(w, torch.float32)
         N = int(pos_d.shape[0])
         xs = (C.c_int32 * (self.world + 1))(*plan.xsplit)
         counts = (C.c_int64 * self.world)()
         out = eng.scratch('route_out', max(N, 1) * 16)
-        check(eng.lib.abk_route_particles(eng.ctx, ptr(pos_d), ptr(w_d), N, plan.n, float(Lbox), 1, self.world, xs,
+        check(eng.lib.abk_route_particles(eng.ctx, ptr(pos_d), ptr(w_d), N, plan.n, float(Lbox),
+                                          0 if str(paste).upper() == 'CIC' else 1, self.world, xs,
                                           ptr(out), counts))
         send_counts = [int(c) for c in counts]
         rows = out[: N * 16].view(torch.float32).view(N, 4)
@@ -181,12 +183,13 @@ class DistEngine:
         return exchange_rows(rows, send_counts, recv_counts, self.group)
 
     # -- 2. deposit + ghosts ----------------------------------------------------------------------------
-    def paint_slab(self, records, plan, Lbox, offsets):
+    def paint_slab(self, records, plan, Lbox, offsets, paste='TSC'):
         """Deposit this rank's records for every offset into slab grids [(nxl+3), n, ldz] and fold the ghosts."""
         import torch
 
         eng, n = self.eng, plan.n
         lib = eng.lib
+        eng.set_scheme(paste)
         x_lo, x_hi = plan.x_range(self.rank)
         nxl = x_hi - x_lo
         ldz = padded_ldz(n)
@@ -331,7 +334,7 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     eng = de.eng
     n = int(nmesh)
     plan = SlabPlan(n, de.world)
-    ps._check_paste(paste)
+    paste = ps._check_paste(paste)
     if kbins is None:
         kbins = nmesh
     if k_max is None:
@@ -348,9 +351,9 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
 
     def field(p, wt):
         ntot = total(len(p))
-        rec = de.route(p, wt, plan, Lbox)
+        rec = de.route(p, wt, plan, Lbox, paste)
         offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
-        grids = de.paint_slab(rec, plan, Lbox, offsets)
+        grids = de.paint_slab(rec, plan, Lbox, offsets, paste)
         return [de.fft_slab(g, plan, ntot) for g in grids], ntot
 
     g1, N1 = field(pos, w)

@@ -64,6 +64,10 @@ int abk_ctx_profile_enable(abk_ctx *ctx, int on);
 int abk_ctx_profile_collect(abk_ctx *ctx, double *ms_h, int64_t *n_h);
 int abk_kernel_count(void);
 const char *abk_kernel_name(int id);
+/* Mass-assignment scheme used by the bucket / deposit entry points: 0 = TSC (analysis/tsc.py, default),
+ * 1 = CIC (analysis/cic.py:13-125 `cic_serial`: same 27-cell update with weights (max(d,0), 1-|d|, max(-d,0)),
+ * cell index from p = ((pos + offset) / box) * g evaluated in double). */
+int abk_ctx_set_scheme(abk_ctx *ctx, int scheme);
 /* tuning knobs (0 = library default): tile-kernel particle capacity per pass */
 int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity);
 

@@ -173,6 +173,35 @@ void abko_tsc_scatter_f32(const float *pos, const float *w, int64_t N, float *de
                       (float)(gz / box), (float)offset);
 }
 
+/* CIC: analysis/cic.py:13-125 `cic_serial` (serial in the reference).  Same 27-cell update as TSC with  */
+/* weights (max(d,0), 1-|d|, max(-d,0)); p = (pos / box) * g and all products evaluated in double, the  */
+/* sum is stored into the float32 grid.                                                                */
+void abko_cic_serial_f32(const float *pos, const float *w, int64_t N, float *dens, int gx, int gy, int gz,
+                         double box)
+{
+    const size_t sy = (size_t)gz, sx = (size_t)gy * gz;
+    for (int64_t n = 0; n < N; n++) {
+        const double W = w ? (double)w[n] : 1.0;
+        const double p[3] = {((double)pos[3 * n] / box) * gx, ((double)pos[3 * n + 1] / box) * gy,
+                             ((double)pos[3 * n + 2] / box) * gz};
+        const int g[3] = {gx, gy, gz};
+        double wt[3][3];
+        int idx[3][3];
+        for (int a = 0; a < 3; a++) {
+            const int i = (int)rint(p[a]);
+            const double d = (double)i - p[a];
+            wt[a][1] = 1.0 - fabs(d);
+            if (d > 0.0) { wt[a][0] = d; wt[a][2] = 0.0; } else { wt[a][2] = -d; wt[a][0] = 0.0; }
+            for (int q = 0; q < 3; q++) idx[a][q] = wrap_idx(i + q - 1, g[a]);
+        }
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) {
+                float *row = dens + idx[0][a] * sx + idx[1][b] * sy;
+                for (int c = 0; c < 3; c++) row[idx[2][c]] += (float)(wt[0][a] * wt[1][b] * wt[2][c] * W);
+            }
+    }
+}
+
 /* T4: two-colour stripe deposit.  analysis/tsc.py:229-256                    */
 /* Even stripes in parallel, then odd stripes.                               */
 void abko_tsc_stripes_f32(const float *psort, const float *wsort, const int64_t *starts,

@@ -56,6 +56,7 @@ def _lib():
     L.abko_partition_f32.restype = C.c_int
     L.abko_tsc_scatter_f32.argtypes = [vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
     L.abko_tsc_stripes_f32.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    L.abko_cic_serial_f32.argtypes = [vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_double]
     L.abko_normalize_field_f32.argtypes = [vp, C.c_int64, C.c_double, C.c_int]
     L.abko_scale_c64.argtypes = [vp, C.c_int64, C.c_float, C.c_int]
     L.abko_shift_field_fft.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_int]
@@ -213,9 +214,15 @@ def get_field(pos, Lbox, nmesh, paste, w=None, d=0.0, nthread=MAX_THREADS, dtype
     if w is not None:
         assert pos.shape[0] == len(w)
     field = np.zeros((nmesh, nmesh, nmesh), dtype=np.float32)
-    if paste.upper() != 'TSC':
+    if paste.upper() == 'CIC':
+        # power_spectrum.py:846-853: cic_serial(pos + d, ...) -- a float32 sum, no periodic wrap
+        p = np.ascontiguousarray(pos + d if d != 0.0 else pos, dtype=np.float32)
+        wc = None if w is None else np.ascontiguousarray(w, dtype=np.float32)
+        _lib().abko_cic_serial_f32(_p(p), _p(wc), len(p), _p(field), nmesh, nmesh, nmesh, float(Lbox))
+    elif paste.upper() == 'TSC':
+        tsc_parallel(pos, field, Lbox, weights=w, nthread=nthread, offset=d)
+    else:
         raise ValueError(f'Unknown pasting method: {paste}')
-    tsc_parallel(pos, field, Lbox, weights=w, nthread=nthread, offset=d)
     normalize_field(field, inplace=True, tot_weight=len(pos), nthread=nthread)
     return field
 

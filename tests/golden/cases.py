@@ -155,3 +155,24 @@ def xi_inputs(c):
     Pk = (np.abs(dk) ** 2).astype(np.float32)
     r_bins = np.linspace(0.0, c['r_max'], c['Nr'] + 1)
     return Pk, r_bins
+
+
+# ---------------------------------------------------------------- CIC paste (analysis/cic.py via paste='CIC')
+CIC_POWER_CASES = {
+    'cic32_ci': _pc(71, 20000, 500.0, 32, 16, 4, [0, 2, 4], True, True),
+    'cic32_c': _pc(71, 20000, 500.0, 32, 16, 4, [0, 2, 4], True, False),
+    'cic32_raw': _pc(72, 20000, 500.0, 32, 16, 4, [0, 2], False, False, weighted=False),
+    'cic40_cross_i': _pc(73, 15000, 400.0, 40, 10, 2, [0, 2, 4], False, True, cross=True),
+}
+CIC_FIELD_CASES = {
+    'cicf24': dict(seed=74, N=4000, L=100.0, nmesh=24, weighted=True, d=0.0),
+    'cicf24_off': dict(seed=74, N=4000, L=100.0, nmesh=24, weighted=True, d=0.5 * 100.0 / 24),
+}
+
+
+def cic_field_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    # stay inside [0, L - d): cic_serial applies no periodic wrap
+    pos = rng.random((c['N'], 3), dtype='f4') * np.float32(c['L'] - 2 * c['L'] / c['nmesh'])
+    w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
+    return pos, w

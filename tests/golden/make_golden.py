@@ -147,10 +147,34 @@ def golden_xi():
     np.savez_compressed(HERE / 'reference_xi.npz', **out)
 
 
+def golden_cic():
+    import warnings
+
+    _, ps = ref_shim.load(num_threads=2)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for name, c in cases.CIC_POWER_CASES.items():
+            pos, w, pos2, w2 = cases.power_inputs(c)
+            t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], logk=c['logk'], paste='CIC',
+                              nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w,
+                              pos2=pos2, w2=w2, poles=c['poles'], nthread=2)
+            for key in t:
+                out[f'power/{name}/{key}'] = np.asarray(t[key])
+            print('cic power', name, np.asarray(t['power']).ravel()[:3])
+        for name, c in cases.CIC_FIELD_CASES.items():
+            pos, w = cases.cic_field_inputs(c)
+            out[f'field/{name}'] = ps.get_field(pos, c['L'], c['nmesh'], 'CIC', w=w, d=c['d'], nthread=2)
+    np.savez_compressed(HERE / 'reference_cic.npz', **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'xi':
         golden_xi()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'cic':
+        golden_cic()
     else:
         golden_ref_tsc()
         golden_reference_runs()
         golden_xi()
+        golden_cic()

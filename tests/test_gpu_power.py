@@ -223,3 +223,29 @@ def test_bin_kmu_configuration_space(ps, oracle):
     assert_close_scaled(got[0], want[0], scale=0.05, rtol=1e-5)
     assert_close_scaled(got[4], want[4], rtol=1e-5)
     assert_close_scaled(got[2], want[2], scale=0.05, rtol=1e-5)
+
+
+@pytest.mark.parametrize('name', list(cases.CIC_POWER_CASES))
+def test_cic_calc_power(ps, name):
+    """paste='CIC' (analysis/cic.py through power_spectrum.py:846-853) vs the unmodified reference."""
+    g = np.load(cases.__file__.replace('cases.py', 'reference_cic.npz'))
+    c = cases.CIC_POWER_CASES[name]
+    pos, w, pos2, w2 = cases.power_inputs(c)
+    t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], logk=c['logk'], paste='CIC', nmesh=c['nmesh'],
+                      compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2, poles=c['poles'])
+    pre = f'power/{name}/'
+    want = {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)}
+    assert set(want) == set(t.keys())
+    compare_power_tables(t, want)
+
+
+@pytest.mark.parametrize('name', list(cases.CIC_FIELD_CASES))
+def test_cic_field(ps, name):
+    g = np.load(cases.__file__.replace('cases.py', 'reference_cic.npz'))
+    c = cases.CIC_FIELD_CASES[name]
+    pos, w = cases.cic_field_inputs(c)
+    f = ps.get_field(pos, c['L'], c['nmesh'], 'CIC', w=w, d=c['d'])
+    np.testing.assert_allclose(f, g[f'field/{name}'], rtol=1e-4, atol=1e-5)
+    # and TSC still is TSC afterwards (the scheme is per call, not sticky)
+    f2 = ps.get_field(pos, c['L'], c['nmesh'], 'TSC', w=w, d=c['d'])
+    assert np.abs(f2 - f).max() > 1e-3
