@@ -38,7 +38,7 @@ class BinRequest(C.Structure):
                 ('kedges2', C.c_void_p), ('muedges2', C.c_void_p), ('Nk', C.c_int32), ('Nmu', C.c_int32),
                 ('Np', C.c_int32), ('pole_coef', C.c_void_p), ('pole_ell', C.c_int32 * ABK_MAX_POLES), ('counts', C.c_void_p),
                 ('sum_p', C.c_void_p), ('sum_k', C.c_void_p), ('sum_poles', C.c_void_p), ('scratch', C.c_void_p),
-                ('scratch_bytes', C.c_size_t)]
+                ('scratch_bytes', C.c_size_t), ('w_symmetric', C.c_int32)]
 
 
 _vp, _i32, _i64, _dbl, _flt, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_float, C.c_size_t

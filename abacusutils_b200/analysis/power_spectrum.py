@@ -187,13 +187,16 @@ class _Painter:
         check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
         scan_tmp = eng.scratch('bucket_scan', nb.value)
         starts_stride = (ntiles + 1 + 63) // 64 * 64
-        # Particles are bucketed ONCE, by the tile of their cell at the first offset.  The deposit of the
-        # half-cell-shifted grid reuses the records: its tile kernel covers one more cell in x and y,
-        # which holds every particle whose cell moved by 0 or +1 (abk_tsc_deposit_tiles, bucket_offset).
-        records = eng.scratch(f'records{tag}', N * 16)
-        starts = eng.scratch(f'starts{tag}', nseg * starts_stride * 4)
-
         host = kind == 'host'
+        # Device-resident input: bucket ONCE (tile of the cell at the first offset); the deposit of the
+        # half-cell-shifted grid reuses the records with the widened tile domain (abk_tsc_deposit_tiles,
+        # bucket_offset) -- one histogram+scatter less.  Host input: the run is bound by the PCIe copy and
+        # bucketing hides behind it, so bucket per offset and keep the (faster) plain tile kernel in the
+        # un-overlapped tail.
+        nbuck = len(offsets) if host else 1
+        records = [eng.scratch(f'records{tag}{o}', N * 16) for o in range(nbuck)]
+        starts = [eng.scratch(f'starts{tag}{o}', nseg * starts_stride * 4) for o in range(nbuck)]
+
         if host:
             csize = max(b - a for a, b in chunks)
             copy_stream = torch.cuda.Stream(device=eng.device)
@@ -223,22 +226,24 @@ class _Painter:
                 wd = None if wsrc is None else wsrc[a:b]
                 if not pd.is_contiguous():
                     pd = pd.contiguous()
-            rec_ptr = records.data_ptr() + a * 16
-            st_ptr = starts.data_ptr() + s * starts_stride * 4
-            check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[0]),
-                                     int(bool(wrap)), C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp),
-                                     scan_tmp.numel()))
+            for o in range(nbuck):
+                rec_ptr = records[o].data_ptr() + a * 16
+                st_ptr = starts[o].data_ptr() + s * starts_stride * 4
+                check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]),
+                                         int(bool(wrap)), C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp),
+                                         scan_tmp.numel()))
             if host:
                 done[slot].record(compute)
 
         VP = C.c_void_p * nseg
         I64 = C.c_int64 * nseg
         counts = I64(*[b - a for a, b in chunks])
-        recs = VP(*[records.data_ptr() + a * 16 for a, _ in chunks])
-        sts = VP(*[starts.data_ptr() + s * starts_stride * 4 for s in range(nseg)])
         for o, off in enumerate(offsets):
+            ob = o if nbuck > 1 else 0
+            recs = VP(*[records[ob].data_ptr() + a * 16 for a, _ in chunks])
+            sts = VP(*[starts[ob].data_ptr() + s * starts_stride * 4 for s in range(nseg)])
             check(lib.abk_tsc_deposit_tiles(eng.ctx, nseg, recs, sts, counts, ptr(grids[o]), n, n, n, ldz, self.L,
-                                            float(off), float(offsets[0]), 0, 0, n))
+                                            float(off), float(offsets[ob]), 0, 0, n))
         return grids
 
     def normalize_fft(self, grid, tot_weight):
@@ -394,7 +399,7 @@ def get_raw_power(field_fft, field2_fft=None):
 # ---------------------------------------------------------------------------------------------
 # binning
 def _bin_device(eng, n, L, kedges, muedges, poles, fourier, *, f1=None, f1s=None, f2=None, f2s=None, real_in=None,
-                row_len=None, W_d=None, scale=1.0, finish=False):
+                row_len=None, W_d=None, scale=1.0, finish=False, W_sym=True):
     """Run abk_power_bin and return the reference's five arrays as float64/int64 NumPy
     (means, not yet cast): (weighted_counts, counts, weighted_counts_poles, counts_poles, weighted_counts_k)."""
     import torch
@@ -432,6 +437,7 @@ def _bin_device(eng, n, L, kedges, muedges, poles, fourier, *, f1=None, f1s=None
     for ip in range(Np):
         req.pole_ell[ip] = int(poles[ip])
     req.Nk, req.Nmu, req.Np = Nk, Nmu, Np
+    req.w_symmetric = int(W_sym)
     sb = sums.data_ptr()
     req.counts = sb
     req.sum_p = sb + 8 * Nb
@@ -585,7 +591,8 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
     binned = _bin_device(eng, n, float(Lbox), kbins, mubins, poles_arr, True, f1=g1[0],
                          f1s=g1[1] if interlaced else None, f2=None if g2 is None else g2[0],
-                         f2s=g2[1] if (g2 is not None and interlaced) else None, W_d=W_d, scale=scale, finish=True)
+                         f2s=g2[1] if (g2 is not None and interlaced) else None, W_d=W_d, scale=scale, finish=True,
+                         W_sym=(W is None) or bool(np.array_equal(np.asarray(W)[1:], np.asarray(W)[:0:-1])))
     P = _package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
 
     kbins = np.asarray(kbins)

@@ -41,6 +41,7 @@ struct abk_ctx {
     int64_t launches;
     int tile_capacity;  // 0 = auto
     int scheme;         // mass-assignment scheme of the deposit entry points: 0 TSC, 1 CIC
+    int bin_no_sym;     // experiments: force the one-mode-at-a-time binning kernel
     // small device scratch owned by the context (work counters, flags)
     unsigned long long *d_scalars;
     // profiling state

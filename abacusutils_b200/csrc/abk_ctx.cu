@@ -40,6 +40,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->launches = 0;
     c->tile_capacity = 0;
     c->scheme = 0;
+    c->bin_no_sym = 0;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -158,7 +159,8 @@ extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
     ABK_REQUIRE(ctx != nullptr, "null context");
     const int cap = capacity & 0xffff;  // bits 16..18: deposit kernel variant (experiments), 0 = default
     ABK_REQUIRE(cap == 0 || (cap >= 256 && cap <= 12288), "tile capacity %d out of range", cap);
-    ctx->tile_capacity = capacity;
+    ctx->tile_capacity = capacity & 0x7ffff;
+    ctx->bin_no_sym = (capacity >> 19) & 1;  // bit 19: disable the mirror-symmetric binning kernel (experiments)
     return ABK_OK;
 }
 

@@ -255,6 +255,9 @@ typedef struct abk_bin_request {
      * into the outputs */
     void *scratch;
     size_t scratch_bytes;
+    /* non-zero if the host verified W[n-a] == W[a] for all a (or W is NULL): enables the kernel that
+     * bins the mirror modes (+-i', +-j', k) together */
+    int32_t w_symmetric;
 } abk_bin_request;
 
 int abk_power_bin_scratch_bytes(int Nk, int Nmu, int Np, size_t *bytes);
