@@ -162,6 +162,12 @@ class Engine:
         check(self.lib.abk_ctx_set_stream(self.ctx, C.c_void_p(s.cuda_stream)))
         return s
 
+    def aux_stream(self):
+        """A second CUDA stream of this device (overlap of independent stages)."""
+        if getattr(self, '_aux', None) is None:
+            self._aux = _torch().cuda.Stream(device=self.device)
+        return self._aux
+
     def sync(self):
         check(self.lib.abk_ctx_sync(self.ctx))
 

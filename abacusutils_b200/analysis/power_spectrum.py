@@ -153,8 +153,14 @@ class _Painter:
         chunk = min(chunk, SEGMENT_MAX)
         return [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
 
-    def paint(self, pos, w, offsets, wrap=True, tag=''):
-        """Returns one padded device grid (n, n, ldz) float32 per offset, holding the raw deposit."""
+    def paint(self, pos, w, offsets, wrap=True, tag='', fft_weight=None):
+        """Returns one padded device grid (n, n, ldz) float32 per offset.  With ``fft_weight=None`` the grids
+        hold the raw deposit; otherwise they are normalised by ``fft_weight`` and transformed in place
+        (the transform of the first grid then overlaps the deposit of the second on an auxiliary stream).
+
+        Host inputs are streamed in chunks: bucketing of chunk i overlaps the copy of chunk i+1, and the
+        tile deposit of the first ~70% of the chunks runs on the auxiliary stream while the remaining
+        chunks are still arriving over PCIe, so only the last chunks' deposit is left for the tail."""
         import torch
 
         eng, n, ldz = self.eng, self.n, self.ldz
@@ -172,6 +178,8 @@ class _Painter:
         compute = eng.bind_stream()
         grids = [eng.zeros((n, n, ldz), torch.float32) for _ in offsets]
         if N == 0:
+            if fft_weight is not None:
+                raise ValueError('cannot normalise an empty particle set')
             return grids
         if psrc.dtype != torch.float32:
             psrc = psrc.to(torch.float32)
@@ -196,6 +204,25 @@ class _Painter:
         nbuck = len(offsets) if host else 1
         records = [eng.scratch(f'records{tag}{o}', N * 16) for o in range(nbuck)]
         starts = [eng.scratch(f'starts{tag}{o}', nseg * starts_stride * 4) for o in range(nbuck)]
+        aux = eng.aux_stream()
+
+        def deposit(lo, hi, o, stream):
+            """Enqueue the tile deposit of segments [lo, hi) for offset o on `stream`."""
+            ob = o if nbuck > 1 else 0
+            m = hi - lo
+            recs = (C.c_void_p * m)(*[records[ob].data_ptr() + chunks[s][0] * 16 for s in range(lo, hi)])
+            sts = (C.c_void_p * m)(*[starts[ob].data_ptr() + s * starts_stride * 4 for s in range(lo, hi)])
+            cnts = (C.c_int64 * m)(*[chunks[s][1] - chunks[s][0] for s in range(lo, hi)])
+            with torch.cuda.stream(stream):
+                eng.bind_stream()
+                check(lib.abk_tsc_deposit_tiles(eng.ctx, m, recs, sts, cnts, ptr(grids[o]), n, n, n, ldz, self.L,
+                                                float(offsets[o]), float(offsets[ob]), 0, 0, n))
+            eng.bind_stream()
+
+        split = 0
+        if host and nseg >= 6:
+            split = nseg - max(3, -(-3 * nseg // 10))
+        early_done = None
 
         if host:
             csize = max(b - a for a, b in chunks)
@@ -234,16 +261,41 @@ class _Painter:
                                          scan_tmp.numel()))
             if host:
                 done[slot].record(compute)
+            if split and s == split - 1:
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                aux.wait_event(ev)
+                for o in range(len(offsets)):
+                    deposit(0, split, o, aux)
+                early_done = torch.cuda.Event()
+                early_done.record(aux)
 
-        VP = C.c_void_p * nseg
-        I64 = C.c_int64 * nseg
-        counts = I64(*[b - a for a, b in chunks])
-        for o, off in enumerate(offsets):
-            ob = o if nbuck > 1 else 0
-            recs = VP(*[records[ob].data_ptr() + a * 16 for a, _ in chunks])
-            sts = VP(*[starts[ob].data_ptr() + s * starts_stride * 4 for s in range(nseg)])
-            check(lib.abk_tsc_deposit_tiles(eng.ctx, nseg, recs, sts, counts, ptr(grids[o]), n, n, n, ldz, self.L,
-                                            float(off), float(offsets[ob]), 0, 0, n))
+        # ---- remaining deposits; FFT of grid o overlaps the deposit of grid o+1 ----------------------------
+        fft_prev = None
+        for o in range(len(offsets)):
+            deposit(split, nseg, o, compute)
+            if fft_weight is None:
+                continue
+            last = o == len(offsets) - 1
+            if not last:
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                aux.wait_event(ev)  # aux already holds the early deposits of this grid, in order
+                with torch.cuda.stream(aux):
+                    self.normalize_fft(grids[o], fft_weight)
+                    fft_prev = torch.cuda.Event()
+                    fft_prev.record(aux)
+                eng.bind_stream()
+            else:
+                if early_done is not None:
+                    compute.wait_event(early_done)
+                if fft_prev is not None:
+                    compute.wait_event(fft_prev)  # one FFT work area: transforms run one after the other
+                self.normalize_fft(grids[o], fft_weight)
+        if early_done is not None:
+            compute.wait_event(early_done)
+        if fft_prev is not None:
+            compute.wait_event(fft_prev)
         return grids
 
     def normalize_fft(self, grid, tot_weight):
@@ -343,10 +395,7 @@ def _field_fft_device(eng, pos, Lbox, nmesh, w, interlaced, tag='', paste='TSC')
     n = int(nmesh)
     P = _Painter(eng, n, Lbox, paste)
     offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
-    grids = P.paint(pos, w, offsets, tag=tag)
-    for g in grids:
-        P.normalize_fft(g, len(pos))
-    return grids
+    return P.paint(pos, w, offsets, tag=tag, fft_weight=len(pos))
 
 
 def get_interlaced_field_fft(pos, Lbox, nmesh, paste, w, nthread=MAX_THREADS, verbose=False):
