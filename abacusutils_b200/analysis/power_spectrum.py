@@ -227,17 +227,20 @@ class _Painter:
         if host:
             csize = max(b - a for a, b in chunks)
             copy_stream = torch.cuda.Stream(device=eng.device)
-            stage_p = [eng.scratch(f'stage_p{i}', csize * 12) for i in range(2)]
-            stage_w = [eng.scratch(f'stage_w{i}', csize * 4) for i in range(2)] if wsrc is not None else None
-            ready = [torch.cuda.Event() for _ in range(2)]
-            done = [torch.cuda.Event() for _ in range(2)]
+            # a ring of staging buffers: deep enough that PCIe keeps streaming while the bucket kernels share
+            # the SMs with the early tile deposits
+            NSTAGE = 4
+            stage_p = [eng.scratch(f'stage_p{i}', csize * 12) for i in range(NSTAGE)]
+            stage_w = [eng.scratch(f'stage_w{i}', csize * 4) for i in range(NSTAGE)] if wsrc is not None else None
+            ready = [torch.cuda.Event() for _ in range(NSTAGE)]
+            done = [torch.cuda.Event() for _ in range(NSTAGE)]
             for ev in done:
                 ev.record(compute)
 
         for s, (a, b) in enumerate(chunks):
             m = b - a
             if host:
-                slot = s % 2
+                slot = s % NSTAGE
                 copy_stream.wait_event(done[slot])
                 with torch.cuda.stream(copy_stream):
                     pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
