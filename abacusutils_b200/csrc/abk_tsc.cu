@@ -77,6 +77,31 @@ __device__ __forceinline__ void cells_of(const TscParams &P, float x, float y, f
     }
 }
 
+// Cell index relative to a tile origin (global cell index `origin`), fast path for the common case that
+// the rounded position already lies inside [origin, origin + T); periodic images take the slow path.
+template <bool CIC>
+__device__ __forceinline__ void local_cell(float x, float off, float inv_h, double box, double g, int n, int origin, int T,
+                                           int &l, float &d)
+{
+    int c;
+    if (CIC) {
+        const double p = ((double)__fadd_rn(x, off) / box) * g;
+        const double r = rint(p);
+        d = (float)(r - p);
+        c = (int)r;
+    } else {
+        const float p = __fmul_rn(__fadd_rn(x, off), inv_h);
+        const float r = rintf(p);
+        d = r - p;
+        c = (int)r;
+    }
+    l = c - origin;
+    if ((unsigned)l >= (unsigned)T) {
+        l = abk_wrap_cell(c, n) - origin;
+        if (l < 0) l += n;
+    }
+}
+
 __device__ __forceinline__ bool tile_of(const TscParams &P, float x, float y, float z, uint32_t &tile)
 {
     int cx, cy, cz;
@@ -301,7 +326,7 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     uint32_t *head = reinterpret_cast<uint32_t *>(outbuf + HEAD_OFF);
     float4 *srec = reinterpret_cast<float4 *>(smem_raw + REC_OFF_BYTES);
     uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);  // !PRE only
-    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS];
+    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
     __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
     // particles whose cell falls just outside the tile's cell domain (z overflow of the shifted deposit):
     // queued here and deposited warp-cooperatively, one lane per stencil point
@@ -321,6 +346,11 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     uint32_t total = 0;
     for (int s = 0; s < segs.nseg; s++) total += seg_cnt[s];
     if (total == 0) return;
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int s = 0; s < segs.nseg; s++) { seg_off[s] = run; run += seg_cnt[s]; }
+        seg_off[segs.nseg] = run;
+    }
 
     const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
@@ -336,55 +366,55 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
         if (tid == 0) ovf_cnt = 0;
         __syncthreads();
         // ---- lane <-> particle: per-cell lists (and, PRE, the x/y weights once per particle) -------
-        for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
-            float4 rr[4];
+        const int ox_g = P.x_lo + x0;  // global cell index of the tile origin in x (slab: may exceed nx, handled by wrap)
+        {
+            int sg = 0;  // this thread's virtual indices only grow: the segment lookup is incremental
+            for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
+                float4 rr[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {  // issue the (streaming) record loads of four particles first
-                const int v = v0 + q * D::NT;
-                if (v < m) {
-                    uint32_t u = chunk0 + v;
-                    int s = 0;
-                    while (u >= seg_cnt[s]) { u -= seg_cnt[s]; s++; }
-                    rr[q] = __ldcs(seg_rec[s] + seg_beg[s] + u);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int v = v0 + q * D::NT;
-                if (v >= m) break;
-                const float4 r = rr[q];
-                int cx, cy, cz;
-                float dx, dy, dz;
-                cells_of(P, r.x, r.y, r.z, cx, cy, cz, dx, dy, dz);
-                int lx = cx - P.x_lo;
-                if (lx < 0) lx += P.nx;
-                lx -= x0;
-                int ly = cy - y0, lz = cz - z0;
-                if (ly < 0) ly += P.ny;  // the shifted cell may have wrapped around the box edge
-                if (lz < 0) lz += P.nz;
-                if (!slab && lx < 0) lx += P.nx;
-                if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
-                    const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
-                    if (PRE) {
-                        float wxm, wx0, wxp, wym, wy0, wyp;
-                        mas_w<CIC>(dx, wxm, wx0, wxp);
-                        mas_w<CIC>(dy, wym, wy0, wyp);
-                        srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
-                        const uint32_t old = atomicExch(&head[c], (uint32_t)v);
-                        srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
-                    } else {
-                        srec[v] = make_float4(dx, dy, dz, r.w);
-                        next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+                for (int q = 0; q < 4; q++) {  // issue the (streaming) record loads of four particles first
+                    const int vq = v0 + q * D::NT;
+                    if (vq < m) {
+                        const uint32_t u = chunk0 + vq;
+                        while (u >= seg_off[sg + 1]) sg++;
+                        rr[q] = __ldcs(seg_rec[sg] + seg_beg[sg] + (u - seg_off[sg]));
                     }
-                } else {
-                    unsigned slot = MAX_OVF;
-                    if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
-                    if (slot < (unsigned)MAX_OVF) {
-                        srec[PRE ? 2 * v : v] = make_float4(dx, dy, dz, r.w);
-                        ovf_v[slot] = (uint16_t)v;
-                        ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int v = v0 + q * D::NT;
+                    if (v >= m) break;
+                    const float4 r = rr[q];
+                    int lx, ly, lz;
+                    float dx, dy, dz;
+                    local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_g >= P.nx ? ox_g - P.nx : ox_g, D::NXC, lx, dx);
+                    local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
+                    local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, ABK_TZ, lz, dz);
+                    if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
+                        const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
+                        if (PRE) {
+                            float wxm, wx0, wxp, wym, wy0, wyp;
+                            mas_w<CIC>(dx, wxm, wx0, wxp);
+                            mas_w<CIC>(dy, wym, wy0, wyp);
+                            srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
+                            const uint32_t old = atomicExch(&head[c], (uint32_t)v);
+                            srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
+                        } else {
+                            srec[v] = make_float4(dx, dy, dz, r.w);
+                            next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+                        }
                     } else {
-                        deposit_direct(grid, P, ldz, slab, cx, cy, cz, dx, dy, dz, r.w);
+                        unsigned slot = MAX_OVF;
+                        if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
+                        if (slot < (unsigned)MAX_OVF) {
+                            srec[PRE ? 2 * v : v] = make_float4(dx, dy, dz, r.w);
+                            ovf_v[slot] = (uint16_t)v;
+                            ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
+                        } else {
+                            // far outside the tile (arbitrary offset difference): global cell = origin + local
+                            deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
+                                           abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
+                        }
                     }
                 }
             }
