@@ -835,14 +835,20 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
 static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int ext, int per_sm)
 {
     if (ctx->tile_capacity & 0xffff) return ctx->tile_capacity & 0xffff;
-    // mean occupancy + 5 sigma (Poisson), so a uniform catalogue needs one pass per tile; capped so
-    // that `per_sm` CTAs stay resident per SM (denser tiles simply take several passes)
+    // mean occupancy + 5 sigma (Poisson): a uniform catalogue then needs ONE pass per tile.  A second pass
+    // repeats the whole per-cell work, which costs more than one resident CTA less per SM (measured on
+    // B200, config 3: 64 ms with 3 CTAs/SM and one pass vs 68 ms with 4 CTAs/SM and two passes for 40%
+    // of the tiles), so the capacity may take one CTA/SM; denser tiles simply take several passes.
     const double mean = ntiles > 0 ? (double)n_total / (double)ntiles : 0.0;
     const double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
     int cap = (int)((want + 63.0) / 64.0) * 64;
-    const size_t per_cta = (size_t)(ctx->smem_optin + 1024) / per_sm - 1024;
     const size_t fixed = deposit_smem_bytes(0, pre, priv, ext);
-    const int fit = (int)((per_cta - fixed) / (pre ? 32 : 18)) / 64 * 64;
+    int fit = 256;
+    for (int occ = per_sm; occ >= (per_sm > 2 ? per_sm - 1 : per_sm); occ--) {
+        const size_t per_cta = (size_t)(ctx->smem_optin + 1024) / occ - 1024;
+        fit = (int)((per_cta - fixed) / (pre ? 32 : 18)) / 64 * 64;
+        if (cap <= fit) break;
+    }
     if (cap > fit) cap = fit;
     if (cap < 256) cap = 256;
     return cap;
