@@ -39,6 +39,12 @@ WORKLOAD = ('configs[2]: calc_power, 1e9 uniform random particles, Lbox=2000, nm
             'interlaced, 100 k x 10 mu bins, poles 0/2/4')
 
 
+# DRAM traffic per launch of the kernels at the default workload, from `ncu --set full` captures of this very
+# command (profiles/r1_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum.
+NCU_TRAFFIC_CONFIG3 = {'tsc_tile_deposit': 25.2e9, 'tsc_bucket_scatter': 3.54e9, 'tsc_bucket_hist': 0.86e9,
+                       'normalize_field': 8.55e9}
+
+
 def peaks():
     p = ROOT / 'MEASURED_PEAKS.json'
     if p.exists():
@@ -297,7 +303,8 @@ def run_gpu_arm(args):
                         'achieved_gbs': (b / (tot_ms / cnt * 1e-3) / 1e9) if b else None}
     top = max(stages, key=lambda k: stages[k]['ms_per_step'])
     roof = {'bound': 'hbm', 'kernel': top, 'achieved': stages[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
-            'frac': (stages[top]['achieved_gbs'] / peak) if stages[top]['achieved_gbs'] else None, 'traffic': None,
+            'frac': (stages[top]['achieved_gbs'] / peak) if stages[top]['achieved_gbs'] else None,
+            'traffic': (NCU_TRAFFIC_CONFIG3.get(top) if not (args.nparticles or args.nmesh) else None),
             'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms}
 
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
