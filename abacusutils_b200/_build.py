@@ -13,12 +13,12 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libabk.so'
-SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu']
+SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu', 'abk_kfields.cu']
 CUDA_HOME = os.environ.get('CUDA_HOME', '/usr/local/cuda')
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-    '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--shared',
+    '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--shared', '--extended-lambda',
     # IEEE division/sqrt and no FMA contraction surprises in the parity-critical paths:
     # the kernels use explicit intrinsics where rounding matters; fast-math stays OFF.
     '-Xptxas', '-v',

@@ -699,8 +699,67 @@ def pk_to_xi(Pk, Lbox, r_bins, poles=[0, 2, 4]):
 
 
 def get_delta_mu2(delta, n1d, dtype_c=np.complex64, dtype_f=np.float32):
-    """``delta(k) * mu^2`` (reference: power_spectrum.py:577-617) -- next on the roadmap, not yet on the GPU."""
-    raise NotImplementedError('get_delta_mu2 is not implemented on the GPU path yet')
+    """``delta(k) * mu^2`` for a Fourier field of shape (n1d, n1d, n1d//2+1), complex64
+    (reference: power_spectrum.py:577-617)."""
+    import torch
+
+    on_device = is_torch_tensor(delta) and delta.is_cuda
+    eng = Engine.get(delta.device if on_device else None)
+    eng.bind_stream()
+    d = eng.to_device(delta, torch.complex64)
+    n = int(n1d)
+    if tuple(d.shape) != (n, n, n // 2 + 1):
+        raise ValueError(f'delta must have shape ({n},{n},{n // 2 + 1}), got {tuple(d.shape)}')
+    out = eng.empty(tuple(d.shape), torch.complex64)
+    check(eng.lib.abk_delta_mu2(eng.ctx, ptr(d), ptr(out), n))
+    return out if on_device else out.cpu().numpy()
+
+
+def get_smoothing(n1d, L, R, dtype=np.float32):
+    """Gaussian smoothing kernel ``exp(-k^2 R^2 / 2)`` on the (n1d, n1d, n1d//2+1) mesh, float32 NumPy array
+    (reference: power_spectrum.py:539-574)."""
+    import torch
+
+    eng = Engine.get(None)
+    eng.bind_stream()
+    n = int(n1d)
+    out = eng.empty((n, n, n // 2 + 1), torch.float32)
+    check(eng.lib.abk_smoothing(eng.ctx, ptr(out), n, float(L), float(R)))
+    return out.cpu().numpy().astype(dtype, copy=False)
+
+
+def expand_poles_to_3d(k_ell, P_ell, n1d, L, poles, dtype=np.float32):
+    """Expand multipoles P_l(k) to a 3-D mesh (n1d, n1d, n1d//2+1): ``sum_l interp(k_ell, P_l)(|k|) P_l(mu)``
+    with linear interpolation on the uniform ``k_ell`` grid, clamped at both ends
+    (reference: power_spectrum.py:450-536)."""
+    import torch
+
+    k_ell = np.asarray(k_ell)
+    P_ell = np.asarray(P_ell)
+    poles = np.asarray(poles, dtype=np.int64).reshape(-1)
+    assert np.abs((k_ell[1] - k_ell[0]) - (k_ell[-1] - k_ell[-2])) < 1.0e-6
+    if P_ell.ndim != 2 or P_ell.shape != (len(poles), len(k_ell)):
+        raise ValueError(f'P_ell must have shape (len(poles), len(k_ell)), got {P_ell.shape}')
+    eng = Engine.get(None)
+    eng.bind_stream()
+    n = int(n1d)
+    coef = legendre_coefficients(poles).astype(np.float64)
+    coef /= (2 * poles[:, None] + 1)  # plain P_l here, no (2l+1)
+    tables = eng.to_device(np.concatenate([k_ell.astype(np.float32), P_ell.astype(np.float32).reshape(-1),
+                                           coef.astype(np.float32).reshape(-1)]), torch.float32)
+    Nk, Np = len(k_ell), len(poles)
+    base = tables.data_ptr()
+    out = eng.empty((n, n, n // 2 + 1), torch.float32)
+    ph = (C.c_int32 * Np)(*[int(p) for p in poles])
+    check(eng.lib.abk_expand_poles_to_3d(eng.ctx, ptr(out), n, float(L), C.c_void_p(base), C.c_void_p(base + 4 * Nk), Nk,
+                                         ph, Np, C.c_void_p(base + 4 * Nk * (1 + Np))))
+    return out.cpu().numpy().astype(dtype, copy=False)
+
+
+def bin_kppi(*args, **kwargs):
+    """(k_perp, k_par) binning (power_spectrum.py:303-412) -- not on the GPU path (unused by the reference's
+    own callers; its early `break` over j makes the result depend on the loop order)."""
+    raise NotImplementedError('bin_kppi is not implemented on the GPU path')
 
 
 _ = (warnings, tsc_parallel)

@@ -93,14 +93,22 @@ def tsc_parallel(pos, densgrid, box, weights=None, nthread=-1, wrap=True, nparti
         densgrid = (int(densgrid),) * 3
     user_supplied_grid = not isinstance(densgrid, tuple)
     shape = tuple(int(s) for s in (densgrid if not user_supplied_grid else densgrid.shape))
-    if len(shape) != 3:
-        raise NotImplementedError('abacusutils_b200.tsc_parallel: only 3-D grids are implemented on the GPU path')
+    if len(shape) not in (2, 3):
+        raise ValueError(f'densgrid must be 2-D or 3-D, got shape {shape}')
+    two_d = len(shape) == 2
+    if two_d:
+        # tsc.py:452-468: a 2-D grid gets the 9-point stencil with w_z = 1.  Here it is painted as a
+        # (nx, ny, 1) grid with z = 0: the three z-weights of the 27-point stencil all land on the single
+        # plane and sum to 1 (to float32 round-off).
+        shape3 = shape + (1,)
+    else:
+        shape3 = shape
     if coord != 0:
         # the partition coordinate only steers the reference's CPU schedule; results do not depend on it
         if coord not in (1, 2):
             raise ValueError(f'coord {coord} out of range')
     _validate_npartition(npartition, shape[coord], nthread)
-    if pos.ndim != 2 or pos.shape[1] != 3:
+    if pos.ndim != 2 or pos.shape[1] not in ((2, 3) if two_d else (3,)):
         raise ValueError(f'pos must have shape (N, 3), got {tuple(pos.shape)}')
     if weights is not None and len(weights) != len(pos):
         raise ValueError('weights and pos have different lengths')
@@ -121,17 +129,33 @@ def tsc_parallel(pos, densgrid, box, weights=None, nthread=-1, wrap=True, nparti
     else:
         pos_d = eng.to_device(pos, torch.float32)
     w_d = None if weights is None else eng.to_device(weights, torch.float32)
+    pos_in = pos_d
+    if two_d:
+        # (x, y, 0) copy for the 3-D kernels; the in-place wrap below is applied to the caller's columns
+        pos_d = torch.zeros((N, 3), dtype=torch.float32, device=eng.device)
+        pos_d[:, :2] = pos_in[:, :2]
 
     if wrap and N > 0:
         # tsc.py:171-173: the caller's array is wrapped in place
         flag = eng.zeros((1,), torch.int64)
         check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(pos_d), N, float(box), ptr(flag)))
         changed = int(flag.item())
-        if changed and pos_d is not pos:
+        if two_d and pos.shape[1] == 3 and N > 0:
+            # the reference wraps every column of the caller's array, also an unused third one
+            zcol = pos_in[:, 2].contiguous().view(-1, 1).repeat(1, 3).contiguous()
+            flag2 = eng.zeros((1,), torch.int64)
+            check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(zcol), N, float(box), ptr(flag2)))
+            changed += int(flag2.item())
+            pos_back = torch.cat([pos_d[:, :2], zcol[:, :1]], dim=1)
+        elif two_d:
+            pos_back = pos_d[:, :2]
+        else:
+            pos_back = pos_d
+        if changed and pos_back is not pos:
             if on_device:
-                pos.copy_(pos_d.to(pos.dtype))
+                pos.copy_(pos_back.to(pos.dtype))
             else:
-                np.copyto(pos, pos_d.cpu().numpy().astype(pos.dtype, copy=False))
+                np.copyto(pos, pos_back.cpu().numpy().astype(pos.dtype, copy=False))
 
     # ---- grid on the device -------------------------------------------------------------------------
     grid_is_cuda = user_supplied_grid and is_torch_tensor(densgrid) and densgrid.is_cuda
@@ -139,7 +163,7 @@ def tsc_parallel(pos, densgrid, box, weights=None, nthread=-1, wrap=True, nparti
         grid_d = densgrid
     else:
         grid_d = eng.zeros(shape, torch.float32)
-    deposit_device(eng, pos_d, w_d, grid_d, shape, shape[2], box, offset, wrap=False)
+    deposit_device(eng, pos_d, w_d, grid_d, shape3, shape3[2], box, offset, wrap=False)
 
     if user_supplied_grid:
         if grid_d is not densgrid:

@@ -263,6 +263,18 @@ typedef struct abk_bin_request {
 int abk_power_bin_scratch_bytes(int Nk, int Nmu, int Np, size_t *bytes);
 int abk_power_bin(abk_ctx *ctx, const abk_bin_request *req_h);
 
+/* ---- k-space field helpers of the reference's ZCV modules ------------------------------------- */
+
+/* power_spectrum.py:577-617 `get_delta_mu2`: out = delta * mu^2, complex64 (n,n,n/2+1), mu^2 = k_z^2/|k|^2 (0 at DC) */
+int abk_delta_mu2(abk_ctx *ctx, const void *delta, void *out, int n);
+/* power_spectrum.py:539-574 `get_smoothing`: out[i,j,k] = exp(-|k|^2 R^2 / 2), float32 (n,n,n/2+1) */
+int abk_smoothing(abk_ctx *ctx, float *out, int n, double L, double R);
+/* power_spectrum.py:450-536 `expand_poles_to_3d`: out[i,j,k] = sum_l interp(k_ell, P_ell[l])(|k|) * P_l(mu);
+ * k_ell float32[Nk] (uniform), P_ell float32[Np][Nk], coef float32[Np][ABK_POLE_NCOEF] = P_l as a polynomial
+ * in mu (host-built, WITHOUT the 2l+1 factor), all on the device; poles_h on the host. */
+int abk_expand_poles_to_3d(abk_ctx *ctx, float *out, int n, double L, const float *k_ell, const float *P_ell, int Nk,
+                           const int32_t *poles_h, int Np, const float *coef);
+
 /* ---- multi-GPU helpers (x-slab sharded mesh) ------------------------------------------------ */
 
 /* dst[i] += src[i] over an (nplanes, ny, nz) region of padded grids (ghost-plane accumulation) */

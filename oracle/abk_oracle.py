@@ -327,6 +327,53 @@ def project_3d_to_poles(k_bin_edges, raw_p3d, Lbox, poles):
     return binned_poles, Npoles
 
 
+def _kgrid(n1d):
+    f = np.fft.fftfreq(n1d, 1.0 / n1d).astype(np.int64)
+    fi = np.where(np.arange(n1d) < n1d // 2, np.arange(n1d), np.arange(n1d) - n1d)
+    k = np.arange(n1d // 2 + 1)
+    kmag2 = (fi[:, None, None] ** 2 + fi[None, :, None] ** 2 + k[None, None, :] ** 2).astype(np.float32)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        mu2 = np.where(kmag2 > 0, (k[None, None, :] ** 2).astype(np.float32) / kmag2, np.float32(0)).astype(np.float32)
+    del f
+    return kmag2, mu2
+
+
+def get_delta_mu2(delta, n1d):
+    """power_spectrum.py:577-617 (NumPy restatement)."""
+    _, mu2 = _kgrid(n1d)
+    return (delta * mu2).astype(np.complex64)
+
+
+def get_smoothing(n1d, L, R):
+    """power_spectrum.py:539-574 (NumPy restatement)."""
+    kmag2, _ = _kgrid(n1d)
+    dk = np.float32(2.0 * np.pi / L)
+    dk2 = np.float32(dk**2)
+    R2 = np.float32(R**2)
+    t = (-kmag2 * dk2) * R2
+    return np.exp(t.astype(np.float64) / 2.0).astype(np.float32)
+
+
+def expand_poles_to_3d(k_ell, P_ell, n1d, L, poles):
+    """power_spectrum.py:450-536 (NumPy restatement; P_l evaluated with abko_P_n)."""
+    kmag2, mu2 = _kgrid(n1d)
+    dk = np.float32(2.0 * np.pi / L)
+    k_ell = np.asarray(k_ell, dtype=np.float32)
+    P_ell = np.asarray(P_ell, dtype=np.float32)
+    xd = np.sqrt(kmag2) * dk
+    dx = k_ell[1] - k_ell[0]
+    f = (xd - k_ell[0]) / dx
+    fl = np.clip(f.astype(np.int64), 0, len(k_ell) - 2)
+    out = np.zeros_like(kmag2)
+    pn = np.vectorize(lambda x, ell: P_n(x, ell), otypes=[np.float32])
+    for ip, ell in enumerate(poles):
+        y = P_ell[ip]
+        yd = y[fl] + (f - fl).astype(np.float32) * (y[fl + 1] - y[fl])
+        yd = np.where(xd <= k_ell[0], y[0], np.where(xd >= k_ell[-1], y[-1], yd)).astype(np.float32)
+        out += yd if ell == 0 else yd * pn(mu2, int(ell))
+    return out
+
+
 def pk_to_xi(Pk, Lbox, r_bins, poles=[0, 2, 4]):
     """power_spectrum.py:620-660."""
     from scipy.fft import irfftn

@@ -176,3 +176,35 @@ def cic_field_inputs(c):
     pos = rng.random((c['N'], 3), dtype='f4') * np.float32(c['L'] - 2 * c['L'] / c['nmesh'])
     w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
     return pos, w
+
+
+# ---------------------------------------------------------------- ZCV k-space helpers
+KFIELD_CASES = {
+    'k16': dict(seed=81, n=16, L=200.0, R=7.5, Nk=12, poles=[0, 2, 4]),
+    'k18': dict(seed=82, n=18, L=90.0, R=3.0, Nk=20, poles=[0, 1, 2]),
+}
+
+
+def kfield_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    n = c['n']
+    shp = (n, n, n // 2 + 1)
+    delta = (rng.standard_normal(shp, dtype='f4') + 1j * rng.standard_normal(shp, dtype='f4')).astype(np.complex64)
+    k_ny = np.pi * n / c['L']
+    k_ell = np.linspace(0.1 * k_ny, 1.2 * k_ny, c['Nk'])   # starts above 0 and ends below the mesh corner: both clamps hit
+    P_ell = (rng.random((len(c['poles']), c['Nk'])) * 100).astype(np.float32)
+    return delta, k_ell, P_ell
+
+
+# ---------------------------------------------------------------- 2-D TSC (tsc.py:57-62, 452-468)
+TSC2D_CASES = {
+    'sq36': dict(seed=91, N=3000, box=60.0, shape=(36, 36), weighted=True, offset=0.0, ncol=2),
+    'rect_off': dict(seed=92, N=2500, box=45.0, shape=(20, 48), weighted=False, offset=0.4, ncol=3),
+}
+
+
+def tsc2d_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    pos = rng.random((c['N'], c['ncol']), dtype='f4') * np.float32(c['box'])
+    w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
+    return pos, w

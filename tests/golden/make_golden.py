@@ -168,8 +168,36 @@ def golden_cic():
     np.savez_compressed(HERE / 'reference_cic.npz', **out)
 
 
+def golden_kfields():
+    _, ps = ref_shim.load(num_threads=2)
+    out = {}
+    for name, c in cases.KFIELD_CASES.items():
+        delta, k_ell, P_ell = cases.kfield_inputs(c)
+        out[f'kf/{name}/delta_mu2'] = ps.get_delta_mu2(delta, c['n'])
+        out[f'kf/{name}/smoothing'] = ps.get_smoothing(c['n'], c['L'], c['R'])
+        out[f'kf/{name}/expand'] = ps.expand_poles_to_3d(k_ell, P_ell, c['n'], c['L'], np.asarray(c['poles']))
+    np.savez_compressed(HERE / 'reference_kfields.npz', **out)
+    print('kfields done')
+
+
+def golden_tsc2d():
+    tsc, _ = ref_shim.load(num_threads=2)
+    out = {}
+    for name, c in cases.TSC2D_CASES.items():
+        pos, w = cases.tsc2d_inputs(c)
+        dens = np.zeros(c['shape'], dtype=np.float32)
+        tsc.tsc_parallel(pos, dens, c['box'], weights=w, nthread=2, offset=c['offset'])
+        out[f'tsc2d/{name}'] = dens
+        print('tsc2d', name, dens.sum(dtype='f8'))
+    np.savez_compressed(HERE / 'reference_tsc2d.npz', **out)
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'xi':
+    if len(sys.argv) > 1 and sys.argv[1] == 'tsc2d':
+        golden_tsc2d()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'kfields':
+        golden_kfields()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'xi':
         golden_xi()
     elif len(sys.argv) > 1 and sys.argv[1] == 'cic':
         golden_cic()
@@ -178,3 +206,5 @@ if __name__ == '__main__':
         golden_reference_runs()
         golden_xi()
         golden_cic()
+        golden_kfields()
+        golden_tsc2d()

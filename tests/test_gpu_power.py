@@ -249,3 +249,23 @@ def test_cic_field(ps, name):
     # and TSC still is TSC afterwards (the scheme is per call, not sticky)
     f2 = ps.get_field(pos, c['L'], c['nmesh'], 'TSC', w=w, d=c['d'])
     assert np.abs(f2 - f).max() > 1e-3
+
+
+@pytest.mark.parametrize('name', list(cases.KFIELD_CASES))
+def test_kfield_helpers(ps, name):
+    """get_delta_mu2 / get_smoothing / expand_poles_to_3d (ZCV helpers) vs the unmodified reference."""
+    g = np.load(cases.__file__.replace('cases.py', 'reference_kfields.npz'))
+    c = cases.KFIELD_CASES[name]
+    delta, k_ell, P_ell = cases.kfield_inputs(c)
+    got = ps.get_delta_mu2(delta, c['n'])
+    want = g[f'kf/{name}/delta_mu2']
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    got = ps.get_smoothing(c['n'], c['L'], c['R'])
+    want = g[f'kf/{name}/smoothing']
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-30)
+    got = ps.expand_poles_to_3d(k_ell, P_ell, c['n'], c['L'], np.asarray(c['poles']))
+    want = g[f'kf/{name}/expand']
+    assert got.dtype == want.dtype and got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())

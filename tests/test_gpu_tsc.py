@@ -241,3 +241,17 @@ def test_deposit_with_foreign_bucket_offset(oracle):
         ref = np.zeros((n, n, n), dtype=np.float32)
         oracle.tsc_scatter_serial(pos, ref, box, weights=w, offset=off)
         assert np.allclose(grid.cpu().numpy(), ref, rtol=1e-5, atol=1e-5), off
+
+
+@pytest.mark.parametrize('name', list(cases.TSC2D_CASES))
+def test_two_d_grids(tsc, name):
+    """2-D grids (9-point stencil, tsc.py:452-468) vs the unmodified reference."""
+    g = np.load(cases.__file__.replace('cases.py', 'reference_tsc2d.npz'))
+    c = cases.TSC2D_CASES[name]
+    pos, w = cases.tsc2d_inputs(c)
+    dens = np.zeros(c['shape'], dtype=np.float32)
+    assert tsc.tsc_parallel(pos, dens, c['box'], weights=w, offset=c['offset']) is None
+    want = g[f'tsc2d/{name}']
+    assert np.allclose(dens, want, rtol=1e-4, atol=1e-5)
+    d2 = tsc.tsc_parallel(pos, c['shape'], c['box'], weights=w, offset=c['offset'])
+    assert d2.shape == c['shape'] and np.allclose(d2, want, rtol=1e-4, atol=1e-5)
