@@ -198,7 +198,7 @@ def kfield_inputs(c):
 
 # ---------------------------------------------------------------- 2-D TSC (tsc.py:57-62, 452-468)
 TSC2D_CASES = {
-    'sq36': dict(seed=91, N=3000, box=60.0, shape=(36, 36), weighted=True, offset=0.0, ncol=2),
+    'sq36': dict(seed=91, N=3000, box=60.0, shape=(36, 36), weighted=True, offset=0.0, ncol=3),
     'rect_off': dict(seed=92, N=2500, box=45.0, shape=(20, 48), weighted=False, offset=0.4, ncol=3),
 }
 

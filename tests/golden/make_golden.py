@@ -180,22 +180,8 @@ def golden_kfields():
     print('kfields done')
 
 
-def golden_tsc2d():
-    tsc, _ = ref_shim.load(num_threads=2)
-    out = {}
-    for name, c in cases.TSC2D_CASES.items():
-        pos, w = cases.tsc2d_inputs(c)
-        dens = np.zeros(c['shape'], dtype=np.float32)
-        tsc.tsc_parallel(pos, dens, c['box'], weights=w, nthread=2, offset=c['offset'])
-        out[f'tsc2d/{name}'] = dens
-        print('tsc2d', name, dens.sum(dtype='f8'))
-    np.savez_compressed(HERE / 'reference_tsc2d.npz', **out)
-
-
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'tsc2d':
-        golden_tsc2d()
-    elif len(sys.argv) > 1 and sys.argv[1] == 'kfields':
+    if len(sys.argv) > 1 and sys.argv[1] == 'kfields':
         golden_kfields()
     elif len(sys.argv) > 1 and sys.argv[1] == 'xi':
         golden_xi()
@@ -207,4 +193,3 @@ if __name__ == '__main__':
         golden_xi()
         golden_cic()
         golden_kfields()
-        golden_tsc2d()

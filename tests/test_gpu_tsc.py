@@ -244,14 +244,19 @@ def test_deposit_with_foreign_bucket_offset(oracle):
 
 
 @pytest.mark.parametrize('name', list(cases.TSC2D_CASES))
-def test_two_d_grids(tsc, name):
-    """2-D grids (9-point stencil, tsc.py:452-468) vs the unmodified reference."""
-    g = np.load(cases.__file__.replace('cases.py', 'reference_tsc2d.npz'))
+def test_two_d_grids(tsc, oracle, name):
+    """2-D grids (documented at tsc.py:57-62).  The reference's own 2-D branch does not compile under Numba
+    (3-index store into a 2-D array, tsc.py:471: typing error [probed]), so there is no reference output;
+    the expected result is the 9-point stencil = the 27-point deposit onto an (nx, ny, 1) grid at z = 0."""
     c = cases.TSC2D_CASES[name]
     pos, w = cases.tsc2d_inputs(c)
     dens = np.zeros(c['shape'], dtype=np.float32)
-    assert tsc.tsc_parallel(pos, dens, c['box'], weights=w, offset=c['offset']) is None
-    want = g[f'tsc2d/{name}']
-    assert np.allclose(dens, want, rtol=1e-4, atol=1e-5)
-    d2 = tsc.tsc_parallel(pos, c['shape'], c['box'], weights=w, offset=c['offset'])
-    assert d2.shape == c['shape'] and np.allclose(d2, want, rtol=1e-4, atol=1e-5)
+    assert tsc.tsc_parallel(pos.copy(), dens, c['box'], weights=w, offset=c['offset']) is None
+    p3 = np.zeros((len(pos), 3), dtype=np.float32)
+    p3[:, :2] = pos[:, :2]
+    want = np.zeros(c['shape'] + (1,), dtype=np.float32)
+    oracle.tsc_scatter_serial(p3, want, c['box'], weights=w, offset=c['offset'])
+    assert np.allclose(dens, want[:, :, 0], rtol=1e-4, atol=1e-5)
+    assert np.isclose(dens.sum(dtype='f8'), len(pos) if w is None else w.sum(dtype='f8'), rtol=1e-6)
+    d2 = tsc.tsc_parallel(pos[:, :2].copy(), c['shape'], c['box'], weights=w, offset=c['offset'])
+    assert d2.shape == c['shape'] and np.allclose(d2, dens, rtol=1e-6, atol=1e-7)
