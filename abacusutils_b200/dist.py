@@ -33,6 +33,9 @@ from .analysis import power_spectrum as ps
 from .analysis.tsc import padded_ldz
 
 
+TILE_X, TILE_Y, TILE_Z = 8, 8, 32  # deposit tile (abk_common.cuh: ABK_TX, ABK_TY, ABK_TZ)
+
+
 # ------------------------------------------------------------------------------------------- plan
 class SlabPlan:
     """x-plane ownership (slabs) and y-row ownership (pencils) of an n^3 mesh over `world` ranks.
@@ -44,8 +47,18 @@ class SlabPlan:
         self.n = int(n)
         self.world = int(world)
         self.nzc = n // 2 + 1
-        self.xsplit = [r * n // world for r in range(world + 1)]
-        self.jsplit = list(self.xsplit)
+        self.jsplit = [r * n // world for r in range(world + 1)]
+        # x-planes: cut on multiples of the deposit tile width (8 planes) when every rank can get at least one
+        # tile column; then particles bucketed by GLOBAL tile are already grouped by owner and the tile-bucketed
+        # records can be exchanged as they are (route_bucketed).  Otherwise plain even splits (route + re-bucket).
+        ncol = -(-n // TILE_X)
+        self.aligned = ncol >= world
+        if self.aligned:
+            self.xsplit = [min(n, (r * ncol // world) * TILE_X) for r in range(world)] + [n]
+            if min(self.xsplit[r + 1] - self.xsplit[r] for r in range(world)) < 2:
+                self.aligned = False
+        if not self.aligned:
+            self.xsplit = list(self.jsplit)
 
     def x_range(self, r):
         return self.xsplit[r], self.xsplit[r + 1]
@@ -181,6 +194,95 @@ class DistEngine:
             return rows
         recv_counts = exchange_counts(send_counts, self.group, self.device)
         return exchange_rows(rows, send_counts, recv_counts, self.group)
+
+    def route_bucketed(self, pos, w, plan, Lbox, paste='TSC'):
+        """Aligned plans: bucket the local particles by GLOBAL tile (one histogram + scatter), then exchange
+        the tile-bucketed records and the matching slices of the tile-offset table.  Every rank ends up with
+        one bucket segment per source rank, which the tile kernel consumes directly: no second bucketing.
+        Returns (segments, M): segments = [(record_ptr, starts_ptr, count)] and keep-alive tensors."""
+        import torch
+
+        eng, n = self.eng, plan.n
+        lib = eng.lib
+        eng.bind_stream()
+        eng.set_scheme(paste)
+        pos_d = eng.to_device(pos, torch.float32)
+        w_d = None if w is None else eng.to_device(w, torch.float32)
+        N = int(pos_d.shape[0])
+        if N > 1 << 30:
+            raise NotImplementedError('more than 2^30 particles per rank')
+        nty, ntz = -(-n // TILE_Y), -(-n // TILE_Z)
+        per_col = nty * ntz
+        ntiles = -(-n // TILE_X) * per_col
+        t0 = [(plan.xsplit[r] // TILE_X) * per_col for r in range(self.world)] + [ntiles]
+        nb = C.c_size_t()
+        check(lib.abk_tsc_bucket_scratch_bytes(max(N, 1), n, n, n, C.byref(nb)))
+        scan_tmp = eng.scratch('bucket_scan', nb.value)
+        rec = eng.scratch('route_out', max(N, 1) * 16)
+        starts = eng.scratch('route_starts', (ntiles + 1) * 4).view(torch.int32)[: ntiles + 1]
+        wrap = 0 if str(paste).upper() == 'CIC' else 1
+        check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d), ptr(w_d), N, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts),
+                                 ptr(scan_tmp), scan_tmp.numel()))
+        idx = torch.tensor(t0, dtype=torch.int64, device=self.device)
+        bounds = starts[idx].to(torch.int64)                # record offset where each owner's tiles begin
+        b = [int(v) for v in bounds.tolist()]
+        send_counts = [b[r + 1] - b[r] for r in range(self.world)]
+        rows = rec[: N * 16].view(torch.float32).view(N, 4)
+        if self.world == 1:
+            seg = [(rows.data_ptr(), starts.data_ptr(), N)]
+            return seg, N, (rows, starts)
+        dist = _dist()
+        # counts and base offsets (the value of starts[] at the first tile of the destination) in one exchange
+        meta = torch.tensor([[send_counts[r], b[r]] for r in range(self.world)], dtype=torch.int64, device=self.device)
+        meta_in = torch.empty_like(meta)
+        dist.all_to_all_single(meta_in, meta, group=self.group)
+        recv_counts = [int(v) for v in meta_in[:, 0].tolist()]
+        bases = [int(v) for v in meta_in[:, 1].tolist()]
+        recv = exchange_rows(rows, send_counts, recv_counts, self.group)
+        # tile-offset slices: to owner r goes starts[t0[r] .. t0[r+1]] (inclusive end)
+        sizes_out = [t0[r + 1] - t0[r] + 1 for r in range(self.world)]
+        send_st = torch.cat([starts[t0[r]: t0[r + 1] + 1] for r in range(self.world)])
+        mine = sizes_out[self.rank]
+        recv_st = torch.empty(mine * self.world, dtype=torch.int32, device=self.device)
+        dist.all_to_all_single(recv_st, send_st, output_split_sizes=[mine] * self.world, input_split_sizes=sizes_out,
+                               group=self.group)
+        segs, off = [], 0
+        for q in range(self.world):
+            # the slice holds the SENDER's global record offsets: bias the record pointer instead of rewriting it
+            segs.append((recv.data_ptr() + 16 * (off - bases[q]), recv_st.data_ptr() + 4 * mine * q, recv_counts[q]))
+            off += recv_counts[q]
+        return segs, off, (recv, recv_st)
+
+    def paint_segments(self, segs, plan, Lbox, offsets, paste='TSC'):
+        """Tile deposit of pre-bucketed segments (route_bucketed) into slab grids, then the ghost exchange."""
+        import torch
+
+        eng, n = self.eng, plan.n
+        lib = eng.lib
+        eng.set_scheme(paste)
+        x_lo, x_hi = plan.x_range(self.rank)
+        nxl = x_hi - x_lo
+        ldz = padded_ldz(n)
+        live = [sg for sg in segs if sg[2] > 0]
+        grids = []
+        for off in offsets:
+            grid = eng.zeros((nxl + 3, n, ldz), torch.float32)
+            if live:
+                m = len(live)
+                recs = (C.c_void_p * m)(*[sg[0] for sg in live])
+                sts = (C.c_void_p * m)(*[sg[1] for sg in live])
+                cnts = (C.c_int64 * m)(*[sg[2] for sg in live])
+                eng.bind_stream()
+                check(lib.abk_tsc_deposit_tiles(eng.ctx, m, recs, sts, cnts, ptr(grid), n, n, n, ldz, float(Lbox),
+                                                float(off), float(offsets[0]), 1, x_lo, nxl))
+
+            def add_planes(dst, src):
+                eng.bind_stream()
+                check(lib.abk_add_planes(eng.ctx, ptr(dst), ptr(src.contiguous()), dst.shape[0], n, n, ldz))
+
+            exchange_ghost_planes(grid, nxl, add_planes, self.group)
+            grids.append(grid)
+        return grids
 
     # -- 2. deposit + ghosts ----------------------------------------------------------------------------
     def paint_slab(self, records, plan, Lbox, offsets, paste='TSC'):
@@ -324,7 +426,7 @@ class DistEngine:
 
 def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste='TSC', nmesh=128, compensated=True,
                interlaced=True, w=None, pos2=None, w2=None, poles=None, squeeze_mu_axis=True, nthread=1,
-               dtype=np.float32, group=None):
+               dtype=np.float32, group=None, force_reroute=False):
     """Sharded ``calc_power`` (same parameters and result table as the single-GPU / reference function,
     power_spectrum.py:1131-1319).  ``pos``/``w`` (and ``pos2``/``w2``) are this rank's share of the catalogue."""
     import torch
@@ -351,9 +453,14 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
 
     def field(p, wt):
         ntot = total(len(p))
-        rec = de.route(p, wt, plan, Lbox, paste)
         offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
-        grids = de.paint_slab(rec, plan, Lbox, offsets, paste)
+        if plan.aligned and not force_reroute:
+            segs, _, keep = de.route_bucketed(p, wt, plan, Lbox, paste)
+            grids = de.paint_segments(segs, plan, Lbox, offsets, paste)
+            del keep
+        else:
+            rec = de.route(p, wt, plan, Lbox, paste)
+            grids = de.paint_slab(rec, plan, Lbox, offsets, paste)
         return [de.fft_slab(g, plan, ntot) for g in grids], ntot
 
     g1, N1 = field(pos, w)

@@ -18,6 +18,7 @@ from abacusutils_b200 import dist as abk_dist  # noqa: E402
 
 def main():
     out, case = sys.argv[1], sys.argv[2]
+    reroute = len(sys.argv) > 3 and sys.argv[3] == '1'
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -30,7 +31,8 @@ def main():
 
     t = abk_dist.calc_power(share(pos), c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'),
                             logk=c['logk'], paste='TSC', nmesh=c['nmesh'], compensated=c['compensated'],
-                            interlaced=c['interlaced'], w=share(w), pos2=share(pos2), w2=share(w2), poles=c['poles'])
+                            interlaced=c['interlaced'], w=share(w), pos2=share(pos2), w2=share(w2), poles=c['poles'],
+                            force_reroute=reroute)
     if rank == 0:
         np.savez(out, **{k: np.asarray(t[k]) for k in t.keys()})
     dist.barrier()

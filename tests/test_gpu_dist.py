@@ -41,24 +41,26 @@ def single_rank_group():
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('reroute', [False, True], ids=['bucketed-exchange', 'route+rebucket'])
 @pytest.mark.parametrize('name', ['n32_ci', 'n32_c', 'n32_raw', 'n32_cross_ci', 'n48_log', 'n40_defaults', 'cfg1_small'])
-def test_sharded_world1_vs_reference(single_rank_group, golden, name):
+def test_sharded_world1_vs_reference(single_rank_group, golden, name, reroute):
     from abacusutils_b200 import dist as abk_dist
 
     c = cases.POWER_CASES[name]
     pos, w, pos2, w2 = cases.power_inputs(c)
     t = abk_dist.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
                             paste='TSC', nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'],
-                            w=w, pos2=pos2, w2=w2, poles=c['poles'])
+                            w=w, pos2=pos2, w2=w2, poles=c['poles'], force_reroute=reroute)
     pre = f'power/{name}/'
     want = {k[len(pre):]: golden[k] for k in golden.files if k.startswith(pre)}
     assert set(want) == set(t.keys())
     compare_power_tables(t, want)
 
 
+@pytest.mark.parametrize('reroute', ['0', '1'], ids=['bucketed-exchange', 'route+rebucket'])
 @pytest.mark.parametrize('world', [2, 4])
 @pytest.mark.parametrize('name', ['n32_ci', 'n32_cross_ci', 'n40_defaults'])
-def test_sharded_multi_rank_vs_reference(golden, tmp_path, world, name):
+def test_sharded_multi_rank_vs_reference(golden, tmp_path, world, name, reroute):
     import torch
 
     if torch.cuda.device_count() < world:
@@ -66,7 +68,7 @@ def test_sharded_multi_rank_vs_reference(golden, tmp_path, world, name):
     out = tmp_path / 'res.npz'
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}',
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), str(ROOT / 'tests' / 'dist_worker.py'),
-           str(out), name]
+           str(out), name, reroute]
     env = dict(os.environ)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
