@@ -198,8 +198,9 @@ class DistEngine:
     def route_bucketed(self, pos, w, plan, Lbox, paste='TSC'):
         """Aligned plans: bucket the local particles by GLOBAL tile (one histogram + scatter), then exchange
         the tile-bucketed records and the matching slices of the tile-offset table.  Every rank ends up with
-        one bucket segment per source rank, which the tile kernel consumes directly: no second bucketing.
-        Returns (segments, M): segments = [(record_ptr, starts_ptr, count)] and keep-alive tensors."""
+        one bucket segment per (source rank, local chunk of <= 2^30 particles), which the tile kernel consumes
+        directly: no second bucketing.  Returns (segments, M, keep-alive) with segments = [(record_ptr,
+        starts_ptr, count)]."""
         import torch
 
         eng, n = self.eng, plan.n
@@ -209,49 +210,65 @@ class DistEngine:
         pos_d = eng.to_device(pos, torch.float32)
         w_d = None if w is None else eng.to_device(w, torch.float32)
         N = int(pos_d.shape[0])
-        if N > 1 << 30:
-            raise NotImplementedError('more than 2^30 particles per rank')
         nty, ntz = -(-n // TILE_Y), -(-n // TILE_Z)
         per_col = nty * ntz
         ntiles = -(-n // TILE_X) * per_col
         t0 = [(plan.xsplit[r] // TILE_X) * per_col for r in range(self.world)] + [ntiles]
+        CH = 1 << 30
+        nchunk_local = max(1, -(-N // CH))
+        # every rank must take part in the same number of exchanges
+        nchunk = nchunk_local
+        if self.world > 1:
+            t = torch.tensor([nchunk_local], dtype=torch.int64, device=self.device)
+            _dist().all_reduce(t, op=_dist().ReduceOp.MAX, group=self.group)
+            nchunk = int(t.item())
+        if nchunk * self.world > 16:
+            raise NotImplementedError(f'{nchunk} local chunks x {self.world} ranks exceed the 16 bucket segments of the tile kernel')
         nb = C.c_size_t()
-        check(lib.abk_tsc_bucket_scratch_bytes(max(N, 1), n, n, n, C.byref(nb)))
+        check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, CH), 1), n, n, n, C.byref(nb)))
         scan_tmp = eng.scratch('bucket_scan', nb.value)
-        rec = eng.scratch('route_out', max(N, 1) * 16)
-        starts = eng.scratch('route_starts', (ntiles + 1) * 4).view(torch.int32)[: ntiles + 1]
         wrap = 0 if str(paste).upper() == 'CIC' else 1
-        check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d), ptr(w_d), N, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts),
-                                 ptr(scan_tmp), scan_tmp.numel()))
         idx = torch.tensor(t0, dtype=torch.int64, device=self.device)
-        bounds = starts[idx].to(torch.int64)                # record offset where each owner's tiles begin
-        b = [int(v) for v in bounds.tolist()]
-        send_counts = [b[r + 1] - b[r] for r in range(self.world)]
-        rows = rec[: N * 16].view(torch.float32).view(N, 4)
-        if self.world == 1:
-            seg = [(rows.data_ptr(), starts.data_ptr(), N)]
-            return seg, N, (rows, starts)
-        dist = _dist()
-        # counts and base offsets (the value of starts[] at the first tile of the destination) in one exchange
-        meta = torch.tensor([[send_counts[r], b[r]] for r in range(self.world)], dtype=torch.int64, device=self.device)
-        meta_in = torch.empty_like(meta)
-        dist.all_to_all_single(meta_in, meta, group=self.group)
-        recv_counts = [int(v) for v in meta_in[:, 0].tolist()]
-        bases = [int(v) for v in meta_in[:, 1].tolist()]
-        recv = exchange_rows(rows, send_counts, recv_counts, self.group)
-        # tile-offset slices: to owner r goes starts[t0[r] .. t0[r+1]] (inclusive end)
-        sizes_out = [t0[r + 1] - t0[r] + 1 for r in range(self.world)]
-        send_st = torch.cat([starts[t0[r]: t0[r + 1] + 1] for r in range(self.world)])
-        mine = sizes_out[self.rank]
-        recv_st = torch.empty(mine * self.world, dtype=torch.int32, device=self.device)
-        dist.all_to_all_single(recv_st, send_st, output_split_sizes=[mine] * self.world, input_split_sizes=sizes_out,
-                               group=self.group)
-        segs, off = [], 0
-        for q in range(self.world):
-            # the slice holds the SENDER's global record offsets: bias the record pointer instead of rewriting it
-            segs.append((recv.data_ptr() + 16 * (off - bases[q]), recv_st.data_ptr() + 4 * mine * q, recv_counts[q]))
-            off += recv_counts[q]
-        return segs, off, (recv, recv_st)
+        segs, keep, total = [], [], 0
+        for c in range(nchunk):
+            a, bnd = min(c * CH, N), min((c + 1) * CH, N)
+            m = bnd - a
+            rec = eng.scratch(f'route_out{c}', max(m, 1) * 16)
+            starts = eng.scratch(f'route_starts{c}', (ntiles + 1) * 4).view(torch.int32)[: ntiles + 1]
+            check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
+                                     m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), ptr(scan_tmp),
+                                     scan_tmp.numel()))
+            rows = rec[: m * 16].view(torch.float32).view(m, 4)
+            if self.world == 1:
+                segs.append((rows.data_ptr(), starts.data_ptr(), m))
+                keep += [rows, starts]
+                total += m
+                continue
+            dist = _dist()
+            b = [int(v) for v in starts[idx].to(torch.int64).tolist()]  # record offset where each owner's tiles begin
+            send_counts = [b[r + 1] - b[r] for r in range(self.world)]
+            # counts and base offsets (value of starts[] at the first tile of the destination) in one exchange
+            meta = torch.tensor([[send_counts[r], b[r]] for r in range(self.world)], dtype=torch.int64, device=self.device)
+            meta_in = torch.empty_like(meta)
+            dist.all_to_all_single(meta_in, meta, group=self.group)
+            recv_counts = [int(v) for v in meta_in[:, 0].tolist()]
+            bases = [int(v) for v in meta_in[:, 1].tolist()]
+            recv = exchange_rows(rows, send_counts, recv_counts, self.group)
+            # tile-offset slices: to owner r goes starts[t0[r] .. t0[r+1]] (inclusive end)
+            sizes_out = [t0[r + 1] - t0[r] + 1 for r in range(self.world)]
+            send_st = torch.cat([starts[t0[r]: t0[r + 1] + 1] for r in range(self.world)])
+            mine = sizes_out[self.rank]
+            recv_st = torch.empty(mine * self.world, dtype=torch.int32, device=self.device)
+            dist.all_to_all_single(recv_st, send_st, output_split_sizes=[mine] * self.world, input_split_sizes=sizes_out,
+                                   group=self.group)
+            off = 0
+            for q in range(self.world):
+                # the slice holds the SENDER's record offsets: bias the record pointer instead of rewriting it
+                segs.append((recv.data_ptr() + 16 * (off - bases[q]), recv_st.data_ptr() + 4 * mine * q, recv_counts[q]))
+                off += recv_counts[q]
+            keep += [recv, recv_st]
+            total += off
+        return segs, total, keep
 
     def paint_segments(self, segs, plan, Lbox, offsets, paste='TSC', bucket_offset=None):
         """Tile deposit of pre-bucketed segments (route_bucketed) into slab grids, then the ghost exchange."""
