@@ -529,6 +529,226 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// "Row streaming" variant of the tile deposit: no output tile in shared memory at all.
+// After each x-step a warp holds, for the finished plane, the z-combined contributions of ITS cell row to
+// the three output rows w-1, w, w+1.  The two side rows go through a small double-buffered exchange array;
+// after ONE block barrier every warp adds what its two neighbours sent to its own centre row and reduces
+// the finished 34-float row straight into the grid (coalesced REDG).  Compared with the shared-tile
+// variant this drops the tile zero-fill, two of the three barriers per x-step, the read-modify-writes
+// and the final flush pass, and frees 13.6 KB of shared memory.
+template <int EXT, bool CIC>
+__global__ void __launch_bounds__(TileDom<EXT>::NT, EXT ? 3 : 4)
+tsc_tile_deposit_stream_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
+{
+    using D = TileDom<EXT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int XROW = D::OZ;                           // 34 floats per exchanged row
+    constexpr int XCH_WORDS = 2 * D::NW * 2 * XROW;       // [parity][warp][side 0/2][z]
+    constexpr int REC_OFF_BYTES = ((XCH_WORDS + D::NCELL) * 4 + 15) / 16 * 16;
+    float *xch = reinterpret_cast<float *>(smem_raw);
+    uint32_t *head = reinterpret_cast<uint32_t *>(xch + XCH_WORDS);
+    float4 *srec = reinterpret_cast<float4 *>(smem_raw + REC_OFF_BYTES);
+    uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);
+    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
+    __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
+    constexpr int MAX_OVF = 512;
+    __shared__ uint16_t ovf_v[MAX_OVF], ovf_xyz[MAX_OVF];
+    __shared__ unsigned ovf_cnt;
+
+    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (tid < segs.nseg) {
+        const uint32_t b = segs.starts[tid][tile], e = segs.starts[tid][tile + 1];
+        seg_beg[tid] = b;
+        seg_cnt[tid] = e - b;
+        seg_rec[tid] = segs.rec[tid];
+    }
+    __syncthreads();
+    uint32_t total = 0;
+    for (int s = 0; s < segs.nseg; s++) total += seg_cnt[s];
+    if (total == 0) return;
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int s = 0; s < segs.nseg; s++) { seg_off[s] = run; run += seg_cnt[s]; }
+        seg_off[segs.nseg] = run;
+    }
+
+    const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
+    const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
+
+    // plane-independent pieces of the output addresses of this warp's rows
+    const int64_t sx = (int64_t)P.ny * ldz;
+    const int gz = abk_wrap_cell(z0 + lane, P.nz);
+    const int ozh = lane ? D::OZ - 1 : 0;
+    const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
+    const int gy_c = abk_wrap_cell(y0 + wy, P.ny);  // centre row oy = wy + 1
+    int emit_no = 0;
+
+    for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
+        const int m = (int)min((uint32_t)cap, total - chunk0);
+        for (int c = tid; c < D::NCELL; c += D::NT) head[c] = NIL;
+        if (tid == 0) ovf_cnt = 0;
+        __syncthreads();
+        const int ox_g = P.x_lo + x0;
+        {
+            int sg = 0;
+            for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
+                float4 rr[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int vq = v0 + q * D::NT;
+                    if (vq < m) {
+                        const uint32_t u = chunk0 + vq;
+                        while (u >= seg_off[sg + 1]) sg++;
+                        rr[q] = __ldcs(seg_rec[sg] + seg_beg[sg] + (u - seg_off[sg]));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int v = v0 + q * D::NT;
+                    if (v >= m) break;
+                    const float4 r = rr[q];
+                    int lx, ly, lz;
+                    float dx, dy, dz;
+                    local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_g >= P.nx ? ox_g - P.nx : ox_g, D::NXC, lx, dx);
+                    local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
+                    local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, ABK_TZ, lz, dz);
+                    if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
+                        const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
+                        srec[v] = make_float4(dx, dy, dz, r.w);
+                        next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
+                    } else {
+                        unsigned slot = MAX_OVF;
+                        if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
+                        if (slot < (unsigned)MAX_OVF) {
+                            srec[v] = make_float4(dx, dy, dz, r.w);
+                            ovf_v[slot] = (uint16_t)v;
+                            ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
+                        } else {
+                            deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
+                                           abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {   // queued out-of-domain particles: one warp per particle, one lane per stencil point
+            const int novf = (int)min(ovf_cnt, (unsigned)MAX_OVF);
+            const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
+            for (int q = wy; q < novf; q += D::NW) {
+                const float4 r = srec[ovf_v[q]];
+                const int xyz = ovf_xyz[q];
+                const int lx = xyz >> 10, ly = (xyz >> 6) & 15, lz = xyz & 63;
+                float wx[3], wyv[3], wz[3];
+                mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
+                mas_w<CIC>(r.y, wyv[0], wyv[1], wyv[2]);
+                mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
+                if (lane < 27) {
+                    const float val = (a == 0 ? wx[0] : (a == 1 ? wx[1] : wx[2])) *
+                                      (b == 0 ? wyv[0] : (b == 1 ? wyv[1] : wyv[2])) *
+                                      (c == 0 ? wz[0] : (c == 1 ? wz[1] : wz[2])) * r.w;
+                    const int64_t gx = slab ? (int64_t)(x0 + lx + a) : (int64_t)abk_wrap_cell(x0 + lx + a - 1, P.nx);
+                    const int gy = abk_wrap_cell(y0 + ly + b - 1, P.ny);
+                    const int gzz = abk_wrap_cell(z0 + lz + c - 1, P.nz);
+                    atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gzz, val);
+                }
+            }
+        }
+        // ---- lane <-> cell (row wy, z = lane); rolling 3-plane register window along x ---------------
+        float S0[3][3], S1[3][3], S2[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) S0[b][c] = S1[b][c] = S2[b][c] = 0.0f;
+
+        // emit plane x (local index, -1 .. NXC): exchange side rows, add neighbours, reduce into the grid
+        auto emit = [&](const float (&S)[3][3], int x) {
+            float v[3], h0[3], h1[3];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
+                const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
+                v[b] = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
+                h0[b] = S[b][0];  // lane 0: z = -1
+                h1[b] = S[b][2];  // lane 31: z = 32
+            }
+            float *buf = xch + (emit_no & 1) * (D::NW * 2 * XROW) + wy * (2 * XROW);
+            buf[lane + 1] = v[0];
+            buf[XROW + lane + 1] = v[2];
+            if (lane == 0) { buf[0] = h0[0]; buf[XROW] = h0[2]; }
+            if (lane == 31) { buf[XROW - 1] = h1[0]; buf[2 * XROW - 1] = h1[2]; }
+            __syncthreads();
+            // centre row of this warp: own b=1 + (warp wy-1).b=2 + (warp wy+1).b=0
+            const float *base = xch + (emit_no & 1) * (D::NW * 2 * XROW);
+            float tot = v[1];
+            const float h1c = __shfl_sync(0xffffffffu, h1[1], 31);
+            float toth = (lane == 0) ? h0[1] : h1c;  // lanes 0 / 1 carry the halo cells z = -1 / 32
+            if (wy > 0) {
+                const float *nb = base + (wy - 1) * (2 * XROW) + XROW;  // b = 2 row of the warp below
+                tot += nb[lane + 1];
+                if (lane < 2) toth += nb[ozh];
+            }
+            if (wy < D::NW - 1) {
+                const float *nb = base + (wy + 1) * (2 * XROW);         // b = 0 row of the warp above
+                tot += nb[lane + 1];
+                if (lane < 2) toth += nb[ozh];
+            }
+            const int64_t gx = slab ? (int64_t)(x0 + x + 1) : (int64_t)abk_wrap_cell(x0 + x, P.nx);
+            float *plane = grid + gx * sx;
+            {
+                float *row = plane + (int64_t)gy_c * ldz;
+                if (tot != 0.0f) atomicAdd(row + gz, tot);
+                if (lane < 2 && toth != 0.0f) atomicAdd(row + gzh, toth);
+            }
+            if (wy == 0 || wy == D::NW - 1) {  // the two halo rows oy = 0 / NW + 1 have a single contributor each
+                const int bsel = (wy == 0) ? 0 : 2;
+                const float vv = (bsel == 0) ? v[0] : v[2];
+                const float hh0 = (bsel == 0) ? h0[0] : h0[2], hh1 = (bsel == 0) ? h1[0] : h1[2];
+                const float hh1_31 = __shfl_sync(0xffffffffu, hh1, 31);  // all lanes take part (warp-uniform branch)
+                const float e = (lane == 0) ? hh0 : hh1_31;
+                float *row = plane + (int64_t)abk_wrap_cell(wy == 0 ? y0 - 1 : y0 + D::NW, P.ny) * ldz;
+                if (vv != 0.0f) atomicAdd(row + gz, vv);
+                if (lane < 2 && e != 0.0f) atomicAdd(row + gzh, e);
+            }
+            emit_no++;
+        };
+
+#pragma unroll 1
+        for (int cx = 0; cx < D::NXC; cx++) {
+            uint32_t i = head[(cx * D::NYC + wy) * ABK_TZ + lane];
+            while (i != NIL) {
+                float wx[3], wyW[3], wz[3];
+                const float4 r = srec[i];
+                const uint16_t nxt = next16[i];
+                i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
+                mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
+                mas_w<CIC>(r.y, wyW[0], wyW[1], wyW[2]);
+                mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
+                wyW[0] *= r.w; wyW[1] *= r.w; wyW[2] *= r.w;
+#pragma unroll
+                for (int b = 0; b < 3; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float t = wyW[b] * wz[c];
+                        S0[b][c] = fmaf(wx[0], t, S0[b][c]);
+                        S1[b][c] = fmaf(wx[1], t, S1[b][c]);
+                        S2[b][c] = fmaf(wx[2], t, S2[b][c]);
+                    }
+            }
+            emit(S0, cx - 1);
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
+        }
+        emit(S0, D::NXC - 1);
+        emit(S1, D::NXC);
+        __syncthreads();  // the lists are rebuilt by the next pass
+    }
+}
+
 // validation path: one thread per particle, 27 global reductions in the reference's cell order
 __global__ void __launch_bounds__(256) tsc_naive_kernel(const float *__restrict__ pos, const float *__restrict__ w,
                                                         int64_t N, float *__restrict__ grid, TscParams P, int64_t ldz)
@@ -890,6 +1110,28 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     // records bucketed at another offset: widen the tile's cell domain by one cell in x and y
     const int ext = ((float)bucket_offset != (float)offset) ? 1 : 0;
     const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
+    if (variant == 5) {  // row-streaming kernel
+        const bool cic5 = ctx->scheme == 1;
+        const size_t xch = (size_t)2 * (ext ? TileDom<1>::NW : TileDom<0>::NW) * 2 * (ABK_TZ + 2) * 4;
+        const size_t ncell = ext ? TileDom<1>::NCELL : TileDom<0>::NCELL;
+        const size_t fixed5 = abk_align_up(xch + ncell * 4, 16) + 64;
+        const double mean = g.ntiles > 0 ? (double)n_total / (double)g.ntiles : 0.0;
+        int cap5 = (ctx->tile_capacity & 0xffff) ? (ctx->tile_capacity & 0xffff)
+                                                 : (int)((mean + 5.0 * sqrt(mean + 1.0) + 32.0 + 63.0) / 64.0) * 64;
+        const int occ5 = ext ? 3 : 4;
+        int fit5 = (int)(((size_t)(ctx->smem_optin + 1024) / occ5 - 1024 - fixed5) / 18) / 64 * 64;
+        if (cap5 > fit5) {
+            const int fit5b = (int)(((size_t)(ctx->smem_optin + 1024) / (occ5 - 1) - 1024 - fixed5) / 18) / 64 * 64;
+            cap5 = cap5 <= fit5b ? cap5 : fit5b;
+        }
+        if (cap5 < 256) cap5 = 256;
+        const size_t smem5 = fixed5 + (size_t)cap5 * 18;
+        deposit_kernel_t k5 = ext ? (cic5 ? tsc_tile_deposit_stream_kernel<1, true> : tsc_tile_deposit_stream_kernel<1, false>)
+                                  : (cic5 ? tsc_tile_deposit_stream_kernel<0, true> : tsc_tile_deposit_stream_kernel<0, false>);
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+        ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, k5<<<(unsigned)g.ntiles, ext ? TileDom<1>::NT : TileDom<0>::NT, smem5, ctx->stream>>>(segs, grid, P, ldz, cap5, slab));
+        return ABK_OK;
+    }
     const bool cic = ctx->scheme == 1;
     const bool pre = (variant && !cic) ? ((variant - 1) & 1) : false;
     const bool priv = (variant && !cic) ? (((variant - 1) >> 1) & 1) : false;

@@ -559,6 +559,8 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count()
+    eng.profile(True)
+    eng.profile_collect()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -570,6 +572,8 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
     dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device='cuda', dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    prof = eng.profile_collect()
+    eng.profile(False)
     launches = eng.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -600,6 +604,9 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
                'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
     if rank == 0:
         peak, peak_src = peaks()
+        stages = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps} for k, v in prof.items()}
+        kernel_ms = sum(v['ms_per_step'] for v in stages.values())
+        stages['nccl_and_host (step - kernels, rank 0)'] = {'ms_per_step': float(ms.item()) - kernel_ms}
         line = {
             'metric': metric, 'value': float(ms.item()), 'unit': 'ms', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': float(ms.item()), 'higher_is_better': False, 'scaling': 'strong',
@@ -609,7 +616,7 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * world),
             'roofline': {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
                          'peak_source': peak_src, 'note': 'per-kernel roofline is reported by the N=1 run'},
-            'cpu_baseline': None, 'mpart_per_s': N / float(ms.item()) / 1e3,
+            'cpu_baseline': None, 'stages': stages, 'mpart_per_s': N / float(ms.item()) / 1e3,
             'N_mode_total': int(np.asarray(res['N_mode']).sum()),
         }
         print(json.dumps(line))
