@@ -92,6 +92,7 @@ SIGNATURES = {
     'abk_power_bin': (_i32, [_vp, C.POINTER(BinRequest)]),
     'abk_add_planes': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64]),
     'abk_transpose_pack': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, C.POINTER(_i64)]),
+    'abk_transpose_scatter_p2p': (_i32, [_vp, _vp, C.POINTER(_vp), _i64, _i64, _i64, _i32, C.POINTER(_i64), _i64]),
 }
 
 _lib = None

@@ -13,6 +13,9 @@
 
 namespace {
 
+constexpr int MAX_RANKS = 64;
+struct SplitTable { int64_t v[MAX_RANKS + 1]; };
+
 __device__ __forceinline__ int fold(int i, int n) { return (i < n / 2) ? i : i - n; }
 
 // ------------------------------------------------------------------------------------------
@@ -535,9 +538,6 @@ __global__ void __launch_bounds__(256) add_planes_kernel(float *__restrict__ dst
 }
 
 // slab [nxl][ny][nzc] -> per-destination blocks [nxl][nyl_r][nzc] laid out back to back
-constexpr int MAX_RANKS = 64;
-struct SplitTable { int64_t v[MAX_RANKS + 1]; };
-
 __global__ void __launch_bounds__(256) transpose_pack_kernel(const float2 *__restrict__ slab, float2 *__restrict__ sendbuf,
                                                              int64_t nxl, int64_t ny, int64_t nzc, int nranks,
                                                              SplitTable js)
@@ -555,6 +555,34 @@ __global__ void __launch_bounds__(256) transpose_pack_kernel(const float2 *__res
         const int64_t nyl = s_js[r + 1] - s_js[r];
         const float2 *src = slab + row * nzc;
         float2 *dst = sendbuf + (nxl * s_js[r] + x * nyl + (j - s_js[r])) * nzc;
+        for (int64_t k = lane; k < nzc; k += 32) dst[k] = src[k];
+    }
+}
+
+// Fused pack + transfer of the slab->pencil transpose: every (x, j) row of the local slab is written straight
+// into its final place in the pencil buffer of the rank that owns j, through peer-mapped pointers (NVLink /
+// NVSwitch P2P stores).  One read of the slab, no staging buffer, no separate collective.
+struct PeerTable { float2 *p[MAX_RANKS]; };
+
+__global__ void __launch_bounds__(256) transpose_scatter_p2p_kernel(const float2 *__restrict__ slab, PeerTable peers,
+                                                                    int64_t nxl, int64_t ny, int64_t nzc, int nranks,
+                                                                    SplitTable js, int64_t x_lo)
+{
+    __shared__ int64_t s_js[MAX_RANKS + 1];
+    __shared__ float2 *s_peer[MAX_RANKS];
+    for (int t = threadIdx.x; t <= nranks; t += blockDim.x) s_js[t] = js.v[t];
+    for (int t = threadIdx.x; t < nranks; t += blockDim.x) s_peer[t] = peers.p[t];
+    __syncthreads();
+    const int64_t nrows = nxl * ny;
+    const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < nrows;
+         row += (int64_t)gridDim.x * warps_per_block) {
+        const int64_t x = row / ny, j = row % ny;
+        int r = 0;
+        while (j >= s_js[r + 1]) r++;
+        const int64_t nyl = s_js[r + 1] - s_js[r];
+        const float2 *src = slab + row * nzc;
+        float2 *dst = s_peer[r] + ((x_lo + x) * nyl + (j - s_js[r])) * nzc;
         for (int64_t k = lane; k < nzc; k += 32) dst[k] = src[k];
     }
 }
@@ -770,6 +798,25 @@ extern "C" int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_
     if (nplanes == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_ADD_PLANES,
                add_planes_kernel<<<grid_for(ctx, nplanes * ny * ldz, 256, 16), 256, 0, ctx->stream>>>(dst, src, nplanes * ny, nz, ldz));
+    return ABK_OK;
+}
+
+extern "C" int abk_transpose_scatter_p2p(abk_ctx *ctx, const void *slab, void *const *peer_pencils_h, int64_t nxl,
+                                         int64_t ny, int64_t nzc, int nranks, const int64_t *jsplit_h, int64_t x_lo)
+{
+    ABK_REQUIRE(ctx && slab && peer_pencils_h && nxl >= 0 && ny > 0 && nzc > 0 && nranks > 0 && nranks <= MAX_RANKS && jsplit_h,
+                "abk_transpose_scatter_p2p: bad arguments");
+    ABK_REQUIRE(jsplit_h[0] == 0 && jsplit_h[nranks] == ny, "abk_transpose_scatter_p2p: jsplit must run from 0 to ny");
+    if (nxl == 0) return ABK_OK;
+    SplitTable js;
+    PeerTable pt;
+    for (int r = 0; r <= nranks; r++) js.v[r] = jsplit_h[r];
+    for (int r = 0; r < nranks; r++) {
+        ABK_REQUIRE(peer_pencils_h[r] != nullptr, "abk_transpose_scatter_p2p: null peer pointer for rank %d", r);
+        pt.p[r] = (float2 *)peer_pencils_h[r];
+    }
+    ABK_LAUNCH(ctx, ABK_K_TRANSPOSE_PACK, transpose_scatter_p2p_kernel<<<grid_for(ctx, nxl * ny * 32, 256, 8), 256, 0, ctx->stream>>>(
+                                              (const float2 *)slab, pt, nxl, ny, nzc, nranks, js, x_lo));
     return ABK_OK;
 }
 

@@ -159,6 +159,41 @@ def transpose_slab_to_pencil(packed, plan, rank, group=None):
     return out.view(plan.n, plan.nyl(rank), plan.nzc)
 
 
+# ------------------------------------------------------------------------------------------- peer memory
+_SYMM = {'ok': None, 'bufs': {}}
+
+
+def _symm_pencil(group, nelem, slot, device):
+    """A symmetric-memory (peer-mapped over NVLink) complex64 buffer of `nelem` elements, cached per slot.
+    Returns (tensor, handle) or None when symmetric memory is unavailable (then NCCL all-to-all is used)."""
+    import os
+
+    import torch
+
+    if os.environ.get('ABK_NO_P2P') == '1' or _SYMM['ok'] is False:
+        return None
+    key = (id(group), slot)
+    ent = _SYMM['bufs'].get(key)
+    if ent is not None and ent[0].numel() >= nelem:
+        return ent
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dist = _dist()
+        g = group if group is not None else dist.group.WORLD
+        t = symm_mem.empty(int(nelem), dtype=torch.complex64, device=device)
+        hdl = symm_mem.rendezvous(t, g)
+        _SYMM['ok'] = True
+        _SYMM['bufs'][key] = (t, hdl)
+        return t, hdl
+    except Exception as e:  # pragma: no cover - depends on the platform
+        import warnings
+
+        warnings.warn(f'symmetric memory unavailable ({type(e).__name__}: {e}); the FFT transpose uses NCCL all-to-all')
+        _SYMM['ok'] = False
+        return None
+
+
 # ------------------------------------------------------------------------------------------- pipeline
 class DistEngine:
     def __init__(self, group=None):
@@ -376,7 +411,7 @@ class DistEngine:
         eng.bind_stream()
         check(eng.lib.abk_fft_exec_generic(eng.ctx, plan_h, C.c_void_p(data_ptr), ptr(work), work.numel()))
 
-    def fft_slab(self, grid_box, plan, n_total):
+    def fft_slab(self, grid_box, plan, n_total, slot=0):
         """Normalise the owned planes, 2-D FFT, transpose, 1-D FFT.  Returns the pencil [n][nyl][nzc] complex64.
         `grid_box` is a one-element list holding the slab; it is emptied as soon as the slab has been packed, so
         the slab's memory is free again before the pencil is allocated (35 GB each at nmesh 4096 on 8 GPUs)."""
@@ -391,15 +426,32 @@ class DistEngine:
         check(eng.lib.abk_normalize_field(eng.ctx, ptr(owned), nxl, n, n, ldz, float(n) ** 3, float(n_total)))
         h, wb = self._plan('yz', nxl, n, n)
         self._exec(h, wb, owned.data_ptr())
-        packed = eng.empty((nxl * n * nzc,), torch.complex64)
         js = (C.c_int64 * (self.world + 1))(*plan.jsplit)
-        check(eng.lib.abk_transpose_pack(eng.ctx, ptr(owned), ptr(packed), nxl, n, nzc, self.world, js))
-        del owned, grid
-        grid_box.clear()
-        if self.world == 1:
-            pencil = packed.view(n, nyl, nzc)
+        sym = None
+        if self.world > 1:
+            # every rank allocates the same (largest) pencil size: symmetric memory needs identical shapes
+            sym = _symm_pencil(self.group, n * max(plan.nyl(r) for r in range(self.world)) * nzc, slot, self.device)
+        if sym is not None:
+            # fused pack + transfer: rows go straight into the owners' pencil buffers over NVLink peer memory
+            buf, hdl = sym
+            hdl.barrier(channel=0)  # nobody still reads the buffer's previous contents
+            peers = (C.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+            eng.bind_stream()
+            check(eng.lib.abk_transpose_scatter_p2p(eng.ctx, ptr(owned), peers, nxl, n, nzc, self.world, js,
+                                                    plan.xsplit[self.rank]))
+            hdl.barrier(channel=0)  # every rank's stores have landed
+            del owned, grid
+            grid_box.clear()
+            pencil = buf[: n * nyl * nzc].view(n, nyl, nzc)
         else:
-            pencil = transpose_slab_to_pencil(packed, plan, self.rank, self.group)
+            packed = eng.empty((nxl * n * nzc,), torch.complex64)
+            check(eng.lib.abk_transpose_pack(eng.ctx, ptr(owned), ptr(packed), nxl, n, nzc, self.world, js))
+            del owned, grid
+            grid_box.clear()
+            if self.world == 1:
+                pencil = packed.view(n, nyl, nzc)
+            else:
+                pencil = transpose_slab_to_pencil(packed, plan, self.rank, self.group)
         h, wb = self._plan('x', n, nyl, nzc)
         self._exec(h, wb, pencil.data_ptr())
         return pencil
@@ -480,7 +532,7 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
             dist.all_reduce(t, group=group)
         return int(t.item())
 
-    def field(p, wt):
+    def field(p, wt, slot_base=0):
         ntot = total(len(p))
         offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
         # one grid at a time (paint -> ghosts -> FFT -> drop the slab): at nmesh 4096 on 8 GPUs a slab is 35 GB
@@ -491,16 +543,16 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
                 gb = de.paint_segments(segs, plan, Lbox, [off], paste, bucket_offset=offsets[0])
                 if io == len(offsets) - 1:
                     del keep, segs  # the routed records are dead once the last grid has been painted
-                pencils.append(de.fft_slab(gb, plan, ntot))
+                pencils.append(de.fft_slab(gb, plan, ntot, slot=slot_base + io))
         else:
             rec = de.route(p, wt, plan, Lbox, paste)
-            for off in offsets:
+            for io, off in enumerate(offsets):
                 gb = de.paint_slab(rec, plan, Lbox, [off], paste, bucket_offset=offsets[0])
-                pencils.append(de.fft_slab(gb, plan, ntot))
+                pencils.append(de.fft_slab(gb, plan, ntot, slot=slot_base + io))
         return pencils, ntot
 
     g1, N1 = field(pos, w)
-    g2, N2 = (field(pos2, w2) if pos2 is not None else (None, None))
+    g2, N2 = (field(pos2, w2, slot_base=2) if pos2 is not None else (None, None))
     meta = dict(Lbox=Lbox, logk=logk, paste=paste, nmesh=nmesh, compensated=compensated, interlaced=interlaced,
                 poles=poles, nthread=nthread, N_pos=N1, is_weighted=w is not None, field_dtype=dtype,
                 squeeze_mu_axis=squeeze_mu_axis, n_ranks=de.world)

@@ -287,6 +287,12 @@ int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_t nplanes, 
  * isplit[r]*nyl*nzc, the receive buffer IS the pencil layout [nx][nyl][nzc]. */
 int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf, int64_t nxl, int64_t ny, int64_t nzc,
                        int nranks, const int64_t *jsplit_h);
+/* Fused pack + transfer over NVLink peer memory: row (x, j) of the local slab [nxl][ny][nzc] is stored directly
+ * at its final position [(x_lo + x)][j - jsplit[r]][.] of the pencil buffer of the rank r that owns j.
+ * peer_pencils_h[r] (host array) is the peer-mapped device pointer of rank r's pencil buffer (e.g. from
+ * torch symmetric memory).  The caller synchronises the ranks before (buffer free) and after (writes landed). */
+int abk_transpose_scatter_p2p(abk_ctx *ctx, const void *slab, void *const *peer_pencils_h, int64_t nxl, int64_t ny,
+                              int64_t nzc, int nranks, const int64_t *jsplit_h, int64_t x_lo);
 
 #ifdef __cplusplus
 }
