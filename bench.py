@@ -307,6 +307,30 @@ def run_gpu_arm(args):
             'traffic': (NCU_TRAFFIC_CONFIG3.get(top) if not (args.nparticles or args.nmesh) else None),
             'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms}
 
+    # ---- configs[1]: tsc_parallel of 1e8 weighted particles onto a 512^3 float32 mesh (extra, device-resident) ----
+    cfg2 = None
+    if not (args.nparticles or args.nmesh):
+        from abacusutils_b200.analysis.tsc import tsc_parallel
+
+        torch.cuda.empty_cache()
+        n2 = 100_000_000
+        p2 = torch.rand((n2, 3), device='cuda', dtype=torch.float32, generator=gen) * 1000.0
+        w2 = torch.rand((n2,), device='cuda', dtype=torch.float32, generator=gen)
+        g2 = torch.zeros((512, 512, 512), device='cuda', dtype=torch.float32)
+        for _ in range(2):
+            tsc_parallel(p2, g2, 1000.0, weights=w2)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            tsc_parallel(p2, g2, 1000.0, weights=w2)
+        b.record()
+        torch.cuda.synchronize()
+        t2 = a.elapsed_time(b) / 3
+        cfg2 = {'workload': 'configs[1]: tsc_parallel, 1e8 weighted particles -> 512^3 float32 (device-resident)',
+                'ms': t2, 'gpart_per_s': n2 / t2 / 1e6,
+                'mass_check': float(g2.sum(dtype=torch.float64).item() / (5 * w2.sum(dtype=torch.float64).item()))}
+        del p2, w2, g2
+
     # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
     cpu = None
     if not args.no_cpu:
@@ -324,7 +348,7 @@ def run_gpu_arm(args):
         'config': {'workload': WORKLOAD if not (args.nparticles or args.nmesh) else f'override N={N} nmesh={n}',
                    'l2': 'inputs (12 GB particles, 4.3 GB grids) are larger than the 126 MB L2'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
-        'stages': stages, 'mpart_per_s': N / ms / 1e3,
+        'stages': stages, 'config2_tsc': cfg2, 'mpart_per_s': N / ms / 1e3,
         'tsc_gpart_per_s': (2 * N / (dep_ms * 1e-3) / 1e9) if dep_ms else None,
         'N_mode_total': int(np.asarray(res['N_mode']).sum()),
     }
