@@ -125,6 +125,7 @@ struct BinArgs {
 // the loop.  Loads stay fully coalesced: lanes hold consecutive k of the same (i,j) row.
 constexpr int BIN_NREP = 16;
 constexpr int BIN_UNROLL = 4;
+constexpr int BIN_PF_DIST = 1;  // prefetch distance (steps) of the symmetric kernel
 
 template <int NPN>
 struct LaneAcc {
@@ -415,6 +416,33 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
             const float2 ej = s_ph[aj];
             float sum = 0.0f;
             int members = 0;
+            // software prefetch of the next step's rows into L2->L1: the loop is otherwise latency-bound
+            // (one dependent batch of loads per step)
+            if (k_ok && aj + BIN_PF_DIST <= amax) {
+                const int an = aj + BIN_PF_DIST;
+                const int njn = (an < n / 2 ? 1 : 0) + ((an >= 1 && an <= amax) ? 1 : 0);
+                const int jn1 = (an < n / 2) ? an : n - an, jn2 = n - an;
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    if (mi >= ni_mem) break;
+                    const int i = mi == 0 ? i_first : i_second;
+#pragma unroll
+                    for (int mj = 0; mj < 2; mj++) {
+                        if (mj >= njn) break;
+                        const int64_t idx = (int64_t)i * M.stride_i + (int64_t)(mj == 0 ? jn1 : jn2) * M.stride_j + k;
+                        if (A.real_in) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.real_in + idx));
+                        } else {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f1 + idx));
+                            if (inter1) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F1.fs + idx));
+                            if (cross) {
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f2 + idx));
+                                if (inter2) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F2.fs + idx));
+                            }
+                        }
+                    }
+                }
+            }
             if (use) {
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) {
@@ -429,20 +457,20 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
                         const int64_t idx = (int64_t)i * M.stride_i + (int64_t)j * M.stride_j + k;
                         float v;
                         if (A.real_in) {
-                            v = __ldcs(A.real_in + idx);
+                            v = __ldg(A.real_in + idx);
                         } else {
-                            float2 a = __ldcs(A.f1 + idx);
+                            float2 a = __ldg(A.f1 + idx);
                             // phase = eki * e^{+- i pi aj / n}
                             const float2 ph = make_float2(eki.x * ej.x - sg * eki.y * ej.y, eki.y * ej.x + sg * eki.x * ej.y);
                             if (inter1) {
-                                const float2 b = __ldcs(A.F1.fs + idx);
+                                const float2 b = __ldg(A.F1.fs + idx);
                                 a.x += b.x * ph.x - b.y * ph.y;
                                 a.y += b.x * ph.y + b.y * ph.x;
                             }
                             if (cross) {
-                                float2 c = __ldcs(A.f2 + idx);
+                                float2 c = __ldg(A.f2 + idx);
                                 if (inter2) {
-                                    const float2 d = __ldcs(A.F2.fs + idx);
+                                    const float2 d = __ldg(A.F2.fs + idx);
                                     c.x += d.x * ph.x - d.y * ph.y;
                                     c.y += d.x * ph.y + d.y * ph.x;
                                 }
