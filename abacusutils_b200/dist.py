@@ -110,6 +110,44 @@ def exchange_rows(rows, send_counts, recv_counts, group=None):
     return out
 
 
+def exchange_bucketed(rows, starts, t0, group=None):
+    """Exchange tile-bucketed records between ranks (aligned slab plans).
+
+    rows   : (N, 4) float32 records sorted by GLOBAL tile id (abk_tsc_bucket)
+    starts : (ntiles + 1,) int32 exclusive tile offsets into `rows`
+    t0     : list of world + 1 global tile ids; rank r owns tiles [t0[r], t0[r+1])
+    Returns a list with one entry per source rank q: (records (M_q, 4), starts_slice (ntiles_me + 1,), base_q)
+    where starts_slice holds the SENDER's offsets: records of local tile t are
+    records[starts_slice[t] - base_q : starts_slice[t + 1] - base_q].
+    """
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    idx = torch.tensor(t0, dtype=torch.int64, device=starts.device)
+    b = [int(v) for v in starts[idx].to(torch.int64).tolist()]  # record offset where each owner's tiles begin
+    send_counts = [b[r + 1] - b[r] for r in range(world)]
+    # counts and base offsets (value of starts[] at the first tile of the destination) in one exchange
+    meta = torch.tensor([[send_counts[r], b[r]] for r in range(world)], dtype=torch.int64, device=starts.device)
+    meta_in = torch.empty_like(meta)
+    dist.all_to_all_single(meta_in, meta, group=group)
+    recv_counts = [int(v) for v in meta_in[:, 0].tolist()]
+    bases = [int(v) for v in meta_in[:, 1].tolist()]
+    recv = exchange_rows(rows, send_counts, recv_counts, group)
+    # tile-offset slices: to owner r goes starts[t0[r] .. t0[r+1]] (inclusive end)
+    sizes_out = [t0[r + 1] - t0[r] + 1 for r in range(world)]
+    send_st = torch.cat([starts[t0[r]: t0[r + 1] + 1] for r in range(world)])
+    mine = sizes_out[rank]
+    recv_st = torch.empty(mine * world, dtype=torch.int32, device=starts.device)
+    dist.all_to_all_single(recv_st, send_st, output_split_sizes=[mine] * world, input_split_sizes=sizes_out, group=group)
+    out, off = [], 0
+    for q in range(world):
+        out.append((recv[off: off + recv_counts[q]], recv_st[mine * q: mine * (q + 1)], bases[q]))
+        off += recv_counts[q]
+    return out
+
+
 def exchange_ghost_planes(grid, nxl, add_planes, group=None):
     """Ring exchange of the ghost planes of a slab grid laid out as
         plane 0          : ghost  x_lo - 1        -> added to the LEFT neighbour's last owned plane
@@ -263,7 +301,6 @@ class DistEngine:
         check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, CH), 1), n, n, n, C.byref(nb)))
         scan_tmp = eng.scratch('bucket_scan', nb.value)
         wrap = 0 if str(paste).upper() == 'CIC' else 1
-        idx = torch.tensor(t0, dtype=torch.int64, device=self.device)
         segs, keep, total = [], [], 0
         for c in range(nchunk):
             a, bnd = min(c * CH, N), min((c + 1) * CH, N)
@@ -283,31 +320,15 @@ class DistEngine:
                 keep += [rows, starts]
                 total += m
                 continue
-            dist = _dist()
-            b = [int(v) for v in starts[idx].to(torch.int64).tolist()]  # record offset where each owner's tiles begin
-            send_counts = [b[r + 1] - b[r] for r in range(self.world)]
-            # counts and base offsets (value of starts[] at the first tile of the destination) in one exchange
-            meta = torch.tensor([[send_counts[r], b[r]] for r in range(self.world)], dtype=torch.int64, device=self.device)
-            meta_in = torch.empty_like(meta)
-            dist.all_to_all_single(meta_in, meta, group=self.group)
-            recv_counts = [int(v) for v in meta_in[:, 0].tolist()]
-            bases = [int(v) for v in meta_in[:, 1].tolist()]
-            recv = exchange_rows(rows, send_counts, recv_counts, self.group)
-            # tile-offset slices: to owner r goes starts[t0[r] .. t0[r+1]] (inclusive end)
-            sizes_out = [t0[r + 1] - t0[r] + 1 for r in range(self.world)]
-            send_st = torch.cat([starts[t0[r]: t0[r + 1] + 1] for r in range(self.world)])
-            mine = sizes_out[self.rank]
-            recv_st = torch.empty(mine * self.world, dtype=torch.int32, device=self.device)
-            dist.all_to_all_single(recv_st, send_st, output_split_sizes=[mine] * self.world, input_split_sizes=sizes_out,
-                                   group=self.group)
+            parts = exchange_bucketed(rows, starts, t0, self.group)
             off = 0
-            for q in range(self.world):
+            for recs_q, st_q, base_q in parts:
                 # the slice holds the SENDER's record offsets: bias the record pointer instead of rewriting it
-                segs.append((recv.data_ptr() + 16 * (off - bases[q]), recv_st.data_ptr() + 4 * mine * q, recv_counts[q]))
-                off += recv_counts[q]
-            keep += [recv, recv_st]
+                segs.append((recs_q.data_ptr() - 16 * base_q, st_q.data_ptr(), int(recs_q.shape[0])))
+                off += int(recs_q.shape[0])
+            keep.append(parts)
             total += off
-            del rec, rows, starts, send_st
+            del rec, rows, starts
         return segs, total, keep
 
     def paint_segments(self, segs, plan, Lbox, offsets, paste='TSC', bucket_offset=None):

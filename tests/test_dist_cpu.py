@@ -151,3 +151,57 @@ def _transpose(rank, world, n):
 @pytest.mark.parametrize('world,n', [(2, 12), (3, 10)])
 def test_transpose(world, n):
     _run(_transpose, world, n)
+
+
+def _tile_ids(pos, n, box):
+    c = (np.rint(pos * np.float32(n / box)).astype(np.int64)) % n
+    nty, ntz = -(-n // 8), -(-n // 32)
+    return ((c[:, 0] // 8) * nty + c[:, 1] // 8) * ntz + c[:, 2] // 32, (-(-n // 8)) * nty * ntz
+
+
+def _bucketed(rank, world, n, box):
+    """exchange_bucketed: tile-bucketed records + tile-offset slices arrive so that, per source rank and
+    local tile, the slice [starts[t]-base, starts[t+1]-base) holds exactly that source's particles of the tile."""
+    from abacusutils_b200.dist import SlabPlan, exchange_bucketed
+
+    plan = SlabPlan(n, world)
+    assert plan.aligned
+    nty, ntz = -(-n // 8), -(-n // 32)
+    per_col = nty * ntz
+    rng = np.random.default_rng(500 + rank)
+    N = 3000 + 500 * rank
+    pos = rng.random((N, 3), dtype='f4') * np.float32(box)
+    w = rng.random(N, dtype='f4')
+    tid, ntiles = _tile_ids(pos, n, box)
+    order = np.argsort(tid, kind='stable')
+    rows = torch.from_numpy(np.c_[pos, w][order].astype(np.float32))
+    starts = torch.from_numpy(np.searchsorted(tid[order], np.arange(ntiles + 1), side='left').astype(np.int32))
+    t0 = [(plan.xsplit[r] // 8) * per_col for r in range(world)] + [ntiles]
+    parts = exchange_bucketed(rows, starts, t0)
+    assert len(parts) == world
+    # what every source holds for my tiles: gather all catalogues (small) and recompute
+    sizes = [3000 + 500 * q for q in range(world)]
+    got_total = 0
+    for q, (recs, st, base) in enumerate(parts):
+        rq = np.random.default_rng(500 + q)
+        pq = rq.random((sizes[q], 3), dtype='f4') * np.float32(box)
+        wq = rq.random(sizes[q], dtype='f4')
+        tq, _ = _tile_ids(pq, n, box)
+        recs, st = recs.numpy(), st.numpy().astype(np.int64)
+        assert len(st) == t0[rank + 1] - t0[rank] + 1
+        assert st[0] == base and st[-1] - base == len(recs)
+        for t in range(0, t0[rank + 1] - t0[rank], 7):  # every 7th tile
+            sl = recs[st[t] - base: st[t + 1] - base]
+            mine = tq == t0[rank] + t
+            want = np.c_[pq[mine], wq[mine]]
+            assert sl.shape == want.shape
+            assert np.array_equal(sl[np.lexsort(sl.T[::-1])], want[np.lexsort(want.T[::-1])])
+        got_total += len(recs)
+    tot = torch.tensor([got_total], dtype=torch.int64)
+    dist.all_reduce(tot)
+    assert int(tot) == sum(sizes)
+
+
+@pytest.mark.parametrize('world,n', [(2, 32), (3, 40)])
+def test_bucketed_exchange(world, n):
+    _run(_bucketed, world, n, 100.0)
