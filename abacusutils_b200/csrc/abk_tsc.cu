@@ -6,20 +6,24 @@
 //   _tsc_parallel        analysis/tsc.py:229-256   (two-colour x-stripe schedule)
 //   _tsc_scatter         analysis/tsc.py:394-507   (27 read-modify-writes per particle)
 //
-// Design (see DESIGN.md "TSC deposit"):
+// Design:
 //   A. bucket particles by the (8 x 8 x 32)-cell tile of their cloud's centre cell: histogram
 //      (one 4-byte reduction per particle), scan, scatter of 16-byte (x,y,z,w) records.  The open
-//      write frontier is one 128-byte line per tile, which stays resident in the 126 MB L2, so the
-//      scatter reaches DRAM as full lines.
+//      write frontier is one 128-byte line per tile; it stays (mostly) resident in the 126 MB L2.
 //   B. one CTA per tile: per-cell particle lists are built in shared memory with one integer
 //      exchange per particle; then warp = y-row, lane = z-cell, x walked serially: every lane sums
 //      the 27 stencil weights of ITS cell's particles in registers (a rolling 3-plane window along
 //      x), neighbouring lanes are combined with two shuffles, neighbouring rows through a
 //      shared-memory tile written without atomics (each (plane,row) is owned by exactly one warp
-//      per phase).  Shared-memory float atomics are a CAS loop on sm_100a
-//      (ATOMS.CAST.SPIN), so the kernel uses none.  The finished tile + 1-cell halo is added to
-//      the grid with coalesced float reductions (REDG.ADD.F32): ~1.7 per CELL instead of 27 per
-//      PARTICLE.
+//      per phase).  Shared-memory float atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN), so the
+//      kernel uses none.  The finished tile + 1-cell halo is added to the grid with coalesced float
+//      reductions (REDG.ADD.F32): ~1.7 per CELL instead of 27 per PARTICLE.
+//   C. interlacing: the half-cell-shifted deposit reuses the records bucketed for the unshifted grid
+//      (template EXT: one more cell row/plane per tile; z overflow is queued and deposited
+//      warp-cooperatively).  CIC (analysis/cic.py) is the same update with other weights (template CIC).
+// Kernel variants kept for measurement (abk_ctx_set_tile_capacity bits 16-18): precomputed 32-byte
+// records (PRE), private per-warp slabs (PRIV), row streaming without an output tile; the default
+// (16-byte records, shared tile) is the fastest on B200 (profiles/r1_ncu_summary.md).
 #include "abk_common.cuh"
 
 namespace {

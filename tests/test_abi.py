@@ -111,3 +111,38 @@ def test_legendre_coefficients(golden):
     for ell in range(11):
         val = sum(co[ell, m] * mu**m for m in range(11)) / (2 * ell + 1)
         np.testing.assert_allclose(val, golden[f'P_n/{ell}'], rtol=1e-5, atol=3e-6 * 4**(ell // 2))
+
+
+def _strip_comments(text):
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return re.sub(r'//[^\n]*', '', text)
+
+
+def _param_types(sig):
+    out = []
+    for a in sig.split(','):
+        a = a.strip()
+        if a in ('', 'void'):
+            continue
+        a = re.sub(r'\b[A-Za-z_][A-Za-z0-9_]*$', '', a).strip()  # drop the parameter name
+        out.append(re.sub(r'\s+', ' ', a).replace(' *', '*').replace('* ', '*'))
+    return out
+
+
+def test_header_prototypes_match_definitions_and_bindings():
+    """Every prototype in include/abk.h has a definition with the same parameter types in csrc/*.cu, and the
+    ctypes binding passes the same number of arguments."""
+    from abacusutils_b200 import _lib
+
+    hdr = _strip_comments((ROOT / 'include' / 'abk.h').read_text())
+    protos = {m.group(1): m.group(2) for m in
+              re.finditer(r'\b(abk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', hdr, flags=re.S)}
+    defs = {}
+    for f in (ROOT / 'abacusutils_b200' / 'csrc').glob('*.cu'):
+        src = _strip_comments(f.read_text())
+        for m in re.finditer(r'extern "C"\s+[A-Za-z0-9_ ]+\*?\s*(abk_[a-z0-9_]+)\s*\(([^{;]*?)\)\s*\{', src, flags=re.S):
+            defs[m.group(1)] = m.group(2)
+    assert set(protos) == set(defs) == set(_lib.SIGNATURES)
+    for name, sig in protos.items():
+        assert _param_types(sig) == _param_types(defs[name]), name
+        assert len(_param_types(sig)) == len(_lib.SIGNATURES[name][1]), name
