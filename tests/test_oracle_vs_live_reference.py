@@ -1,0 +1,72 @@
+"""
+Oracle vs the LIVE, unmodified reference (imported from /root/reference through oracle/ref_shim.py) on
+randomised small cases.  Skipped where the reference tree is absent (the GPU box): the committed goldens in
+tests/golden/ cover that.  Keeps the oracle pinned beyond the fixed golden cases: bit-exact mode counts for
+random (n, Nk, Nmu, logk, k_max), and TSC grids / window tables on random inputs.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason='reference tree not present')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return ref_shim.load(num_threads=2)
+
+
+def test_random_mode_counts_bit_exact(oracle, ref):
+    _, ps = ref
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        n = int(rng.choice([12, 16, 20, 27, 30, 33, 48]))
+        L = float(rng.uniform(50, 3000))
+        Nk, Nmu = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+        logk = bool(rng.integers(0, 2))
+        k_max = float(rng.uniform(0.3, 1.8)) * np.pi * n / L
+        kedges, muedges = ps.get_k_mu_edges(L, k_max, Nk, Nmu, logk)
+        w = rng.random((n, n, n // 2 + 1), dtype='f4')
+        poles = np.array([0, 2, 4], dtype=np.int64)
+        want = ps.bin_kmu(n, L, kedges, muedges, w, poles=poles, nthread=2)
+        got = oracle.bin_kmu(n, L, kedges, muedges, w, poles=poles, nthread=3)
+        assert np.array_equal(got[1], want[1]), (trial, n, Nk, Nmu, logk)
+        assert np.array_equal(got[3], want[3])
+        np.testing.assert_allclose(got[0], want[0], rtol=3e-5, atol=1e-6)
+        np.testing.assert_allclose(got[4], want[4], rtol=3e-5, atol=1e-9)
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=2e-5)
+
+
+def test_random_tsc_grids(oracle, ref):
+    tsc, _ = ref
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        shape = tuple(int(v) for v in rng.integers(9, 40, size=3))
+        box = float(rng.uniform(10, 500))
+        N = int(rng.integers(100, 5000))
+        pos = (rng.random((N, 3), dtype='f4') * np.float32(1.4) - np.float32(0.2)) * np.float32(box)  # some outside [0, box)
+        w = rng.random(N, dtype='f4') if trial % 2 else None
+        off = float(rng.uniform(0, box / shape[0])) if trial % 3 == 0 else 0.0
+        a, b = pos.copy(), pos.copy()
+        want = np.zeros(shape, dtype=np.float32)
+        tsc.tsc_parallel(a, want, box, weights=w, nthread=1, offset=off)
+        got = np.zeros(shape, dtype=np.float32)
+        oracle.tsc_parallel(b, got, box, weights=w, nthread=2, offset=off)
+        np.testing.assert_array_equal(a, b)  # same in-place wrap
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_window_and_edges(oracle, ref):
+    _, ps = ref
+    for n, L in [(7, 33.0), (64, 1000.0), (100, 250.0)]:
+        for paste in ('TSC', 'CIC'):
+            for inter in (True, False):
+                np.testing.assert_array_equal(oracle.get_W_compensated(L, n, paste, inter),
+                                              ps.get_W_compensated(L, n, paste, inter))
+        for logk in (True, False):
+            a = oracle.get_k_mu_edges(L, 0.7, 13, 5, logk)
+            b = ps.get_k_mu_edges(L, 0.7, 13, 5, logk)
+            np.testing.assert_array_equal(a[0], b[0])
+            np.testing.assert_array_equal(a[1], b[1])
