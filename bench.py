@@ -41,6 +41,8 @@ WORKLOAD = ('configs[2]: calc_power, 1e9 uniform random particles, Lbox=2000, nm
 
 # DRAM traffic per launch of the kernels at the default workload, from `ncu --set full` captures of this very
 # command (profiles/r1_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum.
+# warp instructions per launch of the tile deposit at the default workload (ncu smsp__inst_executed.sum, same captures)
+NCU_WARP_INST_CONFIG3 = {'tsc_tile_deposit': 2.4e10}
 NCU_TRAFFIC_CONFIG3 = {'tsc_tile_deposit': 25.2e9, 'tsc_bucket_scatter': 3.54e9, 'tsc_bucket_hist': 0.86e9,
                        'normalize_field': 8.55e9}
 
@@ -306,6 +308,14 @@ def run_gpu_arm(args):
             'frac': (stages[top]['achieved_gbs'] / peak) if stages[top]['achieved_gbs'] else None,
             'traffic': (NCU_TRAFFIC_CONFIG3.get(top) if not (args.nparticles or args.nmesh) else None),
             'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms}
+    if top in NCU_WARP_INST_CONFIG3 and not (args.nparticles or args.nmesh):
+        # the deposit is bound by instruction issue and LSU (ATOMS / RED) cost, not by HBM: report the issue-rate view too
+        sm_mhz = clocks.get('sm_mhz') or 1965.0
+        peak_issue = 148 * 4 * sm_mhz * 1e6          # warp instructions / s: 4 schedulers per SM, 1 per clock
+        ach = NCU_WARP_INST_CONFIG3[top] / (stages[top]['avg_launch_ms'] * 1e-3)
+        roof['issue_view'] = {'warp_inst_per_launch': NCU_WARP_INST_CONFIG3[top], 'achieved_ginst_s': ach / 1e9,
+                              'peak_ginst_s': peak_issue / 1e9, 'frac': ach / peak_issue,
+                              'source': 'profiles/r1_ncu_summary.md (ncu smsp__inst_executed.sum)'}
 
     # ---- configs[1]: tsc_parallel of 1e8 weighted particles onto a 512^3 float32 mesh (extra, device-resident) ----
     cfg2 = None

@@ -1,0 +1,90 @@
+"""CPU tests of host-side logic of the product package (no GPU, no kernels)."""
+
+import numpy as np
+import pytest
+
+
+def test_slab_plan_properties():
+    from abacusutils_b200.dist import TILE_X, SlabPlan
+
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        world = int(rng.integers(1, 9))
+        n = int(rng.integers(2 * world, 4200))
+        p = SlabPlan(n, world)
+        for split in (p.xsplit, p.jsplit):
+            assert split[0] == 0 and split[-1] == n and len(split) == world + 1
+            assert all(b - a >= 1 for a, b in zip(split[:-1], split[1:]))
+        assert all(p.nxl(r) >= 2 for r in range(world))
+        if p.aligned:
+            assert all(x % TILE_X == 0 for x in p.xsplit[:-1])
+        for r in range(world):
+            send, recv = p.transpose_splits(r)
+            assert sum(send) == p.nxl(r) * n * p.nzc and sum(recv) == n * p.nyl(r) * p.nzc
+        # what rank r sends to q is what q expects from r
+        for r in range(world):
+            for q in range(world):
+                assert p.transpose_splits(r)[0][q] == p.transpose_splits(q)[1][r]
+        for ix in (0, n - 1, n, -1, n // 2):
+            o = p.owner_of_plane(ix)
+            assert p.xsplit[o] <= ix % n < p.xsplit[o + 1]
+    with pytest.raises(ValueError):
+        SlabPlan(7, 4)
+
+
+def test_chunk_plan_covers_everything_within_limits():
+    from abacusutils_b200._lib import ABK_MAX_SEGMENTS, SEGMENT_MAX
+    from abacusutils_b200.analysis.power_spectrum import _Painter
+
+    P = _Painter.__new__(_Painter)
+    for N in (1, 1000, (1 << 25) - 1, 1 << 25, 10**8, 10**9, 5 * 10**9, 12 * 10**9):
+        chunks = P.chunk_plan(N)
+        assert chunks[0][0] == 0 and chunks[-1][1] == N
+        assert all(a2 == b1 for (_, b1), (a2, _) in zip(chunks[:-1], chunks[1:]))
+        assert all(0 < b - a <= SEGMENT_MAX for a, b in chunks)
+        assert len(chunks) <= ABK_MAX_SEGMENTS
+
+
+def test_legendre_coefficients_against_numpy():
+    from numpy.polynomial import legendre as npl
+
+    from abacusutils_b200.analysis.power_spectrum import legendre_coefficients
+
+    mu = np.linspace(0, 1, 41)
+    co = legendre_coefficients(list(range(11))).astype(np.float64)
+    for ell in range(11):
+        want = (2 * ell + 1) * npl.legval(mu, [0] * ell + [1])
+        got = sum(co[ell, m] * mu**m for m in range(11))
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-5)
+
+
+def test_table_fallback_and_paste_check():
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    t = ps.Table({'a': np.arange(3)}, meta={'x': 1})
+    assert t.colnames == ['a'] and t.meta['x'] == 1 and t['a'][2] == 2
+    assert ps._check_paste('tsc') == 'TSC' and ps._check_paste('Cic') == 'CIC'
+    with pytest.raises(ValueError):
+        ps._check_paste('NGP')
+
+
+def test_finalize_bins_matches_reference_tail():
+    """Host tail of bin_kmu (power_spectrum.py:276-293): l=0 pole from the wedge sums, divide where count != 0."""
+    import torch
+
+    from abacusutils_b200.analysis.power_spectrum import _finalize_bins
+
+    Nk, Nmu = 4, 3
+    poles = np.array([0, 2])
+    counts = np.array([[1, 0, 2], [0, 0, 0], [4, 4, 4], [2, 0, 0]], dtype=np.int64)
+    sp = np.arange(12, dtype=np.float64).reshape(4, 3) + 1
+    sk = 2 * sp
+    spl = np.array([[9, 9, 9, 9], [1, 2, 3, 4]], dtype=np.float64)
+    sums = torch.from_numpy(np.concatenate([counts.view(np.float64).ravel(), sp.ravel(), sk.ravel(), spl.ravel()]))
+    sw, c, p, cp, k = _finalize_bins(sums, Nk, Nmu, poles, dk=0.5)
+    assert np.array_equal(c, counts) and np.array_equal(cp, counts.sum(1))
+    assert sw[1].tolist() == [4.0, 5.0, 6.0]            # empty bins keep their (zero-count) raw value, never NaN
+    assert sw[0, 0] == 1.0 and sw[0, 2] == 1.5 and sw[2, 1] == 2.0
+    assert k[2, 0] == pytest.approx(14 * 0.5 / 4)
+    np.testing.assert_allclose(p[0], [(1 + 2 + 3) / 3, 15, (7 + 8 + 9) / 12, (10 + 11 + 12) / 2])  # row l=0 = sum over mu / counts
+    np.testing.assert_allclose(p[1], [1 / 3, 2, 3 / 12, 4 / 2])
