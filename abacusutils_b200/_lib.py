@@ -88,6 +88,7 @@ SIGNATURES = {
     'abk_delta_mu2': (_i32, [_vp, _vp, _vp, _i32]),
     'abk_smoothing': (_i32, [_vp, _vp, _i32, _dbl, _dbl]),
     'abk_expand_poles_to_3d': (_i32, [_vp, _vp, _i32, _dbl, _vp, _vp, _i32, C.POINTER(C.c_int32), _i32, _vp]),
+    'abk_bin_kppi': (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     'abk_power_bin_scratch_bytes': (_i32, [_i32, _i32, _i32, _psz]),
     'abk_power_bin': (_i32, [_vp, C.POINTER(BinRequest)]),
     'abk_add_planes': (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i64]),

@@ -756,10 +756,42 @@ def expand_poles_to_3d(k_ell, P_ell, n1d, L, poles, dtype=np.float32):
     return out.cpu().numpy().astype(dtype, copy=False)
 
 
-def bin_kppi(*args, **kwargs):
-    """(k_perp, k_par) binning (power_spectrum.py:303-412) -- not on the GPU path (unused by the reference's
-    own callers; its early `break` over j makes the result depend on the loop order)."""
-    raise NotImplementedError('bin_kppi is not implemented on the GPU path')
+def bin_kppi(n1d, L, kedges, pimax, Npi, weights, dtype=np.float32, fourier=True, nthread=MAX_THREADS):
+    """Mean and mode count in (k_perp, pi) bins of a (n1d, n1d, n1d//2+1) half-spectrum, or of a real
+    (n1d, n1d, n1d) mesh with ``fourier=False`` (reference: power_spectrum.py:303-412).
+
+    Returns ``(weighted_counts, counts)``: the per-bin mean, ``dtype`` (Nk, Npi), and the int64 mode count.
+    Bins are (lo, hi]; ``pi`` runs over ``linspace(0, pimax, Npi + 1)``.  As in the reference, a row of the
+    mesh stops contributing at its first ``j`` whose k_perp reaches ``kedges[-1]``.  ``nthread`` is ignored.
+    """
+    import torch
+
+    dtype = np.dtype(dtype).type
+    if dtype not in (np.float32, np.float64):
+        raise ValueError('dtype must be float32 or float64')
+    on_device = is_torch_tensor(weights) and weights.is_cuda
+    eng = Engine.get(weights.device if on_device else None)
+    eng.bind_stream()
+    n = int(n1d)
+    wt = eng.to_device(weights, torch.float64 if dtype is np.float64 else torch.float32)
+    if wt.ndim != 3 or wt.shape[0] != n or wt.shape[1] != n or wt.shape[2] < n // 2 + 1:
+        raise ValueError(f'weights must have shape ({n},{n},>={n // 2 + 1}), got {tuple(wt.shape)}')
+    Nk, Npi = len(kedges) - 1, int(Npi)
+    dk = 2.0 * np.pi / L if fourier else L / n
+    # squared edges rounded to the compute dtype (:365-366), handed over as float64 (exact)
+    kedges2 = ((np.asarray(kedges, dtype=np.float64) / dk) ** 2).astype(dtype).astype(np.float64)
+    piedges2 = ((np.linspace(0.0, pimax, Npi + 1) / dk) ** 2).astype(dtype).astype(np.float64)
+    ke = eng.to_device(kedges2)
+    pe = eng.to_device(piedges2)
+    counts = eng.zeros((Nk, Npi), torch.int64)
+    sums = eng.zeros((Nk, Npi), torch.float64)
+    check(eng.lib.abk_bin_kppi(eng.ctx, ptr(wt), int(dtype is np.float64), n, int(wt.shape[2]), ptr(ke), Nk, ptr(pe), Npi,
+                               int(dtype is np.float32), ptr(counts), ptr(sums)))
+    c = counts.cpu().numpy()
+    m = sums.cpu().numpy()
+    nz = c != 0
+    m[nz] /= c[nz]
+    return m.astype(dtype), c
 
 
 _ = (warnings, tsc_parallel)

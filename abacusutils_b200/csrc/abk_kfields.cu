@@ -2,6 +2,7 @@
 //   get_delta_mu2       analysis/power_spectrum.py:577-617
 //   get_smoothing       :539-574
 //   expand_poles_to_3d  :450-520  (+ linear_interp :523-536, P_n :121-147)
+//   bin_kppi            :303-412
 // One warp per (i,j) row of the (n, n, n/2+1) mesh, lanes on k: coalesced stores, no reuse -> HBM-bound.
 #include "abk_common.cuh"
 
@@ -96,6 +97,109 @@ __global__ void __launch_bounds__(256) expand_poles_kernel(float *__restrict__ o
     });
 }
 
+// ---- bin_kppi (power_spectrum.py:303-412) ---------------------------------------------------
+// The pi bin depends on k only and the k_perp bin on (i,j) only.  A warp owns (i, 32 consecutive k):
+// every lane keeps ONE pi bin for the whole task and walks j with coalesced 128-byte loads; the
+// k_perp bin, the skip below kedges2[0] and the reference's early `break` are warp-uniform, so runs
+// of equal k_perp bin are summed in registers and flushed with one RED per warp (one per lane only
+// when the 32 k straddle a pi edge).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bin_kppi_kernel(const T *__restrict__ w, int n, int nzc, int64_t ldz, const double *__restrict__ kedges2, int Nk,
+                const double *__restrict__ piedges2, int Npi, int kperp_f32, int nchunk,
+                unsigned long long *__restrict__ counts, double *__restrict__ sums)
+{
+    extern __shared__ double s_ke[];   // kedges2 [Nk+1]
+    for (int t = threadIdx.x; t <= Nk; t += blockDim.x) s_ke[t] = kedges2[t];
+    __syncthreads();
+    const double klo = s_ke[0], khi = s_ke[Nk];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int64_t ntask = (int64_t)n * nchunk;
+
+    for (int64_t task = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); task < ntask; task += (int64_t)gridDim.x * wpb) {
+        const int i = (int)(task / nchunk), k = (int)(task % nchunk) * 32 + lane;
+        // pi bin of this lane: first b with kz2 <= piedges2[b+1]; kz2 is an exact integer, compared in
+        // double like the reference's int-vs-float promotion; dropped when kz2 >= piedges2[Npi] (:388-395)
+        int bpi = -1;
+        if (k < nzc) {
+            const double kz2 = (double)k * (double)k;
+            if (kz2 < piedges2[Npi]) {
+                int lo = 0, hi = Npi - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (kz2 <= piedges2[mid + 1]) hi = mid; else lo = mid + 1;
+                }
+                bpi = lo;
+            }
+        }
+        const unsigned act = __ballot_sync(full, bpi >= 0);
+        if (act == 0) continue;
+        const int b0 = __shfl_sync(full, bpi, __ffs(act) - 1);
+        const bool one_bin = __all_sync(full, bpi < 0 || bpi == b0);
+        const unsigned mult = (k == 0) ? 1u : 2u;
+        // multiplicity summed over the active lanes (only lane 0 of chunk 0 can hold k == 0)
+        const unsigned warp_mult = 2u * (unsigned)__popc(act) - ((task % nchunk) == 0 && (act & 1u) ? 1u : 0u);
+
+        const int ii = fold(i, n), i2 = ii * ii;
+        // the reference breaks out of the j loop at the first j with kperp2 >= kedges2[-1] (:379-380)
+        int jend = n;
+        for (int j = 0; j < n; j++) {
+            const int jj = fold(j, n), ij2 = i2 + jj * jj;
+            const double kp2 = kperp_f32 ? (double)(float)ij2 : (double)ij2;
+            if (kp2 >= khi) { jend = j; break; }
+        }
+        const T *base = w + (int64_t)i * n * ldz + k;
+
+        int cur_bk = -1;
+        unsigned long long run = 0;
+        double acc = 0.0;
+        auto flush = [&]() {
+            if (cur_bk >= 0 && run > 0) {
+                const int64_t slot = (int64_t)cur_bk * Npi;
+                if (one_bin) {
+                    double v = acc;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+                    if (lane == 0) {
+                        atomicAdd(&counts[slot + b0], run * warp_mult);
+                        atomicAdd(&sums[slot + b0], v);
+                    }
+                } else if (bpi >= 0) {
+                    atomicAdd(&counts[slot + bpi], run * mult);
+                    atomicAdd(&sums[slot + bpi], acc);
+                }
+            }
+            run = 0;
+            acc = 0.0;
+        };
+
+        for (int j0 = 0; j0 < jend; j0 += 4) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                v[u] = (bpi >= 0 && j0 + u < jend) ? base[(int64_t)(j0 + u) * ldz] : T(0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u;
+                if (j >= jend) break;
+                const int jj = fold(j, n), ij2 = i2 + jj * jj;
+                const double kp2 = kperp_f32 ? (double)(float)ij2 : (double)ij2;
+                if (kp2 < klo) continue;   // :375-376
+                int lo = 0, hi = Nk - 1;   // first b with kp2 <= kedges2[b+1]  (:382-383), kp2 < kedges2[Nk] here
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (kp2 <= s_ke[mid + 1]) hi = mid; else lo = mid + 1;
+                }
+                if (lo != cur_bk) { flush(); cur_bk = lo; }
+                run++;
+                acc += (double)v[u] * (double)mult;
+            }
+        }
+        flush();
+    }
+}
+
 int blocks_for(const abk_ctx *ctx, int64_t nrows)
 {
     int64_t b = (nrows + 7) / 8;
@@ -139,5 +243,28 @@ extern "C" int abk_expand_poles_to_3d(abk_ctx *ctx, float *out, int n, double L,
         if (poles_h[p] & 1) A.even_only = 0;
     }
     ABK_LAUNCH(ctx, ABK_K_MISC, expand_poles_kernel<<<blocks_for(ctx, (int64_t)n * n), 256, 0, ctx->stream>>>(out, n, n / 2 + 1, A));
+    return ABK_OK;
+}
+
+extern "C" int abk_bin_kppi(abk_ctx *ctx, const void *weights, int weights_f64, int n, int64_t ldz, const double *kedges2,
+                            int Nk, const double *piedges2, int Npi, int kperp_f32, unsigned long long *counts,
+                            double *sum_w)
+{
+    ABK_REQUIRE(ctx && weights && kedges2 && piedges2 && counts && sum_w, "abk_bin_kppi: null argument");
+    ABK_REQUIRE(n > 0 && n <= 32767 && ldz >= n / 2 + 1, "abk_bin_kppi: bad mesh (n=%d, ldz=%lld)", n, (long long)ldz);
+    ABK_REQUIRE(Nk >= 1 && Npi >= 1 && (int64_t)Nk * Npi < ((int64_t)1 << 28), "abk_bin_kppi: bad bin counts");
+    const size_t smem = (size_t)(Nk + 1) * sizeof(double);
+    ABK_REQUIRE(smem + 1024 < (size_t)ctx->smem_optin, "abk_bin_kppi: k edges (%zu B) do not fit in shared memory", smem);
+    const int nzc = n / 2 + 1, nchunk = (nzc + 31) / 32;
+    const int blocks = blocks_for(ctx, (int64_t)n * nchunk);
+    if (weights_f64) {
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(bin_kppi_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ABK_LAUNCH(ctx, ABK_K_MISC, bin_kppi_kernel<double><<<blocks, 256, smem, ctx->stream>>>(
+                                        (const double *)weights, n, nzc, ldz, kedges2, Nk, piedges2, Npi, kperp_f32, nchunk, counts, sum_w));
+    } else {
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(bin_kppi_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ABK_LAUNCH(ctx, ABK_K_MISC, bin_kppi_kernel<float><<<blocks, 256, smem, ctx->stream>>>(
+                                        (const float *)weights, n, nzc, ldz, kedges2, Nk, piedges2, Npi, kperp_f32, nchunk, counts, sum_w));
+    }
     return ABK_OK;
 }

@@ -275,6 +275,18 @@ int abk_smoothing(abk_ctx *ctx, float *out, int n, double L, double R);
 int abk_expand_poles_to_3d(abk_ctx *ctx, float *out, int n, double L, const float *k_ell, const float *P_ell, int Nk,
                            const int32_t *poles_h, int Np, const float *coef);
 
+/* bin_kppi (analysis/power_spectrum.py:303-412): count and sum the modes of an (n, n, >= n/2+1) mesh in
+ * (k_perp, pi) bins.  weights: device, float32 (weights_f64 = 0) or float64 (1), row stride ldz elements
+ * (n/2+1 for a half-spectrum, n for a real-space mesh binned with fourier=False).  kedges2 [Nk+1] and
+ * piedges2 [Npi+1]: device float64, the squared edges in units of dk^2 AFTER rounding to the compute dtype
+ * (:365-366).  kperp_f32 != 0 rounds i'^2 + j'^2 to float32 before the comparison (dtype=float32).
+ * Bins are (lo, hi]; k_perp^2 < kedges2[0] is skipped; a row i stops at its first j with
+ * k_perp^2 >= kedges2[Nk] (the reference's `break`, :379-380); kz^2 >= piedges2[Npi] is dropped; a mode
+ * counts once on the k = 0 plane and twice elsewhere.  counts u64 [Nk*Npi] and sum_w f64 [Nk*Npi] are
+ * accumulated into (the caller zeroes them and divides). */
+int abk_bin_kppi(abk_ctx *ctx, const void *weights, int weights_f64, int n, int64_t ldz, const double *kedges2, int Nk,
+                 const double *piedges2, int Npi, int kperp_f32, unsigned long long *counts, double *sum_w);
+
 /* ---- multi-GPU helpers (x-slab sharded mesh) ------------------------------------------------ */
 
 /* dst[i] += src[i] over an (nplanes, ny, nz) region of padded grids (ghost-plane accumulation) */

@@ -315,6 +315,52 @@ def bin_kmu(n1d, L, kedges, muedges, weights, poles=np.empty(0, 'i8'), dtype=np.
     return sw.astype(np.float32), counts, sp.astype(np.float32), counts_poles, sk.astype(np.float32)
 
 
+def bin_kppi(n1d, L, kedges, pimax, Npi, weights, dtype=np.float32, fourier=True, nthread=MAX_THREADS, raw=False):
+    """power_spectrum.py:303-412 (NumPy restatement, row-vectorised).
+
+    Reference behaviour kept on purpose:
+      * kperp^2 = dtype(i'^2 + j'^2) with (lo, hi] bins, skipped below kedges2[0] (:371-386);
+      * the j loop *breaks* at the first j whose kperp^2 >= kedges2[-1] (:379-380), so for a row i
+        whose peak value (at j = n//2) is out of range every j >= that first failing j is dropped,
+        including the mirror modes j > n//2 that would be back in range;
+      * kz^2 stays an integer and is compared with the float edges after promotion to float64
+        (:388-395); modes with kz^2 >= piedges2[-1] are dropped; multiplicity 1 for k == 0, else 2.
+    Returns (weighted_counts dtype (Nk,Npi), counts i64); ``raw=True`` keeps the float64 means.
+    """
+    dtype = np.dtype(dtype).type
+    weights = np.asarray(weights)
+    kzlen = n1d // 2 + 1
+    Nk = len(kedges) - 1
+    dk = 2.0 * np.pi / L if fourier else L / n1d
+    kedges2 = ((np.asarray(kedges, dtype=np.float64) / dk) ** 2).astype(dtype)
+    piedges2 = ((np.linspace(0.0, pimax, Npi + 1) / dk) ** 2).astype(dtype)
+    counts = np.zeros((Nk, Npi), dtype=np.int64)
+    sums = np.zeros((Nk, Npi), dtype=np.float64)
+
+    kz2 = (np.arange(kzlen, dtype=np.int64) ** 2).astype(np.float64)
+    pie = piedges2.astype(np.float64)
+    kuse = kz2 < pie[-1]
+    bpi = np.searchsorted(pie[1:], kz2[kuse], side='left')
+    mult = np.where(np.arange(kzlen) == 0, 1, 2)[kuse]
+    fold = np.where(np.arange(n1d) < n1d // 2, np.arange(n1d), np.arange(n1d) - n1d).astype(np.int64)
+    for i in range(n1d):
+        kp2 = (fold[i] ** 2 + fold ** 2).astype(dtype)
+        over = np.flatnonzero(kp2 >= kedges2[-1])
+        jend = over[0] if len(over) else n1d
+        js = np.flatnonzero(kp2[:jend] >= kedges2[0])
+        if len(js) == 0 or len(bpi) == 0:
+            continue
+        bk = np.searchsorted(kedges2[1:], kp2[js], side='left')
+        flat = (bk[:, None] * Npi + bpi[None, :]).ravel()
+        wrow = weights[i, js][:, :kzlen][:, kuse].astype(np.float64) * mult[None, :]
+        counts += np.bincount(flat, weights=np.broadcast_to(mult, (len(js), len(mult))).ravel(),
+                              minlength=Nk * Npi).astype(np.int64).reshape(Nk, Npi)
+        sums += np.bincount(flat, weights=wrow.ravel(), minlength=Nk * Npi).reshape(Nk, Npi)
+    nz = counts != 0
+    sums[nz] /= counts[nz]
+    return (sums if raw else sums.astype(dtype)), counts
+
+
 def project_3d_to_poles(k_bin_edges, raw_p3d, Lbox, poles):
     """power_spectrum.py:415-447."""
     assert np.max(poles) <= 10, 'numba implementation works up to ell = 10'

@@ -208,3 +208,27 @@ def tsc2d_inputs(c):
     pos = rng.random((c['N'], c['ncol']), dtype='f4') * np.float32(c['box'])
     w = rng.random(c['N'], dtype='f4') if c['weighted'] else None
     return pos, w
+
+
+# ---------------------------------------------------------------- bin_kppi (power_spectrum.py:303-412)
+# kmax / pimax are in units of the mesh Nyquist scale (pi n / L in Fourier space, L / 2 in real space)
+KPPI_CASES = {
+    'f16': dict(seed=101, n=16, L=100.0, k0=0.0, kmax=1.0, Nk=5, pimax=0.6, Npi=4, fourier=True, dtype='f4'),
+    'f16_break': dict(seed=102, n=16, L=100.0, k0=0.0, kmax=0.6, Nk=5, pimax=1.2, Npi=7, fourier=True, dtype='f4'),
+    'f15_odd': dict(seed=103, n=15, L=50.0, k0=0.05, kmax=0.8, Nk=6, pimax=0.5, Npi=3, fourier=True, dtype='f4'),
+    'f72': dict(seed=104, n=72, L=300.0, k0=0.02, kmax=0.9, Nk=11, pimax=0.7, Npi=9, fourier=True, dtype='f4'),
+    'f72_wide': dict(seed=105, n=72, L=300.0, k0=0.0, kmax=1.5, Nk=40, pimax=1.01, Npi=37, fourier=True, dtype='f4'),
+    'r24': dict(seed=106, n=24, L=200.0, k0=0.0, kmax=1.1, Nk=8, pimax=0.6, Npi=6, fourier=False, dtype='f4'),
+    'f20_f64': dict(seed=107, n=20, L=50.0, k0=0.1, kmax=0.9, Nk=6, pimax=1.0, Npi=3, fourier=True, dtype='f8'),
+    'f40_1bin': dict(seed=108, n=40, L=80.0, k0=0.0, kmax=2.0, Nk=1, pimax=1.01, Npi=1, fourier=True, dtype='f4'),
+}
+
+
+def kppi_inputs(c):
+    rng = np.random.default_rng(c['seed'])
+    n = c['n']
+    shape = (n, n, n // 2 + 1) if c['fourier'] else (n, n, n)
+    w = rng.standard_normal(shape).astype(c['dtype']) + np.dtype(c['dtype']).type(0.25)
+    scale = np.pi * n / c['L'] if c['fourier'] else c['L'] / 2
+    kedges = np.linspace(c['k0'] * scale, c['kmax'] * scale, c['Nk'] + 1)
+    return w, kedges, c['pimax'] * scale

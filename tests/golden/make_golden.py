@@ -180,9 +180,24 @@ def golden_kfields():
     print('kfields done')
 
 
+def golden_kppi():
+    _, ps = ref_shim.load(num_threads=2)
+    out = {}
+    for name, c in cases.KPPI_CASES.items():
+        w, kedges, pimax = cases.kppi_inputs(c)
+        mean, cnt = ps.bin_kppi(c['n'], c['L'], kedges, pimax, c['Npi'], w, dtype=np.dtype(c['dtype']).type,
+                                fourier=c['fourier'], nthread=2)
+        out[f'kppi/{name}/mean'] = mean
+        out[f'kppi/{name}/counts'] = cnt
+        print('kppi', name, cnt.sum(), mean.dtype)
+    np.savez_compressed(HERE / 'reference_kppi.npz', **out)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'kfields':
         golden_kfields()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'kppi':
+        golden_kppi()
     elif len(sys.argv) > 1 and sys.argv[1] == 'xi':
         golden_xi()
     elif len(sys.argv) > 1 and sys.argv[1] == 'cic':
@@ -193,3 +208,4 @@ if __name__ == '__main__':
         golden_xi()
         golden_cic()
         golden_kfields()
+        golden_kppi()

@@ -70,3 +70,22 @@ def test_window_and_edges(oracle, ref):
             b = ps.get_k_mu_edges(L, 0.7, 13, 5, logk)
             np.testing.assert_array_equal(a[0], b[0])
             np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_random_bin_kppi(oracle, ref):
+    """bin_kppi (power_spectrum.py:303-412): bit-exact counts on random meshes/edges, both spaces."""
+    _, ps = ref
+    rng = np.random.default_rng(4321)
+    for trial in range(10):
+        n = int(rng.choice([12, 16, 21, 30, 48]))
+        L = float(rng.uniform(50, 3000))
+        fourier = bool(rng.integers(0, 2))
+        scale = np.pi * n / L if fourier else L / 2
+        Nk, Npi = int(rng.integers(1, 30)), int(rng.integers(1, 20))
+        kedges = np.linspace(float(rng.uniform(0, 0.2)) * scale, float(rng.uniform(0.3, 1.6)) * scale, Nk + 1)
+        pimax = float(rng.uniform(0.2, 1.3)) * scale
+        w = rng.standard_normal((n, n, n // 2 + 1 if fourier else n)).astype('f4')
+        want = ps.bin_kppi(n, L, kedges, pimax, Npi, w, fourier=fourier, nthread=2)
+        got = oracle.bin_kppi(n, L, kedges, pimax, Npi, w, fourier=fourier)
+        assert np.array_equal(got[1], want[1]), (trial, n, Nk, Npi, fourier)
+        np.testing.assert_allclose(got[0], want[0], rtol=1e-4, atol=3e-6)
