@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libabk.so'
-SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu', 'abk_kfields.cu']
+SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu', 'abk_kfields.cu', 'abk_ingest.cu']
 CUDA_HOME = os.environ.get('CUDA_HOME', '/usr/local/cuda')
 
 NVCC_FLAGS = [
@@ -29,7 +29,7 @@ def needs_build():
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / 'abk_common.cuh', ROOT / 'include' / 'abk.h']
+    deps = [CSRC / s for s in SOURCES] + [CSRC / 'abk_common.cuh', CSRC / 'abk_ingest.cuh', ROOT / 'include' / 'abk.h']
     return any(d.stat().st_mtime > t for d in deps)
 
 

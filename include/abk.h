@@ -287,6 +287,31 @@ int abk_expand_poles_to_3d(abk_ctx *ctx, float *out, int n, double L, const floa
 int abk_bin_kppi(abk_ctx *ctx, const void *weights, int weights_f64, int n, int64_t ldz, const double *kedges2, int Nk,
                  const double *piedges2, int Npi, int kperp_f32, unsigned long long *counts, double *sum_w);
 
+/* ---- device-side particle ingest --------------------------------------- */
+
+/* `unpack_rvint` (abacusnbody/data/bitpacked.py:29-120): intdata int32[N][3] on the device; every int32 holds 20
+ * signed bits of position (units of boxsize/1e6) above 12 bits of velocity (offset 2048, units of 6000/2048 km/s).
+ * posout / velout: device [N][3] float32 (out_f64 = 0) or float64 (1); either may be NULL (not unpacked).
+ * Values are bit-identical to the reference (float64 product, one rounding to the output type). */
+int abk_unpack_rvint(abk_ctx *ctx, const int32_t *intdata, int64_t N, double boxsize, void *posout, void *velout,
+                     int out_f64);
+
+/* `unpack_pack9` (abacusnbody/data/pack9.py:16-123) in two calls, because the number of particle records is only
+ * known after the cell headers (records whose first byte is 0xFF) have been counted:
+ *   abk_pack9_count   counts headers per 256-record block and scans the counts into `scratch`
+ *                     (abk_pack9_scratch_bytes(nrec), 256-byte aligned); SYNCHRONISES the stream and returns the
+ *                     number of headers in *nheaders_h (host).  Particles = nrec - headers.
+ *   abk_pack9_decode  decodes the headers into hdr_tab (device, nheaders * 5 * sizeof(out type) bytes) and the
+ *                     particles into posout / velout (device [nrec - nheaders][3], either may be NULL), in stream
+ *                     order.  `scratch` must still hold the result of abk_pack9_count for the same data.
+ * data: device uint8[nrec][9], 4-byte aligned.  Particle records that precede the first header decode to NaN, as in
+ * the reference.  All roundings follow the reference's (non-fastmath) Numba kernel for the chosen output type. */
+int abk_pack9_scratch_bytes(int64_t nrec, size_t *bytes);
+int abk_pack9_count(abk_ctx *ctx, const uint8_t *data, int64_t nrec, void *scratch, size_t scratch_bytes,
+                    int64_t *nheaders_h);
+int abk_pack9_decode(abk_ctx *ctx, const uint8_t *data, int64_t nrec, double boxsize, double velzspace_to_kms,
+                     const void *scratch, void *hdr_tab, int64_t nheaders, void *posout, void *velout, int out_f64);
+
 /* ---- multi-GPU helpers (x-slab sharded mesh) ------------------------------------------------ */
 
 /* dst[i] += src[i] over an (nplanes, ny, nz) region of padded grids (ghost-plane accumulation) */

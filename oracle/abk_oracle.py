@@ -496,3 +496,86 @@ __all__ = ['tsc_parallel', 'partition_parallel', 'calc_power', 'pk_to_xi', 'calc
            'get_interlaced_field_fft', 'shift_field_fft', 'get_raw_power', 'bin_kmu', 'P_n',
            'tsc_scatter_serial', 'Table', 'build']
 _ = warnings
+
+
+# ---------------------------------------------------------------------------------------------
+# Particle-format decoders: NumPy restatements, checked bit for bit against the
+# unmodified reference (tests/test_oracle_vs_live_reference.py) and against the reference's own golden files
+# (tests/golden/ref_ingest.npz).
+
+def unpack_rvint(intdata, boxsize, float_dtype=np.float32, posout=None, velout=None):
+    """abacusnbody/data/bitpacked.py:29-120.  int32 op uint32 promotes to int64 there; the products are
+    float64 and are rounded once on the store."""
+    iv = np.asarray(intdata).reshape(-1, 3)
+    assert iv.dtype == np.int32
+    v = iv.astype(np.int64)
+    ret = []
+    for spec, val in ((posout, (v >> 12) * (boxsize / 1e6)), (velout, ((v & 0xFFF) - 2048) * (6000.0 / 2048))):
+        if spec is None:
+            ret.append(val.astype(float_dtype))
+        elif spec is False:
+            ret.append(0)
+        else:
+            out = spec.view()
+            out.shape = (-1, 3)
+            out[: len(iv)] = val
+            ret.append(len(iv))
+    return tuple(ret)
+
+
+def _pack9_fields(d):
+    c = d.astype(np.int64)
+    s = np.empty((len(d), 6), dtype=np.int64)
+    s[:, 0] = (c[:, 1] & 0x0F) | (c[:, 0] << 4)
+    s[:, 1] = ((c[:, 1] & 0xF0) << 4) | c[:, 2]
+    s[:, 2] = (c[:, 4] & 0x0F) | (c[:, 3] << 4)
+    s[:, 3] = ((c[:, 4] & 0xF0) << 4) | c[:, 5]
+    s[:, 4] = (c[:, 7] & 0x0F) | (c[:, 6] << 4)
+    s[:, 5] = ((c[:, 7] & 0xF0) << 4) | c[:, 8]
+    return s - 2048
+
+
+def unpack_pack9(data, boxsize, velzspace_to_kms, float_dtype=np.float32, posout=None, velout=None):
+    """abacusnbody/data/pack9.py:16-123, vectorised: the header that governs a particle record is the last
+    record with first byte 0xFF at or before it; particles before any header decode to NaN (the reference's
+    initial header state).  Every rounding of the serial reference is kept (T = float_dtype):
+    invcpd = T(1/(cpd)), csize = T*T, vscale = T(f64) * T * T, cell origin and pscale computed in float64 and
+    rounded to T, particle = T(int16) * pscale + origin with two roundings in T."""
+    T = np.dtype(float_dtype).type
+    d = np.asanyarray(data, dtype=np.ubyte).reshape(-1, 9)
+    s = _pack9_fields(d)
+    is_hdr = d[:, 0] == 0xFF
+    box, velz = T(boxsize), T(velzspace_to_kms)
+    halfbox = np.float64(box) / 2
+    hs = s[is_hdr].astype(np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        invcpd = (1.0 / (hs[:, 1] + 2000)).astype(T)
+        csize = (box * invcpd).astype(T)
+        vscale = (((hs[:, 2] + 2000) * 0.0005).astype(T) * invcpd).astype(T) * velz
+        cell = ((hs[:, 3:6] + 2000.5) * csize.astype(np.float64)[:, None] - halfbox).astype(T)
+        pscale = (0.0005 * csize.astype(np.float64)).astype(T)
+    # per-record header number (-1: none yet)
+    hnum = np.cumsum(is_hdr) - 1
+    part = ~is_hdr
+    hn = hnum[part]
+    nan = T(np.nan)
+    def take(a):
+        out = np.full((len(hn),) + a.shape[1:], nan, dtype=T)
+        ok = hn >= 0
+        out[ok] = a[hn[ok]]
+        return out
+    sp = s[part]
+    with np.errstate(invalid='ignore'):
+        pos = (sp[:, 0:3].astype(T) * take(pscale)[:, None]).astype(T) + take(cell)
+        vel = (sp[:, 3:6].astype(T) * take(vscale)[:, None]).astype(T)
+    npart = int(part.sum())
+    ret = []
+    for spec, val in ((posout, pos), (velout, vel)):
+        if spec is None:
+            ret.append(val.astype(T))
+        elif spec is False:
+            ret.append(0)
+        else:
+            spec[:npart] = val
+            ret.append(npart)
+    return tuple(ret)

@@ -6,7 +6,7 @@ Neither ``asdf`` nor ``blosc`` is installed here, so this decodes the three laye
      (ASDF standard 1.5, "Block header").
   2. the reference's own framing of a 'blsc' block: a sequence of ``[u32 big-endian length][blosc frame]``
      (/root/reference/abacusnbody/data/asdf.py:72-84).
-  3. blosc-1 frame: 16-byte header (version, versionlz, flags, typesize, nbytes, blocksize, cbytes),
+  3. blosc-1 frame (byte-shuffle flag 0x1 or bit-shuffle flag 0x4, undone per block): 16-byte header (version, versionlz, flags, typesize, nbytes, blocksize, cbytes),
      ``bstarts`` table, then per block either one stream (flag 0x10 "don't split") or ``typesize``
      streams, each ``[i32 csize][payload]``; byte-shuffle (flag 0x1) undone per block.
      Only the zstd codec (flags >> 5 == 4; what the golden files use) and memcpy'd frames (flag 0x2)
@@ -27,6 +27,20 @@ def _unshuffle(buf, typesize):
     return main.tobytes() + bytes(buf[n * typesize:])
 
 
+def _bitunshuffle(buf, typesize):
+    """Undo blosc-1's bitshuffle.  c-blosc only bit-shuffles a block whose element count is a multiple of 8
+    (otherwise the block is stored unshuffled, shuffle.c `blosc_internal_bitshuffle`); a shuffled block is laid
+    out as [byte-in-element][bit][n/8] rows (element 8j in the least significant bit of byte j), and bytes
+    beyond the last whole element are copied verbatim."""
+    n = len(buf) // typesize
+    if n == 0 or n % 8:
+        return bytes(buf)
+    rows = np.frombuffer(buf[: n * typesize], dtype=np.uint8).reshape(typesize, 8, n // 8)
+    bits = np.unpackbits(rows, axis=2, bitorder='little')          # [typesize][8][n] : bit k of byte b of element e
+    elems = np.packbits(bits.transpose(2, 0, 1), axis=2, bitorder='little')  # [n][typesize][1]
+    return elems.reshape(-1).tobytes() + bytes(buf[n * typesize:])
+
+
 def blosc1_decompress(frame):
     version, versionlz, flags, typesize, nbytes, blocksize, cbytes = struct.unpack('<BBBBIII', frame[:16])
     assert cbytes == len(frame), (cbytes, len(frame))
@@ -36,7 +50,7 @@ def blosc1_decompress(frame):
     assert codec == 4, f'only zstd blosc frames supported, got codec {codec}'
     zstd = pa.Codec('zstd')
     doshuffle = bool(flags & 0x1)
-    assert not (flags & 0x4), 'bitshuffle not supported'
+    dobitshuffle = bool(flags & 0x4)
     dont_split = bool(flags & 0x10)
     nblocks = (nbytes + blocksize - 1) // blocksize
     bstarts = struct.unpack(f'<{nblocks}i', frame[16:16 + 4 * nblocks])
@@ -60,6 +74,8 @@ def blosc1_decompress(frame):
         blk = b''.join(parts)
         if doshuffle and typesize > 1:
             blk = _unshuffle(blk, typesize)
+        elif dobitshuffle:
+            blk = _bitunshuffle(blk, typesize)
         out.append(blk)
     res = b''.join(out)
     assert len(res) == nbytes

@@ -232,3 +232,42 @@ def kppi_inputs(c):
     scale = np.pi * n / c['L'] if c['fourier'] else c['L'] / 2
     kedges = np.linspace(c['k0'] * scale, c['kmax'] * scale, c['Nk'] + 1)
     return w, kedges, c['pimax'] * scale
+
+
+# ---------------------------------------------------------------- particle decoders (data/bitpacked.py, data/pack9.py)
+PACK9_GOLDEN_RECORDS = 12000   # prefix of the reference's slab000.L0.pack9 fixture kept in ref_ingest.npz
+
+
+def rvint_inputs(seed, N):
+    rng = np.random.default_rng(seed)
+    return rng.integers(-2**31, 2**31, size=(N, 3), dtype=np.int64).astype(np.int32)
+
+
+def pack9_inputs(seed, nrec, hdr_frac=0.05, cpd=875, first_header=True):
+    """A synthetic pack9 stream: random particle records with cell headers (first byte 0xFF, fields 1..5 =
+    cpd, velocity scale, cell i/j/k, each stored + 2048 in 12 bits) sprinkled in."""
+    rng = np.random.default_rng(seed)
+    d = rng.integers(0, 256, size=(nrec, 9), dtype=np.int64).astype(np.uint8)
+    d[d[:, 0] == 0xFF, 0] = 0xFE
+    is_hdr = rng.random(nrec) < hdr_frac
+    if nrec:
+        is_hdr[0] = first_header
+    idx = np.flatnonzero(is_hdr)
+
+    def setfield(f, val):
+        val = (val + 2048).astype(np.int64)
+        b = 3 * (f // 2)
+        if f % 2 == 0:
+            d[idx, b] = (val >> 4) & 0xFF
+            d[idx, b + 1] = (d[idx, b + 1] & 0xF0) | (val & 0xF)
+        else:
+            d[idx, b + 1] = (d[idx, b + 1] & 0x0F) | (((val >> 8) & 0xF) << 4)
+            d[idx, b + 2] = val & 0xFF
+
+    nh = len(idx)
+    setfield(1, np.full(nh, cpd - 2000))
+    setfield(2, rng.integers(-1500, 2000, nh))
+    for f in (3, 4, 5):
+        setfield(f, rng.integers(-2000, cpd - 2000, nh))
+    d[idx, 0] = 0xFF
+    return d

@@ -193,8 +193,51 @@ def golden_kppi():
     np.savez_compressed(HERE / 'reference_kppi.npz', **out)
 
 
+def golden_ingest():
+    """The reference's own fixtures for the particle decoders (tests/test_data.py:258-325): packed inputs from
+    tests/Mini_N64_L32 and the decoded outputs the reference test-suite compares against (tests/ref_data)."""
+    import re
+
+    from asdf_blsc import read_asdf_blocks
+
+    def header_value(path, key):
+        raw = open(path, 'rb').read()
+        y = raw[: raw.find(b'\n...\n')].decode('latin1')
+        return float(re.search(rf'\n  {key}: (\S+)', y).group(1))
+
+    out = {}
+    sim = REF_TESTS / 'Mini_N64_L32'
+    # RVint: halos/z0.000/field_rv_A/field_rv_A_000.asdf -> ref_data/test_read_asdf.asdf (blocks 0, 1 = pos, vel)
+    fn = sim / 'halos' / 'z0.000' / 'field_rv_A' / 'field_rv_A_000.asdf'
+    rv = np.frombuffer(read_asdf_blocks(fn)[0], dtype='<i4').reshape(-1, 3)
+    gb = read_asdf_blocks(REF_TESTS / 'ref_data' / 'test_read_asdf.asdf')
+    out['rvint/in'] = rv
+    out['rvint/box'] = header_value(fn, 'BoxSize')
+    out['rvint/pos'] = np.frombuffer(gb[0], dtype='<f4').reshape(-1, 3)[: len(rv)]
+    out['rvint/vel'] = np.frombuffer(gb[1], dtype='<f4').reshape(-1, 3)[: len(rv)]
+    # pack9: slices/z0.000/L0_pack9/slab000.L0.pack9.asdf -> ref_data/test_pack9.asdf; keep the first records only
+    fn = sim / 'slices' / 'z0.000' / 'L0_pack9' / 'slab000.L0.pack9.asdf'
+    raw = open(fn, 'rb').read()
+    nrec = int(re.search(rb'shape: \[(\d+), 9\]', raw).group(1))
+    d = np.frombuffer(read_asdf_blocks(fn)[0][: nrec * 9], dtype=np.uint8).reshape(-1, 9)
+    gb = read_asdf_blocks(REF_TESTS / 'ref_data' / 'test_pack9.asdf')
+    keep = cases.PACK9_GOLDEN_RECORDS
+    npart = int((d[:keep, 0] != 0xFF).sum())
+    out['pack9/in'] = d[:keep]
+    out['pack9/box'] = header_value(fn, 'BoxSize')
+    out['pack9/velz'] = header_value(fn, 'VelZSpace_to_kms')
+    out['pack9/pos'] = np.frombuffer(gb[0], dtype='<f4').reshape(-1, 3)[:npart]
+    out['pack9/vel'] = np.frombuffer(gb[1], dtype='<f4').reshape(-1, 3)[:npart]
+    out['pack9/npart_full'] = int((d[:, 0] != 0xFF).sum())
+    out['pack9/nrec_full'] = nrec
+    np.savez_compressed(HERE / 'ref_ingest.npz', **out)
+    print('ingest: rvint', rv.shape, 'pack9', d[:keep].shape, '->', npart, 'particles')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'kfields':
+    if len(sys.argv) > 1 and sys.argv[1] == 'ingest':
+        golden_ingest()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'kfields':
         golden_kfields()
     elif len(sys.argv) > 1 and sys.argv[1] == 'kppi':
         golden_kppi()
@@ -209,3 +252,4 @@ if __name__ == '__main__':
         golden_cic()
         golden_kfields()
         golden_kppi()
+        golden_ingest()
