@@ -90,6 +90,7 @@ SIGNATURES = {
     'abk_expand_poles_to_3d': (_i32, [_vp, _vp, _i32, _dbl, _vp, _vp, _i32, C.POINTER(C.c_int32), _i32, _vp]),
     'abk_bin_kppi': (_i32, [_vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _i32, _i32, _vp, _vp]),
     'abk_unpack_rvint': (_i32, [_vp, _vp, _i64, _dbl, _vp, _vp, _i32]),
+    'abk_unpack_pids': (_i32, [_vp, _vp, _i64, _dbl, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     'abk_pack9_scratch_bytes': (_i32, [_i64, C.POINTER(C.c_size_t)]),
     'abk_pack9_count': (_i32, [_vp, _vp, _i64, _vp, C.c_size_t, C.POINTER(C.c_int64)]),
     'abk_pack9_decode': (_i32, [_vp, _vp, _i64, _dbl, _dbl, _vp, _vp, _i64, _vp, _vp, _i32]),

@@ -1,6 +1,7 @@
 // Device-side particle ingest: decode Abacus RVint and pack9 particle records that were
 // copied to the GPU still packed, so positions never exist on the host.
 //   RVint  abacusnbody/data/bitpacked.py:29-120   one thread per int32, HBM-bound (4 B in, 4-16 B out)
+//   PIDs   abacusnbody/data/bitpacked.py:123-311  one thread per packed 64-bit aux word
 //   pack9  abacusnbody/data/pack9.py:16-123       9-byte records; a record whose first byte is 0xFF is a cell
 //          header that sets the origin/scales of the particle records after it.  The reference walks the
 //          stream serially; here the "last header before me" dependency is a prefix count of header flags:
@@ -124,6 +125,31 @@ __global__ void __launch_bounds__(P9_BLOCK) pack9_decode_kernel(const uint8_t *_
     if (vel) { vel[3 * w] = v[0]; vel[3 * w + 1] = v[1]; vel[3 * w + 2] = v[2]; }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) pids_kernel(const uint64_t *__restrict__ packed, int64_t n, T inv_ppd, T half,
+                                                   int64_t *__restrict__ pid, T *__restrict__ lagr_pos,
+                                                   int16_t *__restrict__ lagr_idx, uint8_t *__restrict__ tagged,
+                                                   T *__restrict__ density)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t p = packed[i];
+        if (pid) pid[i] = abk_pid_pid(p);
+        if (lagr_pos) {
+            T v[3];
+            abk_pid_lagr_pos<T>(p, inv_ppd, half, v);
+            lagr_pos[3 * i] = v[0]; lagr_pos[3 * i + 1] = v[1]; lagr_pos[3 * i + 2] = v[2];
+        }
+        if (lagr_idx) {
+            int16_t v[3];
+            abk_pid_lagr_idx(p, v);
+            lagr_idx[3 * i] = v[0]; lagr_idx[3 * i + 1] = v[1]; lagr_idx[3 * i + 2] = v[2];
+        }
+        if (tagged) tagged[i] = abk_pid_tagged(p);
+        if (density) density[i] = abk_pid_density<T>(p);
+    }
+}
+
 int64_t p9_blocks(int64_t nrec) { return (nrec + P9_BLOCK - 1) / P9_BLOCK; }
 
 }  // namespace
@@ -206,5 +232,22 @@ extern "C" int abk_pack9_decode(abk_ctx *ctx, const uint8_t *data, int64_t nrec,
             ABK_LAUNCH(ctx, ABK_K_MISC, pack9_decode_kernel<float><<<(unsigned)nb, P9_BLOCK, 0, ctx->stream>>>(
                                             data, nrec, incl, (const H *)hdr_tab, (float *)posout, (float *)velout));
     }
+    return ABK_OK;
+}
+
+extern "C" int abk_unpack_pids(abk_ctx *ctx, const uint64_t *packed, int64_t N, double box, int64_t ppd, int64_t *pid,
+                               void *lagr_pos, int16_t *lagr_idx, uint8_t *tagged, void *density, int out_f64)
+{
+    ABK_REQUIRE(ctx && N >= 0 && (N == 0 || packed) && ppd > 0, "abk_unpack_pids: bad arguments");
+    if (N == 0 || (!pid && !lagr_pos && !lagr_idx && !tagged && !density)) return ABK_OK;
+    int64_t blocks = (N + 256 * 4 - 1) / (256 * 4);
+    const int64_t cap = (int64_t)ctx->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (out_f64)
+        ABK_LAUNCH(ctx, ABK_K_MISC, pids_kernel<double><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                                        packed, N, box / (double)ppd, box / 2, pid, (double *)lagr_pos, lagr_idx, tagged, (double *)density));
+    else
+        ABK_LAUNCH(ctx, ABK_K_MISC, pids_kernel<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>(
+                                        packed, N, (float)(box / (double)ppd), (float)(box / 2), pid, (float *)lagr_pos, lagr_idx, tagged, (float *)density));
     return ABK_OK;
 }

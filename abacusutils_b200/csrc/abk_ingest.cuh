@@ -106,3 +106,32 @@ ABK_HD void abk_pack9_particle(const int s[6], const abk_pack9_cell<T> &h, T pos
     vel[1] = abk_mul((T)s[4], h.vscale);
     vel[2] = abk_mul((T)s[5], h.vscale);
 }
+
+// ---- packed PID / aux word (bitpacked.py:15-23, 269-311): bits 0-14, 16-30, 32-46 = Lagrangian index (x, y, z),
+// bit 48 = L2-tagged, bits 49-58 = sqrt of the local density.  uint64 times a float scale promotes to float64 in the
+// reference; the store rounds once to the output type.
+constexpr uint64_t ABK_AUX_X = 0x7FFFull, ABK_AUX_Y = 0x7FFF0000ull, ABK_AUX_Z = 0x7FFF00000000ull;
+constexpr uint64_t ABK_AUX_PID = ABK_AUX_X | ABK_AUX_Y | ABK_AUX_Z, ABK_AUX_DENS = 0x07FE000000000000ull;
+
+ABK_HD void abk_pid_lagr_idx(uint64_t p, int16_t idx[3])
+{
+    idx[0] = (int16_t)(p & ABK_AUX_X);
+    idx[1] = (int16_t)((p & ABK_AUX_Y) >> 16);
+    idx[2] = (int16_t)((p & ABK_AUX_Z) >> 32);
+}
+// inv_ppd and half are already rounded to T by the caller (bitpacked.py:286-287)
+template <typename T>
+ABK_HD void abk_pid_lagr_pos(uint64_t p, T inv_ppd, T half, T pos[3])
+{
+    pos[0] = (T)abk_add(abk_mul((double)(p & ABK_AUX_X), (double)inv_ppd), -(double)half);
+    pos[1] = (T)abk_add(abk_mul((double)((p & ABK_AUX_Y) >> 16), (double)inv_ppd), -(double)half);
+    pos[2] = (T)abk_add(abk_mul((double)((p & ABK_AUX_Z) >> 32), (double)inv_ppd), -(double)half);
+}
+ABK_HD uint8_t abk_pid_tagged(uint64_t p) { return (uint8_t)((p >> 48) & 1ull); }
+template <typename T>
+ABK_HD T abk_pid_density(uint64_t p)
+{
+    const uint64_t r = (p & ABK_AUX_DENS) >> 49;
+    return (T)(r * r);
+}
+ABK_HD int64_t abk_pid_pid(uint64_t p) { return (int64_t)(p & ABK_AUX_PID); }

@@ -296,6 +296,13 @@ int abk_bin_kppi(abk_ctx *ctx, const void *weights, int weights_f64, int n, int6
 int abk_unpack_rvint(abk_ctx *ctx, const int32_t *intdata, int64_t N, double boxsize, void *posout, void *velout,
                      int out_f64);
 
+/* `unpack_pids` (abacusnbody/data/bitpacked.py:123-311): fields of the packed 64-bit PID/aux word, packed uint64[N] on
+ * the device.  Any output may be NULL: pid int64[N] (the three 15-bit Lagrangian indices in place), lagr_pos [N][3]
+ * float32/float64 (index * T(box/ppd) - T(box/2), float64 arithmetic rounded once), lagr_idx int16[N][3], tagged
+ * uint8[N] (bit 48), density [N] float32/float64 (bits 49-58, squared). */
+int abk_unpack_pids(abk_ctx *ctx, const uint64_t *packed, int64_t N, double box, int64_t ppd, int64_t *pid, void *lagr_pos,
+                    int16_t *lagr_idx, uint8_t *tagged, void *density, int out_f64);
+
 /* `unpack_pack9` (abacusnbody/data/pack9.py:16-123) in two calls, because the number of particle records is only
  * known after the cell headers (records whose first byte is 0xFF) have been counted:
  *   abk_pack9_count   counts headers per 256-record block and scans the counts into `scratch`

@@ -579,3 +579,30 @@ def unpack_pack9(data, boxsize, velzspace_to_kms, float_dtype=np.float32, posout
             spec[:npart] = val
             ret.append(npart)
     return tuple(ret)
+
+
+def unpack_pids(packed, box=None, ppd=None, pid=False, lagr_pos=False, tagged=False, density=False, lagr_idx=False,
+                float_dtype=np.float32):
+    """abacusnbody/data/bitpacked.py:123-311.  uint64 * float promotes to float64 in the reference's kernel; the
+    scale and the half-box are rounded to ``float_dtype`` first (:286-287)."""
+    T = np.dtype(float_dtype).type
+    p = np.asanyarray(packed, dtype=np.uint64).reshape(-1)
+    ppd = 1 if ppd is None else int(round(ppd))
+    box = 1.0 if box is None else float(box)
+    inv_ppd, half = np.float64(T(box / ppd)), np.float64(T(box / 2))
+    ix = (p & np.uint64(0x7FFF)).astype(np.int64)
+    iy = ((p & np.uint64(0x7FFF0000)) >> np.uint64(16)).astype(np.int64)
+    iz = ((p & np.uint64(0x7FFF00000000)) >> np.uint64(32)).astype(np.int64)
+    out = {}
+    if pid is True:
+        out['pid'] = (p & np.uint64(0x7FFF7FFF7FFF)).astype(np.int64)
+    if lagr_pos is True:
+        out['lagr_pos'] = (np.stack([ix, iy, iz], axis=1).astype(np.float64) * inv_ppd - half).astype(T)
+    if lagr_idx is True:
+        out['lagr_idx'] = np.stack([ix, iy, iz], axis=1).astype(np.int16)
+    if tagged is True:
+        out['tagged'] = ((p >> np.uint64(48)) & np.uint64(1)).astype(np.uint8)
+    if density is True:
+        r = ((p & np.uint64(0x07FE000000000000)) >> np.uint64(49)).astype(np.int64)
+        out['density'] = (r * r).astype(T)
+    return out

@@ -215,6 +215,20 @@ def golden_ingest():
     out['rvint/box'] = header_value(fn, 'BoxSize')
     out['rvint/pos'] = np.frombuffer(gb[0], dtype='<f4').reshape(-1, 3)[: len(rv)]
     out['rvint/vel'] = np.frombuffer(gb[1], dtype='<f4').reshape(-1, 3)[: len(rv)]
+    # packed PIDs: halos/z0.000/field_pid_A/field_pid_A_000.asdf -> ref_data/test_read_asdf.asdf blocks 2..7
+    # (aux, pid, lagr_pos, lagr_idx, tagged, density; tests/test_data.py:303-318)
+    fn = sim / 'halos' / 'z0.000' / 'field_pid_A' / 'field_pid_A_000.asdf'
+    packed = np.frombuffer(read_asdf_blocks(fn)[0], dtype='<u8')
+    n = len(packed)
+    out['pids/in'] = packed
+    out['pids/box'] = header_value(fn, 'BoxSize')
+    out['pids/ppd'] = header_value(fn, 'ppd')
+    assert np.array_equal(np.frombuffer(gb[2], dtype='<u8')[:n], packed)
+    out['pids/pid'] = np.frombuffer(gb[3], dtype='<i8')[:n]
+    out['pids/lagr_pos'] = np.frombuffer(gb[4], dtype='<f4').reshape(-1, 3)[:n]
+    out['pids/lagr_idx'] = np.frombuffer(gb[5], dtype='<i2').reshape(-1, 3)[:n]
+    out['pids/tagged'] = np.frombuffer(gb[6], dtype='u1')[:n]
+    out['pids/density'] = np.frombuffer(gb[7], dtype='<f4')[:n]
     # pack9: slices/z0.000/L0_pack9/slab000.L0.pack9.asdf -> ref_data/test_pack9.asdf; keep the first records only
     fn = sim / 'slices' / 'z0.000' / 'L0_pack9' / 'slab000.L0.pack9.asdf'
     raw = open(fn, 'rb').read()

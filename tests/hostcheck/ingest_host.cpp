@@ -48,3 +48,22 @@ void hc_rvint_f64(const int32_t *in, int64_t n, double box, double *pos, double 
 int64_t hc_pack9_f32(const uint8_t *d, int64_t n, double box, double velz, float *pos, float *vel) { return pack9<float>(d, n, box, velz, pos, vel); }
 int64_t hc_pack9_f64(const uint8_t *d, int64_t n, double box, double velz, double *pos, double *vel) { return pack9<double>(d, n, box, velz, pos, vel); }
 }
+
+template <typename T>
+static void pids(const uint64_t *packed, int64_t n, double box, int64_t ppd, int64_t *pid, T *lagr_pos, int16_t *lagr_idx,
+                 uint8_t *tagged, T *density)
+{
+    const T inv_ppd = (T)(box / (double)ppd), half = (T)(box / 2);
+    for (int64_t i = 0; i < n; i++) {
+        if (pid) pid[i] = abk_pid_pid(packed[i]);
+        if (lagr_pos) abk_pid_lagr_pos<T>(packed[i], inv_ppd, half, lagr_pos + 3 * i);
+        if (lagr_idx) abk_pid_lagr_idx(packed[i], lagr_idx + 3 * i);
+        if (tagged) tagged[i] = abk_pid_tagged(packed[i]);
+        if (density) density[i] = abk_pid_density<T>(packed[i]);
+    }
+}
+
+extern "C" {
+void hc_pids_f32(const uint64_t *p, int64_t n, double box, int64_t ppd, int64_t *pid, float *lp, int16_t *li, uint8_t *tg, float *de) { pids<float>(p, n, box, ppd, pid, lp, li, tg, de); }
+void hc_pids_f64(const uint64_t *p, int64_t n, double box, int64_t ppd, int64_t *pid, double *lp, int16_t *li, uint8_t *tg, double *de) { pids<double>(p, n, box, ppd, pid, lp, li, tg, de); }
+}

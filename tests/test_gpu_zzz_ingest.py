@@ -47,6 +47,34 @@ def test_rvint_vs_oracle(mods, oracle, dt):
     np.testing.assert_array_equal(buf, ovel)
 
 
+PID_KEYS = ('pid', 'lagr_pos', 'lagr_idx', 'tagged', 'density')
+
+
+def test_pids_reference_fixture(mods):
+    bitpacked, _ = mods
+    g = np.load(GOLD)
+    got = bitpacked.unpack_pids(g['pids/in'], box=float(g['pids/box']), ppd=float(g['pids/ppd']), **{k: True for k in PID_KEYS})
+    for k in PID_KEYS:
+        assert got[k].dtype == g[f'pids/{k}'].dtype, k
+        np.testing.assert_array_equal(got[k], g[f'pids/{k}'], err_msg=k)
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+def test_pids_vs_oracle(mods, oracle, dt):
+    import torch
+
+    bitpacked, _ = mods
+    rng = np.random.default_rng(61)
+    packed = rng.integers(0, 2**63, size=200001, dtype=np.int64).astype(np.uint64) | (rng.integers(0, 2, size=200001).astype(np.uint64) << np.uint64(63))
+    want = oracle.unpack_pids(packed, box=2000.0, ppd=6912, float_dtype=dt, **{k: True for k in PID_KEYS})
+    got = bitpacked.unpack_pids(packed, box=2000.0, ppd=6912, float_dtype=dt, **{k: True for k in PID_KEYS})
+    for k in PID_KEYS:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    dev = bitpacked.unpack_pids(torch.from_numpy(packed.view(np.int64)).cuda(), density=True, float_dtype=dt)
+    assert dev.keys() == {'density'} and dev['density'].is_cuda
+    np.testing.assert_array_equal(dev['density'].cpu().numpy(), want['density'])
+
+
 def test_pack9_reference_fixture(mods):
     _, pack9 = mods
     g = np.load(GOLD)

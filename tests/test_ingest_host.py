@@ -34,6 +34,8 @@ def hc(tmp_path_factory):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
     for f in ('hc_rvint_f32', 'hc_rvint_f64'):
         getattr(lib, f).argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+    for f in ('hc_pids_f32', 'hc_pids_f64'):
+        getattr(lib, f).argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_int64] + [C.c_void_p] * 5
     return lib
 
 
@@ -51,6 +53,48 @@ def hc_pack9(lib, d, box, velz, dt):
     fn = lib.hc_pack9_f32 if dt == np.float32 else lib.hc_pack9_f64
     n = fn(d.ctypes.data, len(d), box, velz, pos.ctypes.data, vel.ctypes.data)
     return pos[:n], vel[:n]
+
+
+def hc_pids(lib, packed, box, ppd, dt):
+    packed = np.ascontiguousarray(packed, dtype=np.uint64)
+    n = len(packed)
+    out = dict(pid=np.empty(n, np.int64), lagr_pos=np.empty((n, 3), dt), lagr_idx=np.empty((n, 3), np.int16),
+               tagged=np.empty(n, np.uint8), density=np.empty(n, dt))
+    fn = lib.hc_pids_f32 if dt == np.float32 else lib.hc_pids_f64
+    fn(packed.ctypes.data, n, box, ppd, *(out[k].ctypes.data for k in ('pid', 'lagr_pos', 'lagr_idx', 'tagged', 'density')))
+    return out
+
+
+PID_KEYS = ('pid', 'lagr_pos', 'lagr_idx', 'tagged', 'density')
+
+
+def random_packed_pids(seed, n):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 2**63, size=n, dtype=np.int64).astype(np.uint64) | (rng.integers(0, 2, size=n).astype(np.uint64) << np.uint64(63))
+
+
+def test_oracle_pids_vs_reference_fixture(oracle):
+    g = np.load(GOLD)
+    got = oracle.unpack_pids(g['pids/in'], box=float(g['pids/box']), ppd=float(g['pids/ppd']), **{k: True for k in PID_KEYS})
+    for k in PID_KEYS:
+        assert got[k].dtype == g[f'pids/{k}'].dtype, k
+        np.testing.assert_array_equal(got[k], g[f'pids/{k}'], err_msg=k)
+    assert oracle.unpack_pids(g['pids/in'], pid=True).keys() == {'pid'}
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+def test_kernel_arithmetic_pids(hc, oracle, dt):
+    g = np.load(GOLD)
+    got = hc_pids(hc, g['pids/in'], float(g['pids/box']), int(g['pids/ppd']), dt)
+    if dt == np.float32:
+        for k in PID_KEYS:
+            np.testing.assert_array_equal(got[k], g[f'pids/{k}'], err_msg=k)
+    for seed, box, ppd in ((61, 2000.0, 6912), (62, 500.0, 1728), (63, 296.0, 1000)):
+        packed = random_packed_pids(seed, 40000)
+        got = hc_pids(hc, packed, box, ppd, dt)
+        want = oracle.unpack_pids(packed, box=box, ppd=ppd, float_dtype=dt, **{k: True for k in PID_KEYS})
+        for k in PID_KEYS:
+            np.testing.assert_array_equal(got[k], want[k], err_msg=k)
 
 
 def test_oracle_rvint_vs_reference_fixture(oracle):
@@ -118,6 +162,11 @@ class _FakeLib:
     def abk_unpack_rvint(self, ctx, data, N, box, pos, vel, f64):
         fn = self.hc.hc_rvint_f64 if f64 else self.hc.hc_rvint_f32
         fn(self._addr(data), N, box, self._addr(pos) or None, self._addr(vel) or None)
+        return 0
+
+    def abk_unpack_pids(self, ctx, packed, N, box, ppd, pid, lagr_pos, lagr_idx, tagged, density, f64):
+        fn = self.hc.hc_pids_f64 if f64 else self.hc.hc_pids_f32
+        fn(self._addr(packed), N, box, ppd, *(self._addr(p) or None for p in (pid, lagr_pos, lagr_idx, tagged, density)))
         return 0
 
     def abk_pack9_scratch_bytes(self, nrec, out):
@@ -217,3 +266,23 @@ def test_wrapper_unpack_pack9_conventions(fake_engine, oracle, dt):
     # empty stream
     pos, vel = unpack_pack9(np.zeros((0, 9), np.uint8), 1000.0, 321.0, float_dtype=dt)
     assert pos.shape == (0, 3) and vel.shape == (0, 3)
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64])
+def test_wrapper_unpack_pids_conventions(fake_engine, oracle, dt):
+    from abacusutils_b200.data.bitpacked import unpack_pids
+
+    packed = random_packed_pids(71, 3001)
+    want = oracle.unpack_pids(packed, box=720.0, ppd=1440, float_dtype=dt, **{k: True for k in PID_KEYS})
+    got = unpack_pids(packed, box=720.0, ppd=1440.0, float_dtype=dt, **{k: True for k in PID_KEYS})
+    assert got.keys() == want.keys()
+    for k in PID_KEYS:
+        assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape, k
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    only = unpack_pids(packed, tagged=True, density=True, float_dtype=dt)   # no box / ppd needed (bitpacked.py:200-205)
+    assert only.keys() == {'tagged', 'density'}
+    np.testing.assert_array_equal(only['density'], want['density'])
+    with pytest.raises(ValueError):
+        unpack_pids(packed, lagr_pos=True)
+    with pytest.raises(ValueError):
+        unpack_pids(packed, box=720.0, ppd=12.5, lagr_pos=True)
