@@ -214,6 +214,26 @@ def used_entries(n, L, kmax):
     return int(np.clip(cnt, 0, n // 2 + 1).sum())
 
 
+def make_positions(torch, N, L, seed, clustered=0.0, chunk=50_000_000):
+    """Seeded synthetic catalogue on the device: uniform, or (testing only) a fraction `clustered` of the particles in
+    4096 Gaussian blobs of sigma = L/400 (periodic), which stresses tile load balance and the capacity passes."""
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(seed)
+    pos = torch.rand((N, 3), device='cuda', dtype=torch.float32, generator=gen)
+    pos *= L
+    nb = int(N * clustered)
+    if nb:
+        centers = torch.rand((4096, 3), device='cuda', dtype=torch.float32, generator=gen) * L
+        for a in range(0, nb, chunk):
+            b = min(nb, a + chunk)
+            idx = torch.randint(0, 4096, (b - a,), device='cuda', generator=gen)
+            blob = centers[idx] + torch.randn((b - a, 3), device='cuda', dtype=torch.float32, generator=gen) * (L / 400.0)
+            pos[a:b] = torch.remainder(blob, L)
+            del idx, blob
+        pos.clamp_(0.0, float(torch.nextafter(torch.tensor(L, dtype=torch.float32), torch.tensor(0.0))))
+    return pos
+
+
 def run_gpu_arm(args):
     import torch
 
@@ -238,8 +258,7 @@ def run_gpu_arm(args):
     N, L, n = cfg['N'], cfg['L'], cfg['nmesh']
     gen = torch.Generator(device='cuda')
     gen.manual_seed(cfg['seed'])
-    pos = torch.rand((N, 3), device='cuda', dtype=torch.float32, generator=gen)
-    pos *= L
+    pos = make_positions(torch, N, L, cfg['seed'], args.clustered)
     kw = dict(kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=n, compensated=True, interlaced=True, poles=cfg['poles'])
 
     def step(p):
@@ -355,7 +374,8 @@ def run_gpu_arm(args):
         'metric': METRIC, 'value': ms, 'unit': 'ms', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD if not (args.nparticles or args.nmesh) else f'override N={N} nmesh={n}',
+        'config': {'workload': (WORKLOAD if not (args.nparticles or args.nmesh or args.clustered) else
+                                f'override N={N} nmesh={n} clustered={args.clustered}'),
                    'l2': 'inputs (12 GB particles, 4.3 GB grids) are larger than the 126 MB L2'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'stages': stages,
@@ -378,6 +398,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--nparticles', type=int, default=0, help='override the particle count (testing only)')
     ap.add_argument('--nmesh', type=int, default=0, help='override nmesh (testing only)')
+    ap.add_argument('--clustered', type=float, default=0.0,
+                    help='fraction of the particles placed in Gaussian blobs (testing only; the headline is uniform)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs only)')
     args = ap.parse_args()
