@@ -42,9 +42,10 @@ class Output:
             self.direct = True
         else:
             if self.user is not None:
-                a = np.asarray(self.user)
+                a = np.asarray(self.user)   # shares memory with NumPy arrays and CPU tensors
                 if a.size < 3 * nrows:
                     raise ValueError('output array too small')
+                self.user = a
             self.dev = eng.empty((nrows, 3), tdtype)
             self.direct = False
 
