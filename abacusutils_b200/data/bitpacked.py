@@ -8,7 +8,7 @@ be copied to the GPU still packed, 12 bytes per particle for positions *and* vel
 
 import numpy as np
 
-from .._lib import check, is_torch_tensor, ptr
+from .._lib import check, ptr
 from ._common import Output, engine_for, torch_float
 
 __all__ = ['unpack_rvint', 'unpack_pids']
