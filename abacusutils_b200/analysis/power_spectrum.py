@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import warnings
 
 import numpy as np
@@ -147,10 +148,17 @@ class _Painter:
         # applies no periodic wrap to the positions (power_spectrum.py:846-853)
         self.paste = _check_paste(paste)
 
-    def chunk_plan(self, N):
+    def chunk_plan(self, N, host=True):
+        """Chunks of the particle set; every chunk becomes one bucket segment.  Host inputs want many chunks (they
+        are the unit of copy/compute overlap).  Device-resident inputs only need them below SEGMENT_MAX particles;
+        ABK_DEVICE_SEGMENTS (experiment knob, default: same plan as host inputs) sets their number."""
         max_seg = ABK_MAX_SEGMENTS - 2
-        chunk = max(1 << 25, -(-N // max_seg))
-        chunk = min(chunk, SEGMENT_MAX)
+        if not host and os.environ.get('ABK_DEVICE_SEGMENTS'):
+            max_seg = max(1, min(max_seg, int(os.environ['ABK_DEVICE_SEGMENTS'])))
+            chunk = -(-N // max_seg)
+        else:
+            chunk = max(1 << 25, -(-N // max_seg))
+        chunk = min(max(chunk, 1), SEGMENT_MAX)
         return [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
 
     def paint(self, pos, w, offsets, wrap=True, tag='', fft_weight=None):
@@ -189,7 +197,7 @@ class _Painter:
         ntiles = C.c_int64()
         check(lib.abk_tsc_num_tiles(n, n, n, C.byref(ntiles)))
         ntiles = ntiles.value
-        chunks = self.chunk_plan(N)
+        chunks = self.chunk_plan(N, host=(kind == 'host'))
         nseg = len(chunks)
         nb = C.c_size_t()
         check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))

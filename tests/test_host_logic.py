@@ -45,6 +45,21 @@ def test_chunk_plan_covers_everything_within_limits():
         assert len(chunks) <= ABK_MAX_SEGMENTS
 
 
+def test_chunk_plan_device_segment_knob(monkeypatch):
+    from abacusutils_b200._lib import SEGMENT_MAX
+    from abacusutils_b200.analysis.power_spectrum import _Painter
+
+    P = _Painter.__new__(_Painter)
+    assert P.chunk_plan(10**9, host=False) == P.chunk_plan(10**9, host=True)      # default: same plan
+    monkeypatch.setenv('ABK_DEVICE_SEGMENTS', '1')
+    assert P.chunk_plan(10**9, host=False) == [(0, 10**9)]
+    assert P.chunk_plan(10**9, host=True) == _Painter.chunk_plan(P, 10**9)          # host plan untouched
+    big = P.chunk_plan(3 * 10**9, host=False)                                       # still bounded by SEGMENT_MAX
+    assert big[-1][1] == 3 * 10**9 and all(b - a <= SEGMENT_MAX for a, b in big)
+    monkeypatch.setenv('ABK_DEVICE_SEGMENTS', '4')
+    assert len(P.chunk_plan(10**9, host=False)) == 4
+
+
 def test_legendre_coefficients_against_numpy():
     from numpy.polynomial import legendre as npl
 
