@@ -135,3 +135,32 @@ def test_packed_to_power_on_device(mods, oracle):
     b = calc_power(opos.copy(), L, **kw)
     np.testing.assert_array_equal(np.asarray(a['N_mode']), np.asarray(b['N_mode']))
     np.testing.assert_allclose(np.asarray(a['power']), np.asarray(b['power']), rtol=1e-4, atol=1e-4 * np.abs(np.asarray(b['power'])).max())
+
+
+def test_read_asdf_to_device(tmp_path, oracle):
+    """File -> host decompression -> packed bytes to the GPU -> decode there -> columns stay on the device."""
+    from asdf_writer import write_asdf
+
+    from abacusutils_b200.data.read_abacus import read_asdf
+
+    g = np.load(GOLD)
+    hdr = {'BoxSize': float(g['pack9/box']), 'VelZSpace_to_kms': float(g['pack9/velz']), 'ppd': float(g['pids/ppd'])}
+    fn = tmp_path / 'p9.asdf'
+    write_asdf(fn, {'pack9': g['pack9/in'].view(np.int8)}, hdr, shuffle='bitshuffle', pad=700)
+    t = read_asdf(fn, device=True, verbose=False)
+    assert t['pos'].is_cuda and t['vel'].is_cuda and t.meta['BoxSize'] == hdr['BoxSize']
+    np.testing.assert_array_equal(t['pos'].cpu().numpy(), g['pack9/pos'])
+    np.testing.assert_array_equal(t['vel'].cpu().numpy(), g['pack9/vel'])
+    t = read_asdf(fn, load=('pos',))
+    np.testing.assert_array_equal(t['pos'], g['pack9/pos'])
+    fn = tmp_path / 'rv.asdf'
+    write_asdf(fn, {'rvint': g['rvint/in']}, hdr)
+    t = read_asdf(fn)
+    np.testing.assert_array_equal(t['pos'], g['rvint/pos'])
+    np.testing.assert_array_equal(t['vel'], g['rvint/vel'])
+    fn = tmp_path / 'pid.asdf'
+    write_asdf(fn, {'packedpid': g['pids/in']}, hdr)
+    t = read_asdf(fn, load=('aux', 'pid', 'lagr_pos', 'tagged', 'density', 'lagr_idx'))
+    np.testing.assert_array_equal(t['aux'], g['pids/in'])
+    for k in PID_KEYS:
+        np.testing.assert_array_equal(t[k], g[f'pids/{k}'], err_msg=k)
