@@ -103,3 +103,63 @@ def test_finalize_bins_matches_reference_tail():
     assert k[2, 0] == pytest.approx(14 * 0.5 / 4)
     np.testing.assert_allclose(p[0], [(1 + 2 + 3) / 3, 15, (7 + 8 + 9) / 12, (10 + 11 + 12) / 2])  # row l=0 = sum over mu / counts
     np.testing.assert_allclose(p[1], [1 / 3, 2, 3 / 12, 4 / 2])
+
+
+def test_bin_kppi_wrapper_marshalling(monkeypatch):
+    """The Python side of bin_kppi (squared-edge tables, dtype flags, row stride, final division) against the
+    reference's outputs, with the kernel replaced by a NumPy stand-in that consumes exactly what the wrapper passes."""
+    import ctypes as C
+
+    import torch
+
+    import cases
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    def as_np(p, dtype, count):
+        addr = p.value if hasattr(p, 'value') else p
+        return np.ctypeslib.as_array(C.cast(addr, C.POINTER(C.c_uint8)), shape=(count * np.dtype(dtype).itemsize,)).view(dtype)
+
+    class Lib:
+        def abk_bin_kppi(self, ctx, w, w_f64, n, ldz, ke2, Nk, pe2, Npi, kperp_f32, counts, sums):
+            wt = as_np(w, np.float64 if w_f64 else np.float32, n * n * ldz).reshape(n, n, ldz)
+            ke, pe = as_np(ke2, np.float64, Nk + 1), as_np(pe2, np.float64, Npi + 1)
+            cnt, sm = as_np(counts, np.int64, Nk * Npi).reshape(Nk, Npi), as_np(sums, np.float64, Nk * Npi).reshape(Nk, Npi)
+            fold = np.where(np.arange(n) < n // 2, np.arange(n), np.arange(n) - n).astype(np.int64)
+            kz2 = np.arange(n // 2 + 1, dtype=np.float64) ** 2
+            use = kz2 < pe[-1]
+            bpi = np.searchsorted(pe[1:], kz2[use], side='left')
+            mult = np.where(np.arange(n // 2 + 1) == 0, 1, 2)[use]
+            for i in range(n):
+                kp2 = fold[i] ** 2 + fold ** 2
+                kp2 = kp2.astype(np.float32).astype(np.float64) if kperp_f32 else kp2.astype(np.float64)
+                over = np.flatnonzero(kp2 >= ke[-1])
+                jend = over[0] if len(over) else n
+                for j in np.flatnonzero(kp2[:jend] >= ke[0]):
+                    bk = np.searchsorted(ke[1:], kp2[j], side='left')
+                    np.add.at(cnt[bk], bpi, mult)
+                    np.add.at(sm[bk], bpi, wt[i, j, :n // 2 + 1][use].astype(np.float64) * mult)
+            return 0
+
+    class Eng:
+        lib, ctx = Lib(), None
+
+        def bind_stream(self):
+            pass
+
+        def to_device(self, arr, dtype=None):
+            t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(arr))
+            return (t.to(dtype) if dtype is not None and t.dtype != dtype else t).contiguous()
+
+        def zeros(self, shape, dtype):
+            return torch.zeros(shape, dtype=dtype)
+
+    monkeypatch.setattr(ps.Engine, 'get', classmethod(lambda cls, device=None: Eng()))
+    g = np.load(cases.__file__.replace('cases.py', 'reference_kppi.npz'))
+    for name in ('f16', 'f16_break', 'f15_odd', 'r24', 'f20_f64', 'f40_1bin'):
+        c = cases.KPPI_CASES[name]
+        w, kedges, pimax = cases.kppi_inputs(c)
+        mean, cnt = ps.bin_kppi(c['n'], c['L'], kedges, pimax, c['Npi'], w, dtype=np.dtype(c['dtype']).type, fourier=c['fourier'])
+        want = g[f'kppi/{name}/mean']
+        assert mean.dtype == want.dtype and cnt.dtype == np.int64
+        np.testing.assert_array_equal(cnt, g[f'kppi/{name}/counts'], err_msg=name)
+        np.testing.assert_allclose(mean, want, rtol=1e-5, atol=2e-6, err_msg=name)
