@@ -5,8 +5,9 @@ GPU parity of the particle decoders (abk_ingest.cu) -- bit-
   * the CPU oracle on seeded streams (cell headers at block/warp boundaries, no leading header, empty input),
 and the packed -> calc_power path with the positions never leaving the device.
 
-This file sorts last on purpose: the kernels were written after the round-1 GPU budget was spent; their
-per-record arithmetic is pinned on the CPU (tests/test_ingest_host.py), the launch plumbing is first exercised here.
+This file sorts last on purpose: the kernels were written after the round-1 GPU budget was spent.  Their per-record
+arithmetic is pinned on the CPU (tests/test_ingest_host.py) and the unmodified kernel sources run under the CPU
+emulator (tests/test_emu_kernels.py); this is their first execution on a device.
 """
 
 import numpy as np
