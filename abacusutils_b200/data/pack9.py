@@ -43,14 +43,15 @@ def unpack_pack9(data, boxsize, velzspace_to_kms, float_dtype=np.float32, posout
     nrec = int(d.shape[0])
     nb = C.c_size_t()
     check(eng.lib.abk_pack9_scratch_bytes(nrec, C.byref(nb)))
-    scratch = eng.scratch('pack9', nb.value)
+    scratch = eng.scratch('pack9', nb.value + 256)
+    sptr = C.c_void_p((scratch.data_ptr() + 255) & ~255)   # the scan wants 256-byte alignment whatever the allocator gives
     nhdr = C.c_int64()
-    check(eng.lib.abk_pack9_count(eng.ctx, ptr(d), nrec, ptr(scratch), scratch.numel(), C.byref(nhdr)))
+    check(eng.lib.abk_pack9_count(eng.ctx, ptr(d), nrec, sptr, nb.value, C.byref(nhdr)))
     nhdr = nhdr.value
     npart = nrec - nhdr
     hdr_tab = eng.empty((max(nhdr, 1), 5), tdtype)
     pos = Output(eng, posout, npart, tdtype, on_device)
     vel = Output(eng, velout, npart, tdtype, on_device)
-    check(eng.lib.abk_pack9_decode(eng.ctx, ptr(d), nrec, float(boxsize), float(velzspace_to_kms), ptr(scratch),
+    check(eng.lib.abk_pack9_decode(eng.ctx, ptr(d), nrec, float(boxsize), float(velzspace_to_kms), sptr,
                                    ptr(hdr_tab), nhdr, pos.pointer(), vel.pointer(), f64))
     return pos.result(), vel.result()

@@ -5,7 +5,7 @@ from pathlib import Path
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
-for p in (ROOT, ROOT / 'tests' / 'golden'):
+for p in (ROOT, ROOT / 'tests' / 'golden', ROOT / 'tests' / 'emu'):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))
 
@@ -31,3 +31,9 @@ def oracle():
 
     abk_oracle.build()
     return abk_oracle
+
+
+@pytest.fixture(scope='session')
+def emu_build_dir(tmp_path_factory):
+    """Where tests/emu/build_emu.py puts libabk_emu.so (built once per session)."""
+    return tmp_path_factory.mktemp('abk_emu')

@@ -1,5 +1,5 @@
 """
-Build libabk_emu.so: the UNMODIFIED kernel sources of libabk (ctx, ingest, kfields) compiled for the CPU against
+Build libabk_emu.so: the UNMODIFIED kernel sources of libabk (everything but the cuFFT wrapper) compiled for the CPU against
 tests/emu/include/cuda_runtime.h, which runs every CUDA thread as an OS thread (TEST INFRASTRUCTURE ONLY).
 
 The only source transformation is syntactic: `kernel<<<grid, block, smem, stream>>>(args)` becomes
@@ -15,14 +15,16 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / 'abacusutils_b200' / 'csrc'
-SOURCES = ['abk_ctx.cu', 'abk_ingest.cu', 'abk_kfields.cu']
+SOURCES = ['abk_ctx.cu', 'abk_ingest.cu', 'abk_kfields.cu', 'abk_kspace.cu', 'abk_tsc.cu']
 
 LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(', re.S)
-DYN_SMEM = re.compile(r'extern\s+__shared__\s+([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;')
+PTX_HINT = re.compile(r'asm\s+volatile\s*\(\s*"prefetch[^;]*;[^;]*;')   # the PTX string itself ends in ';'
+DYN_SMEM = re.compile(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:<> ]+?)\s+(\w+)\s*\[\s*\]\s*;')
 
 
 def translate(text):
     text = LAUNCH.sub(lambda m: f'emu::launch({m.group(2)})({m.group(1)})(', text)
+    text = PTX_HINT.sub('(void)0;', text)   # cache hints have no functional effect
     text = DYN_SMEM.sub(lambda m: f'{m.group(1)} *{m.group(2)} = ({m.group(1)} *)emu::dyn_smem();', text)
     return text
 
@@ -30,14 +32,17 @@ def translate(text):
 def build(outdir):
     outdir = Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
+    so = outdir / 'libabk_emu.so'
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob('*.cuh')) + [HERE / 'include' / 'cuda_runtime.h', ROOT / 'include' / 'abk.h']
+    if so.exists() and all(so.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return so
     cpps = []
     for s in SOURCES:
         dst = outdir / (Path(s).stem + '_emu.cpp')
         dst.write_text(translate((CSRC / s).read_text()))
         cpps.append(str(dst))
-    so = outdir / 'libabk_emu.so'
     gxx = '/usr/bin/g++' if Path('/usr/bin/g++').exists() else 'g++'
-    cmd = [gxx, '-std=c++20', '-O1', '-g', '-pthread', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-attributes',
+    cmd = [gxx, '-std=c++20', '-O1', '-g', '-pthread', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-attributes', '-D__CUDACC__',
            f'-I{HERE / "include"}', f'-I{CSRC}', f'-I{ROOT / "include"}', '-o', str(so), *cpps]
     subprocess.run(cmd, check=True)
     return so

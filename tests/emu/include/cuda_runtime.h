@@ -1,20 +1,23 @@
 // CPU stand-in for the CUDA runtime + SIMT execution model (TEST INFRASTRUCTURE ONLY; tests/emu/README in build_emu.py).
-// Every CUDA thread of a block is a real OS thread: __syncthreads() is a std::barrier over the block, the
-// warp-synchronous intrinsics (__ballot_sync, __shfl_*_sync, ...) exchange through a per-warp buffer guarded by a
-// std::barrier over the warp's lanes, atomics are real atomics, __shared__ variables are function-local statics
-// (blocks run one after the other).  A thread that returns drops out of both barriers, as on the GPU.
+// Every CUDA thread of a block is a fiber (ucontext) scheduled round-robin on one OS thread: __syncthreads() parks the
+// fiber until all live threads of the block have arrived, the warp-synchronous intrinsics (__ballot_sync,
+// __shfl_*_sync, __match_any_sync, ...) exchange through a per-warp buffer between two warp barriers, atomics are plain
+// read-modify-writes, __shared__ variables are function-local statics (blocks run one after the other).  A thread that
+// returns no longer counts for any barrier, as on the GPU; a barrier that can never complete (reached by only part of
+// its threads) is reported as a deadlock instead of hanging.
 // Kernel launches `k<<<grid, block, smem, stream>>>(args)` are rewritten to `emu::launch(grid, block, smem, stream)(k)(args)`
 // by tests/emu/build_emu.py.  Only what libabk's ctx / ingest / kfields sources use is provided.
 #pragma once
-#include <atomic>
-#include <barrier>
+#include <ucontext.h>
+
+#include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <memory>
-#include <thread>
+#include <type_traits>
 #include <vector>
 
 #define __global__
@@ -31,61 +34,140 @@ struct dim3 {
     dim3(unsigned long long x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x((unsigned)x_), y(y_), z(z_) {}
 };
 
+// ---- SIMT execution: one fiber (ucontext) per CUDA thread, cooperative round-robin scheduling ----------------
 namespace emu {
-struct Warp {
-    std::barrier<> bar;
+enum Wait { RUNNABLE = 0, AT_BLOCK_BARRIER, AT_WARP_BARRIER, DONE };
+struct Fiber {
+    ucontext_t uc;
+    unsigned char *stack = nullptr;
+    dim3 tid, bid;
+    int lane = 0, warp = 0;
+    Wait wait = RUNNABLE;
+};
+struct WarpState {
     uint64_t buf[32];
-    explicit Warp(int lanes) : bar(lanes) { std::memset(buf, 0, sizeof(buf)); }
+    int live = 0, waiting = 0;
 };
-struct Block {
-    std::barrier<> bar;
-    std::vector<std::unique_ptr<Warp>> warps;
+struct BlockState {
+    std::vector<Fiber> fibers;
+    std::vector<WarpState> warps;
     std::vector<unsigned char> dyn;
-    explicit Block(int n) : bar(n) {}
+    int live = 0, waiting = 0;
 };
-inline thread_local Block *t_block = nullptr;
-inline thread_local Warp *t_warp = nullptr;
-inline thread_local int t_lane = 0;
-inline void *dyn_smem() { return t_block->dyn.data(); }
-}  // namespace emu
+inline BlockState *g_block = nullptr;
+inline Fiber *g_cur = nullptr;
+inline ucontext_t g_sched;
+inline const std::function<void()> *g_body = nullptr;
+inline void *dyn_smem() { return g_block->dyn.data(); }
+inline void yield() { swapcontext(&g_cur->uc, &g_sched); }
 
-inline thread_local dim3 threadIdx, blockIdx;
-inline dim3 blockDim, gridDim;
+inline void fiber_main()
+{
+    (*g_body)();
+    Fiber *f = g_cur;
+    f->wait = DONE;
+    g_block->live--;
+    g_block->warps[f->warp].live--;
+    g_block->warps[f->warp].buf[f->lane] = 0;
+    swapcontext(&f->uc, &g_sched);
+}
 
-namespace emu {
+// release the barriers whose live participants have all arrived (an exited thread no longer counts, as on the GPU)
+inline void release_barriers(BlockState &b)
+{
+    if (b.live > 0 && b.waiting == b.live) {
+        for (auto &f : b.fibers) if (f.wait == AT_BLOCK_BARRIER) f.wait = RUNNABLE;
+        b.waiting = 0;
+    }
+    for (size_t w = 0; w < b.warps.size(); w++) {
+        WarpState &ws = b.warps[w];
+        if (ws.live > 0 && ws.waiting == ws.live) {
+            for (auto &f : b.fibers) if (f.warp == (int)w && f.wait == AT_WARP_BARRIER) f.wait = RUNNABLE;
+            ws.waiting = 0;
+        }
+    }
+}
+
+inline void block_barrier()
+{
+    g_cur->wait = AT_BLOCK_BARRIER;
+    g_block->waiting++;
+    yield();
+}
+inline void warp_barrier()
+{
+    g_cur->wait = AT_WARP_BARRIER;
+    g_block->warps[g_cur->warp].waiting++;
+    yield();
+}
+
 struct Cfg {
     dim3 g, b;
     size_t smem;
 };
-template <class Body>
-void run(const Cfg &c, Body body)
+inline dim3 g_blockDim, g_gridDim;
+
+inline void run(const Cfg &c, const std::function<void()> &body)
 {
-    blockDim = c.b;
-    gridDim = c.g;
-    const int nthreads = (int)(c.b.x * c.b.y * c.b.z);
+    g_blockDim = c.b;
+    g_gridDim = c.g;
+    g_body = &body;
+    const int n = (int)(c.b.x * c.b.y * c.b.z);
+    constexpr size_t STACK = 256 * 1024;
+    static std::vector<unsigned char *> pool;   // fiber stacks, allocated once and never touched up front
+    while ((int)pool.size() < n) pool.push_back((unsigned char *)std::malloc(STACK));
+    BlockState blk;
+    blk.fibers.resize(n);
+    for (int t = 0; t < n; t++) blk.fibers[t].stack = pool[t];
+    blk.warps.resize((n + 31) / 32);
+    g_block = &blk;
     for (unsigned bz = 0; bz < c.g.z; bz++)
         for (unsigned by = 0; by < c.g.y; by++)
             for (unsigned bx = 0; bx < c.g.x; bx++) {
-                Block blk(nthreads);
                 blk.dyn.assign(c.smem + 16, 0);
-                for (int w = 0; w * 32 < nthreads; w++) blk.warps.emplace_back(new Warp(std::min(32, nthreads - w * 32)));
-                std::vector<std::thread> th;
-                th.reserve(nthreads);
-                for (int t = 0; t < nthreads; t++)
-                    th.emplace_back([&, t] {
-                        threadIdx = dim3(t % c.b.x, (t / c.b.x) % c.b.y, t / (c.b.x * c.b.y));
-                        blockIdx = dim3(bx, by, bz);
-                        t_block = &blk;
-                        t_warp = blk.warps[t / 32].get();
-                        t_lane = t % 32;
-                        body();
-                        t_warp->buf[t_lane] = 0;
-                        t_warp->bar.arrive_and_drop();
-                        blk.bar.arrive_and_drop();
-                    });
-                for (auto &x : th) x.join();
+                blk.live = n;
+                blk.waiting = 0;
+                for (auto &w : blk.warps) { std::memset(w.buf, 0, sizeof(w.buf)); w.live = 0; w.waiting = 0; }
+                for (int t = 0; t < n; t++) {
+                    Fiber &f = blk.fibers[t];
+                    f.tid = dim3(t % c.b.x, (t / c.b.x) % c.b.y, t / (c.b.x * c.b.y));
+                    f.bid = dim3(bx, by, bz);
+                    f.lane = t % 32;
+                    f.warp = t / 32;
+                    f.wait = RUNNABLE;
+                    blk.warps[f.warp].live++;
+                    getcontext(&f.uc);
+                    f.uc.uc_stack.ss_sp = f.stack;
+                    f.uc.uc_stack.ss_size = STACK;
+                    f.uc.uc_link = nullptr;
+                    makecontext(&f.uc, (void (*)())fiber_main, 0);
+                }
+                while (blk.live > 0) {
+                    bool progressed = false;
+                    for (int t = 0; t < n; t++) {
+                        Fiber &f = blk.fibers[t];
+                        if (f.wait != RUNNABLE) continue;
+                        g_cur = &f;
+                        swapcontext(&g_sched, &f.uc);
+                        progressed = true;
+                    }
+                    release_barriers(blk);
+                    if (!progressed) {
+                        bool any = false;
+                        for (auto &f : blk.fibers) any |= (f.wait == RUNNABLE);
+                        if (!any) {
+                            std::fprintf(stderr, "emu: deadlock in block (%u,%u,%u): %d live threads, %d at the block barrier; "
+                                         "a barrier or warp-synchronous intrinsic is reached by only part of its threads\n",
+                                         bx, by, bz, blk.live, blk.waiting);
+                            std::abort();
+                        }
+                    }
+                }
             }
+    g_block = nullptr;
+    g_cur = nullptr;
 }
+
 template <class F>
 struct Bound {
     Cfg c;
@@ -93,7 +175,8 @@ struct Bound {
     template <class... A>
     void operator()(A... a)
     {
-        run(c, [&] { f(a...); });
+        std::function<void()> body = [&] { f(a...); };
+        run(c, body);
     }
 };
 struct Launch {
@@ -122,27 +205,34 @@ inline T from_bits(uint64_t u)
 template <class T, class Pick>
 inline T exchange(T v, Pick src)
 {
-    Warp *w = t_warp;
-    w->buf[t_lane] = to_bits(v);
-    w->bar.arrive_and_wait();
-    const int s = src(t_lane);
-    const T r = (s >= 0 && s < 32) ? from_bits<T>(w->buf[s]) : v;
-    w->bar.arrive_and_wait();
+    WarpState &w = g_block->warps[g_cur->warp];
+    const int lane = g_cur->lane;
+    w.buf[lane] = to_bits(v);
+    warp_barrier();
+    const int s = src(lane);
+    const T r = (s >= 0 && s < 32) ? from_bits<T>(w.buf[s]) : v;
+    warp_barrier();
     return r;
 }
 }  // namespace emu
 
-inline void __syncthreads() { emu::t_block->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_warp->bar.arrive_and_wait(); }
+#define threadIdx (emu::g_cur->tid)
+#define blockIdx (emu::g_cur->bid)
+#define blockDim (emu::g_blockDim)
+#define gridDim (emu::g_gridDim)
+
+inline void __syncthreads() { emu::block_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_barrier(); }
 inline unsigned __ballot_sync(unsigned, int pred)
 {
-    emu::Warp *w = emu::t_warp;
-    w->buf[emu::t_lane] = pred ? 1 : 0;
-    w->bar.arrive_and_wait();
+    emu::WarpState &w = emu::g_block->warps[emu::g_cur->warp];
+    const int lane = emu::g_cur->lane;
+    w.buf[lane] = pred ? 1 : 0;
+    emu::warp_barrier();
     unsigned r = 0;
-    for (int l = 0; l < 32; l++) r |= (unsigned)(w->buf[l] != 0) << l;
-    w->bar.arrive_and_wait();
-    w->buf[emu::t_lane] = 0;
+    for (int l = 0; l < 32; l++) r |= (unsigned)(w.buf[l] != 0) << l;
+    emu::warp_barrier();
+    w.buf[lane] = 0;
     return r;
 }
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
@@ -155,6 +245,19 @@ template <class T>
 inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) { return emu::exchange(v, [=](int l) { return l + (int)d; }); }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu::exchange(v, [=](int l) { return l ^ m; }); }
+template <class T>
+inline unsigned __match_any_sync(unsigned, T v)
+{
+    emu::WarpState &w = emu::g_block->warps[emu::g_cur->warp];
+    const int lane = emu::g_cur->lane;
+    w.buf[lane] = emu::to_bits(v) ^ 0x8000000000000000ull;   // exited lanes hold 0: never equal to a live value
+    emu::warp_barrier();
+    unsigned r = 0;
+    for (int l = 0; l < 32; l++) r |= (unsigned)(w.buf[l] == w.buf[lane]) << l;
+    emu::warp_barrier();
+    w.buf[lane] = 0;
+    return r;
+}
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
@@ -167,26 +270,26 @@ inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
+using std::max;
+using std::min;
+inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+inline unsigned min(int a, unsigned b) { return (unsigned)a < b ? (unsigned)a : b; }
+inline long long min(long long a, int b) { return a < b ? a : b; }
+inline long long max(long long a, int b) { return a > b ? a : b; }
+inline void sincospif(float x, float *s, float *c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
+inline void sincospi(double x, double *s, double *c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
 template <class T>
 inline T __ldcs(const T *p) { return *p; }
 
 template <class T>
-inline T atomicAdd(T *p, T v)
-{
-    if constexpr (std::is_integral_v<T>) {
-        return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
-    } else {
-        std::atomic_ref<T> a(*p);
-        T old = a.load(std::memory_order_relaxed);
-        while (!a.compare_exchange_weak(old, old + v, std::memory_order_relaxed)) {}
-        return old;
-    }
-}
+inline T atomicAdd(T *p, T v) { const T old = *p; *p = old + v; return old; }
 inline unsigned atomicAdd(unsigned *p, int v) { return atomicAdd<unsigned>(p, (unsigned)v); }
 template <class T>
-inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline T atomicSub(T *p, T v) { const T old = *p; *p = old - v; return old; }
+template <class T>
+inline T atomicExch(T *p, T v) { const T old = *p; *p = v; return old; }
 
 // ---- runtime API ------------------------------------------------------------------------------
 typedef int cudaError_t;

@@ -1,0 +1,143 @@
+"""
+The product's Python layer on top of the real kernel sources, end to end on the CPU (tests/emu/emu_engine.py):
+tsc_parallel, calc_power (auto/cross, interlaced, compensated, log-k), get_field_fft, calc_pk_from_deltak, pk_to_xi,
+CIC, partition_parallel, 2-D grids and the ingest entry points, compared with the outputs of the unmodified reference
+(tests/golden/*.npz) exactly like the `-m gpu` tests do on the device.  Only cuFFT is substituted (scipy).
+"""
+
+import numpy as np
+import pytest
+
+import cases
+from common import assert_int_exact, compare_power_tables
+
+
+@pytest.fixture
+def emu(monkeypatch, emu_build_dir):
+    import emu_engine
+
+    return emu_engine.install(monkeypatch, emu_build_dir)
+
+
+@pytest.mark.parametrize('name', ['cube24_w_off', 'aniso', 'unwrapped', 'tiny10'])
+def test_tsc_parallel(emu, golden, name):
+    from abacusutils_b200.analysis import tsc
+
+    c = cases.TSC_CASES[name]
+    pos, w = cases.tsc_inputs(c)
+    dens = np.zeros(c['shape'], dtype=np.float32)
+    assert tsc.tsc_parallel(pos, dens, c['box'], weights=w, offset=c['offset'], wrap=c.get('wrap', True)) is None
+    np.testing.assert_allclose(dens, golden[f'tsc/{name}'], rtol=1e-4, atol=1e-5)
+    out = tsc.tsc_parallel(pos, c['shape'], c['box'], weights=w, offset=c['offset'], wrap=c.get('wrap', True))
+    np.testing.assert_allclose(out, golden[f'tsc/{name}'], rtol=1e-4, atol=1e-5)
+
+
+def test_tile_capacity_passes_and_variants(emu, oracle):
+    """Clustered input that overflows the per-tile record capacity (several passes per tile), and the alternative
+    deposit kernels (bits 16-18 of abk_ctx_set_tile_capacity) -- all against the oracle."""
+    from abacusutils_b200._lib import check
+    from abacusutils_b200.analysis import tsc
+
+    rng = np.random.default_rng(3)
+    box, n = 50.0, 20
+    pos = np.concatenate([rng.normal(25.0, 1.0, size=(6000, 3)), rng.random((1500, 3)) * box]).astype(np.float32) % np.float32(box)
+    w = rng.random(len(pos), dtype=np.float32)
+    want = np.zeros((n, n, n), np.float32)
+    oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
+    try:
+        for variant in (0, 1, 2, 3, 5):
+            check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 256 | (variant << 16)))
+            got = tsc.tsc_parallel(pos.copy(), (n, n, n), box, weights=w)
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5, err_msg=f'variant {variant}')
+    finally:
+        check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
+
+
+@pytest.mark.parametrize('name', ['n32_ci', 'n32_cross_ci', 'n32_raw', 'n36_nopoles_mu'])
+def test_calc_power(emu, golden, name):
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    c = cases.POWER_CASES[name]
+    pos, w, pos2, w2 = cases.power_inputs(c)
+    t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
+                      nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2,
+                      poles=c['poles'])
+    want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
+    compare_power_tables(t, want)
+
+
+def test_calc_power_cic(emu):
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    g = np.load(cases.__file__.replace('cases.py', 'reference_cic.npz'))
+    name = next(iter(cases.CIC_POWER_CASES))
+    c = cases.CIC_POWER_CASES[name]
+    pos, w, pos2, w2 = cases.power_inputs(c)
+    t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], logk=c['logk'], paste='CIC', nmesh=c['nmesh'],
+                      compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2, poles=c['poles'])
+    want = {k[len(f'power/{name}/'):]: g[k] for k in g.files if k.startswith(f'power/{name}/')}
+    compare_power_tables(t, want)
+
+
+def test_field_fft_and_deltak_binning(emu, golden):
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    name = next(n for n, c in cases.FIELD_CASES.items() if c['interlaced'] and c['compensated'])
+    c = cases.FIELD_CASES[name]
+    pos, w, _, _ = cases.power_inputs(c)
+    W = ps.get_W_compensated(c['L'], c['nmesh'], 'TSC', True)
+    f = ps.get_field_fft(pos, c['L'], c['nmesh'], 'TSC', w, W, True, True)
+    want = golden[f'field/{name}']
+    assert f.dtype == want.dtype and f.shape == want.shape
+    assert np.abs(f - want).max() <= 2e-5 * np.sqrt(np.mean(np.abs(want) ** 2))
+    name = next(iter(cases.DELTAK_CASES))
+    c = cases.DELTAK_CASES[name]
+    f1, f2, raw = cases.deltak_inputs(c)
+    kedges, muedges = cases.count_edges(c)
+    poles = np.asarray(c['poles'], dtype=np.int64)
+    P = ps.calc_pk_from_deltak(f1, c['L'], kedges, muedges, field2_fft=f2, poles=poles)
+    assert_int_exact(P['N_mode'], golden[f'deltak/{name}/N_mode'], 'N_mode')
+    np.testing.assert_allclose(P['power'], golden[f'deltak/{name}/power'], rtol=1e-4,
+                               atol=1e-5 * np.abs(golden[f'deltak/{name}/power']).max())
+
+
+def test_pk_to_xi(emu):
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    g = np.load(cases.__file__.replace('cases.py', 'reference_xi.npz'))
+    name = next(iter(cases.XI_CASES))
+    c = cases.XI_CASES[name]
+    Pk, r_bins = cases.xi_inputs(c)
+    r_binc, binned_poles, Npoles = ps.pk_to_xi(Pk.copy(), c['L'], r_bins, poles=c['poles'])
+    assert_int_exact(Npoles, g[f'xi/{name}/Npoles'], 'Npoles')
+    want = g[f'xi/{name}/binned_poles']
+    np.testing.assert_allclose(binned_poles, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+
+
+def test_partition_parallel(emu, golden):
+    from abacusutils_b200.analysis import tsc
+
+    name = next(iter(cases.PARTITION_CASES))
+    c = cases.PARTITION_CASES[name]
+    pos, w = cases.tsc_inputs(c)
+    ppart, starts, wpart = tsc.partition_parallel(pos, c['npartition'], c['box'], weights=w)
+    np.testing.assert_array_equal(starts, golden[f'partition/{name}/starts'])
+    ref = golden[f'partition/{name}/ppart']
+    for i in range(c['npartition']):                       # same multiset per stripe (the scatter order is free)
+        a, b = starts[i], starts[i + 1]
+        np.testing.assert_array_equal(np.sort(ppart[a:b].view('f4,f4,f4'), axis=0), np.sort(ref[a:b].view('f4,f4,f4'), axis=0))
+
+
+def test_ingest_through_the_product_wrappers(emu, oracle):
+    from abacusutils_b200.data import bitpacked, pack9
+
+    g = np.load(cases.__file__.replace('cases.py', 'ref_ingest.npz'))
+    pos, vel = pack9.unpack_pack9(g['pack9/in'][:5000], float(g['pack9/box']), float(g['pack9/velz']))
+    np.testing.assert_array_equal(pos, g['pack9/pos'][:len(pos)])
+    np.testing.assert_array_equal(vel, g['pack9/vel'][:len(vel)])
+    pos, vel = bitpacked.unpack_rvint(g['rvint/in'], float(g['rvint/box']))
+    np.testing.assert_array_equal(pos, g['rvint/pos'])
+    got = bitpacked.unpack_pids(g['pids/in'], box=float(g['pids/box']), ppd=float(g['pids/ppd']), pid=True, lagr_pos=True,
+                                density=True)
+    for k in got:
+        np.testing.assert_array_equal(got[k], g[f'pids/{k}'], err_msg=k)

@@ -1,6 +1,6 @@
 """
-The real kernel sources of libabk (abk_ctx.cu, abk_ingest.cu, abk_kfields.cu) executed on the CPU by the thread-per-
-CUDA-thread emulator of tests/emu (TEST INFRASTRUCTURE ONLY): the launch plumbing -- grid/block decomposition, block
+The real kernel sources of libabk executed through the raw C ABI on the CPU by the fiber-per-CUDA-thread emulator of
+tests/emu (TEST INFRASTRUCTURE ONLY): the launch plumbing -- grid/block decomposition, block
 scans, ballots, barriers, shared-memory staging, header look-ups, warp-aggregated reductions -- runs unmodified and is
 compared with the oracle and the reference's golden arrays.  This is how kernels written without GPU time are checked
 before they ever reach a B200; the `-m gpu` tests repeat the comparison on the device.
@@ -16,16 +16,15 @@ import pytest
 import cases
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / 'tests' / 'emu'))
 GOLD = ROOT / 'tests' / 'golden'
 vp = C.c_void_p
 
 
 @pytest.fixture(scope='module')
-def emu(tmp_path_factory):
+def emu(emu_build_dir):
     import build_emu
 
-    lib = C.CDLL(str(build_emu.build(tmp_path_factory.mktemp('abk_emu'))))
+    lib = C.CDLL(str(build_emu.build(emu_build_dir)))
     lib.abk_last_error.restype = C.c_char_p
     ctx = vp()
     assert lib.abk_ctx_create(0, C.byref(ctx)) == 0, lib.abk_last_error()
