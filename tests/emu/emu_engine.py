@@ -75,6 +75,34 @@ class EmuLib:
         _view(grid, np.float32, nx * ny * ldz).reshape(nx, ny, ldz)[:, :, :nz] = real
         return 0
 
+    def abk_fft_yz_plan_create(self, ctx, nplanes, ny, nz, plan_out, work_bytes_out):
+        h = len(self._plans) + 1
+        self._plans[h] = ('yz', int(nplanes), int(ny), int(nz))
+        plan_out._obj.value = h
+        work_bytes_out._obj.value = 256
+        return 0
+
+    def abk_fft_x_plan_create(self, ctx, nx, nrows, nzc, plan_out, work_bytes_out):
+        h = len(self._plans) + 1
+        self._plans[h] = ('x', int(nx), int(nrows), int(nzc))
+        plan_out._obj.value = h
+        work_bytes_out._obj.value = 256
+        return 0
+
+    def abk_fft_exec_generic(self, ctx, plan, data, work, work_bytes):
+        from scipy.fft import fft, rfft2
+
+        kind, a, b, c = self._shape(plan)
+        if kind == 'yz':      # 2-D R2C over (y, z) on a planes, in place, ldz = 2 (nz/2 + 1)
+            ldz = 2 * (c // 2 + 1)
+            real = _view(data, np.float32, a * b * ldz).reshape(a, b, ldz)
+            spec = rfft2(real[:, :, :c].astype(np.float32), axes=(1, 2)).astype(np.complex64)
+            _view(data, np.complex64, a * b * (c // 2 + 1)).reshape(a, b, c // 2 + 1)[...] = spec
+        else:                 # 1-D C2C along x of [x][row][nzc]
+            arr = _view(data, np.complex64, a * b * c).reshape(a, b, c)
+            arr[...] = fft(arr.copy(), axis=0).astype(np.complex64)
+        return 0
+
     def abk_fft_plan_destroy(self, plan):
         return 0
 
@@ -150,4 +178,5 @@ def install(monkeypatch, build_dir):
     monkeypatch.setattr(torch.cuda, 'Stream', lambda *a, **k: _NullStream())
     monkeypatch.setattr(torch.cuda, 'Event', _NullEvent)
     monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, 'current_device', lambda: 0)
     return eng
