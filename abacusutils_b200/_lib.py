@@ -55,6 +55,7 @@ SIGNATURES = {
     'abk_ctx_launch_count': (_i64, [_vp]),
     'abk_ctx_set_tile_capacity': (_i32, [_vp, _i32]),
     'abk_ctx_set_scheme': (_i32, [_vp, _i32]),
+    'abk_ctx_set_weight_scale': (_i32, [_vp, _dbl]),
     'abk_ctx_profile_enable': (_i32, [_vp, _i32]),
     'abk_ctx_profile_collect': (_i32, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     'abk_kernel_count': (_i32, []),
@@ -187,6 +188,10 @@ class Engine:
     def set_scheme(self, paste):
         """Select the mass-assignment scheme ('TSC' / 'CIC') of the following bucket / deposit calls."""
         check(self.lib.abk_ctx_set_scheme(self.ctx, 1 if str(paste).upper() == 'CIC' else 0))
+
+    def set_weight_scale(self, scale):
+        """Factor applied to every particle weight by the following bucket calls (1.0 = off)."""
+        check(self.lib.abk_ctx_set_weight_scale(self.ctx, float(scale)))
 
     def profile(self, on):
         check(self.lib.abk_ctx_profile_enable(self.ctx, int(bool(on))))

@@ -41,6 +41,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->tile_capacity = 0;
     c->scheme = 0;
     c->bin_no_sym = 0;
+    c->wscale = 1.0f;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -151,6 +152,14 @@ extern "C" int abk_ctx_set_scheme(abk_ctx *ctx, int scheme)
     ABK_REQUIRE(ctx != nullptr, "null context");
     ABK_REQUIRE(scheme == 0 || scheme == 1, "unknown mass-assignment scheme %d (0 = TSC, 1 = CIC)", scheme);
     ctx->scheme = scheme;
+    return ABK_OK;
+}
+
+extern "C" int abk_ctx_set_weight_scale(abk_ctx *ctx, double scale)
+{
+    ABK_REQUIRE(ctx != nullptr, "null context");
+    ABK_REQUIRE(scale == scale && scale != 0.0, "weight scale must be a non-zero number");
+    ctx->wscale = (float)scale;
     return ABK_OK;
 }
 

@@ -39,6 +39,8 @@ struct TscParams {
     int wrap;
     int cic;                       // 0: TSC (tsc.py), 1: CIC (cic.py:13-125)
     double gx_d, gy_d, gz_d;       // CIC works in double: p = (x / box) * g
+    float wscale;                  // multiplies every weight as the bucket records are written (1 unless the caller
+                                   // folds the field normalisation into the deposit, abk_ctx_set_weight_scale)
 };
 
 // tsc.py:219-226: one-shot wrap; compare against the double box, store float32
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
             for (int q = 0; q < 4; q++) slot[q] = ok[q] ? atomicSub(&counts[tile[q]], 1u) - 1u : 0u;
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (ok[q]) records[slot[q]] = make_float4(c[3 * q], c[3 * q + 1], c[3 * q + 2], wv[q]);
+                if (ok[q]) records[slot[q]] = make_float4(c[3 * q], c[3 * q + 1], c[3 * q + 2], wv[q] * P.wscale);
         }
     }
 }
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(256) tsc_naive_kernel(const float *__restrict_
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
         float x = pos[3 * n], y = pos[3 * n + 1], z = pos[3 * n + 2];
         if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
-        const float W = w ? w[n] : 1.0f;
+        const float W = (w ? w[n] : 1.0f) * P.wscale;
         int cx, cy, cz;
         float dx, dy, dz;
         cells_of(P, x, y, z, cx, cy, cz, dx, dy, dz);
@@ -890,6 +892,7 @@ int make_params(const abk_ctx *ctx, TscParams &P, int nx, int ny, int nz, double
     P.wrap = wrap;
     P.cic = ctx->scheme == 1;
     P.gx_d = nx; P.gy_d = ny; P.gz_d = nz;
+    P.wscale = ctx->wscale;
     return ABK_OK;
 }
 

@@ -379,9 +379,10 @@ def run_gpu_arm(args):
                    'l2': 'inputs (12 GB particles, 4.3 GB grids) are larger than the 126 MB L2'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'stages': stages,
-        'stages_note': ('per-kernel CUDA-event times; normalize_field/cufft of the first grid run on an auxiliary stream '
+        'stages_note': ('per-kernel CUDA-event times; the cufft of the first grid runs on an auxiliary stream '
                         'concurrently with the tile deposit of the second grid, so their event times include the time '
-                        'they share the SMs and the stage times add up to more than the step'),
+                        'they share the SMs and the stage times add up to more than the step; normalize_field is '
+                        'folded into the deposit (grid starts at -1, weights scaled by n^3/N)'),
         'config2_tsc': cfg2, 'mpart_per_s': N / ms / 1e3,
         'tsc_gpart_per_s': (2 * N / (dep_ms * 1e-3) / 1e9) if dep_ms else None,
         'N_mode_total': int(np.asarray(res['N_mode']).sum()),

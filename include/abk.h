@@ -68,6 +68,11 @@ const char *abk_kernel_name(int id);
  * 1 = CIC (analysis/cic.py:13-125 `cic_serial`: same 27-cell update with weights (max(d,0), 1-|d|, max(-d,0)),
  * cell index from p = ((pos + offset) / box) * g evaluated in double). */
 int abk_ctx_set_scheme(abk_ctx *ctx, int scheme);
+/* Every particle weight is multiplied by `scale` when bucket records are written (abk_tsc_bucket*, abk_tsc_deposit)
+ * and in abk_tsc_deposit_naive; default 1.  With scale = n^3 / N and a grid initialised to -1 the deposit itself
+ * produces the normalised field rho * n^3/N - 1 of `normalize_field` (power_spectrum.py:860-901): one read+write pass
+ * over the mesh less.  Records routed between GPUs (REC4 input) are scaled when they are re-bucketed, i.e. once. */
+int abk_ctx_set_weight_scale(abk_ctx *ctx, double scale);
 /* tuning knobs (0 = library default): tile-kernel particle capacity per pass */
 int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity);
 
