@@ -157,7 +157,8 @@ class _Painter:
             max_seg = max(1, min(max_seg, int(os.environ['ABK_DEVICE_SEGMENTS'])))
             chunk = -(-N // max_seg)
         else:
-            chunk = max(1 << 25, -(-N // max_seg))
+            # ABK_CHUNK_MIN: testing knob, lets small inputs exercise the multi-segment / early-deposit machinery
+            chunk = max(int(os.environ.get('ABK_CHUNK_MIN', 1 << 25)), -(-N // max_seg))
         chunk = min(max(chunk, 1), SEGMENT_MAX)
         return [(a, min(a + chunk, N)) for a in range(0, N, chunk)]
 
@@ -245,9 +246,16 @@ class _Painter:
                                                 float(offsets[o]), float(offsets[ob]), 0, 0, n))
             eng.bind_stream()
 
-        split = 0
+        # Early deposits (host input): segments [0, split) are deposited on the auxiliary stream while the remaining
+        # chunks are still arriving; `cuts` are the ends of the early groups.  Every group costs one full per-cell pass
+        # over the mesh, so one group is the default; ABK_EARLY_GROUPS (experiment knob) asks for more, smaller ones
+        # with a shorter tail.
+        split, cuts = 0, []
         if host and nseg >= 6:
-            split = nseg - max(3, -(-3 * nseg // 10))
+            groups = max(1, int(os.environ.get('ABK_EARLY_GROUPS', '1')))
+            tail = max(3, -(-3 * nseg // 10)) if groups == 1 else max(2, -(-(2 if groups == 2 else 1.5) * nseg // 10))
+            split = nseg - int(tail)
+            cuts = sorted({max(1, round(split * (j + 1) / groups)) for j in range(groups)})
         early_done = None
 
         if host:
@@ -290,12 +298,13 @@ class _Painter:
                                          scan_tmp.numel()))
             if host:
                 done[slot].record(compute)
-            if split and s == split - 1:
+            if (s + 1) in cuts:
+                lo = ([0] + cuts)[cuts.index(s + 1)]
                 ev = torch.cuda.Event()
                 ev.record(compute)
                 aux.wait_event(ev)
                 for o in range(len(offsets)):
-                    deposit(0, split, o, aux)
+                    deposit(lo, s + 1, o, aux)
                 early_done = torch.cuda.Event()
                 early_done.record(aux)
 

@@ -5,6 +5,7 @@
 Times device-resident (and with --host, pinned-host) calc_power at config 3 for every combination of
   ABK_FUSED_NORMALIZE   0 / 1    normalize_field folded into the deposit (default 1)
   ABK_DEVICE_SEGMENTS   - / 1 / 4 number of bucket segments for device-resident input (default: 14)
+  ABK_EARLY_GROUPS      1 / 2 / 3 early deposit groups while host chunks are still arriving (--host, default 1)
 and, with the best of those, the deposit kernel variants (abk_ctx_set_tile_capacity bits 16-18).
 Prints one line per configuration: CUDA-event ms per step (median of reps after 2 warm-ups) and the per-kernel stage times.
 """
@@ -75,8 +76,11 @@ for fused, segs in itertools.product(('1', '0'), (None, '1', '4')):
     if best is None or ms < best[0]:
         best = (ms, fused, segs)
     if host is not None and segs is None:
-        ms_h, stages, _ = measure(host)
-        print(f'host   fused_norm={fused}: {ms_h:.1f} ms   {stages}', flush=True)
+        for groups in ('1', '2', '3'):
+            os.environ['ABK_EARLY_GROUPS'] = groups
+            ms_h, stages, _ = measure(host)
+            print(f'host   fused_norm={fused} early_groups={groups}: {ms_h:.1f} ms   {stages}', flush=True)
+        os.environ.pop('ABK_EARLY_GROUPS', None)
 
 print(f'best: {best[0]:.1f} ms with fused_norm={best[1]} segments={best[2] or "default"}')
 if args.variants:

@@ -141,3 +141,23 @@ def test_ingest_through_the_product_wrappers(emu, oracle):
                                 density=True)
     for k in got:
         np.testing.assert_array_equal(got[k], g[f'pids/{k}'], err_msg=k)
+
+
+@pytest.mark.parametrize('groups', ['1', '2', '3'])
+def test_multi_segment_early_deposit_groups(emu, golden, monkeypatch, groups):
+    """Host input cut into 14 chunks (one bucket segment each) with 1-3 early deposit groups on the auxiliary
+    stream: the orchestration of abacusutils_b200.analysis.power_spectrum._Painter, result unchanged."""
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    monkeypatch.setenv('ABK_CHUNK_MIN', '64')
+    monkeypatch.setenv('ABK_EARLY_GROUPS', groups)
+    name = 'n32_ci'
+    c = cases.POWER_CASES[name]
+    pos, w, pos2, w2 = cases.power_inputs(c)
+    P = ps._Painter.__new__(ps._Painter)
+    assert len(P.chunk_plan(len(pos))) == 14
+    t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
+                      nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2,
+                      poles=c['poles'])
+    want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
+    compare_power_tables(t, want)
