@@ -269,3 +269,18 @@ def test_kfield_helpers(ps, name):
     want = g[f'kf/{name}/expand']
     assert got.dtype == want.dtype and got.shape == want.shape
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+
+
+def test_fused_normalisation_matches_separate_pass(ps, monkeypatch):
+    """normalize_field folded into the deposit (grid starts at -1, weights scaled by n^3/N; the default) against the
+    separate normalisation kernel (ABK_FUSED_NORMALIZE=0): same spectrum to float32 round-off, same mode counts."""
+    c = cases.POWER_CASES['n32_ci']
+    pos, w, _, _ = cases.power_inputs(c)
+    kw = dict(kbins=16, mubins=4, nmesh=32, poles=[0, 2, 4], w=w)
+    monkeypatch.setenv('ABK_FUSED_NORMALIZE', '1')
+    a = ps.calc_power(pos, c['L'], **kw)
+    monkeypatch.setenv('ABK_FUSED_NORMALIZE', '0')
+    b = ps.calc_power(pos, c['L'], **kw)
+    assert_int_exact(a['N_mode'], b['N_mode'])
+    np.testing.assert_allclose(a['power'], b['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(b['power'])).max())
+    np.testing.assert_allclose(a['poles'], b['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(b['poles'])).max())
