@@ -170,6 +170,11 @@ def install(monkeypatch, build_dir):
         def aux_stream(self):
             return _NullStream()
 
+        def to_device(self, arr, dtype=None):
+            # a host->device copy never aliases the caller's array; keep that property on the CPU
+            t = super().to_device(arr, dtype)
+            return t.clone() if isinstance(arr, torch.Tensor) or t.data_ptr() == np.asarray(arr).ctypes.data else t
+
     if 'engine' not in _STATE:
         _STATE['engine'] = EmuEngine()
     eng = _STATE['engine']
