@@ -218,9 +218,14 @@ class _Painter:
         ntiles = ntiles.value
         chunks = self.chunk_plan(N, host=(kind == 'host'))
         nseg = len(chunks)
+        # ABK_SCATTER=2 (experiment knob): two-level multisplit bucketing with coalesced record writes
+        two_level = os.environ.get('ABK_SCATTER', '1') == '2'
+        bucket_fn = lib.abk_tsc_bucket2 if two_level else lib.abk_tsc_bucket
         nb = C.c_size_t()
-        check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
-        scan_tmp = eng.scratch('bucket_scan', nb.value)
+        check((lib.abk_tsc_bucket2_scratch_bytes if two_level else lib.abk_tsc_bucket_scratch_bytes)(
+            chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
+        scan_buf = eng.scratch('bucket_scan', nb.value + 256)
+        scan_ptr = C.c_void_p((scan_buf.data_ptr() + 255) & ~255)
         starts_stride = (ntiles + 1 + 63) // 64 * 64
         host = kind == 'host'
         # Device-resident input: bucket ONCE (tile of the cell at the first offset); the deposit of the
@@ -293,9 +298,8 @@ class _Painter:
             for o in range(nbuck):
                 rec_ptr = records[o].data_ptr() + a * 16
                 st_ptr = starts[o].data_ptr() + s * starts_stride * 4
-                check(lib.abk_tsc_bucket(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]),
-                                         int(bool(wrap)), C.c_void_p(rec_ptr), C.c_void_p(st_ptr), ptr(scan_tmp),
-                                         scan_tmp.numel()))
+                check(bucket_fn(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]), int(bool(wrap)),
+                                C.c_void_p(rec_ptr), C.c_void_p(st_ptr), scan_ptr, nb.value))
             if host:
                 done[slot].record(compute)
             if (s + 1) in cuts:

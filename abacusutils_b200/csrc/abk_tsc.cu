@@ -1057,6 +1057,232 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
     return ABK_OK;
 }
 
+// ==============================================================================================
+// Two-level bucketing (experiment, abk_tsc_bucket2): same result layout as abk_tsc_bucket (records grouped by
+// tile, tile_starts exclusive), but the 16-byte records reach memory in coalesced runs instead of one scattered
+// store per particle -- the classic scatter is bound by the rate of scattered store requests, not by bandwidth.
+//   level 1: tile id >> shift  (<= 1024 coarse buckets, each a contiguous range of tiles)
+//   level 2: tile id within the coarse bucket (<= 1024 tiles)
+// Each level is a CTA-local multisplit of a 4096-record chunk: rank inside (chunk, bucket) with one shared-memory
+// atomic per record, one global cursor reservation per (chunk, non-empty bucket), records staged in shared memory
+// in bucket order and written out as runs of consecutive addresses.
+namespace {
+
+constexpr int SPLIT_CH = 4096, SPLIT_NT = 256, SPLIT_IT = SPLIT_CH / SPLIT_NT, SPLIT_MAXB = 1024;
+
+struct SplitSmem {
+    float4 stage[SPLIT_CH];
+    uint16_t skey[SPLIT_CH];
+    uint32_t cnt[SPLIT_MAXB], off[SPLIT_MAXB], gbase[SPLIT_MAXB];
+    uint32_t warp_tot[SPLIT_NT / 32];
+};
+
+// One chunk: `rec[it]`/`key[it]` are this thread's items (item it of thread t is chunk element it*256 + t, valid if
+// below m).  cursors[key] hands out positions in `out`.
+__device__ __forceinline__ void multisplit_chunk(SplitSmem &S, const float4 (&rec)[SPLIT_IT], const int (&key)[SPLIT_IT], int m,
+                                                 int nb, uint32_t *__restrict__ cursors, float4 *__restrict__ out)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int b = tid; b < nb; b += SPLIT_NT) S.cnt[b] = 0;
+    __syncthreads();
+    uint32_t rank[SPLIT_IT];
+#pragma unroll
+    for (int it = 0; it < SPLIT_IT; it++)
+        if (it * SPLIT_NT + tid < m) rank[it] = atomicAdd(&S.cnt[key[it]], 1u);
+    __syncthreads();
+    // exclusive scan of cnt[0..nb) (4 buckets per thread), and the global reservation of every non-empty bucket
+    uint32_t c[4], run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int b = tid * 4 + q;
+        c[q] = b < nb ? S.cnt[b] : 0u;
+        run += c[q];
+    }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) S.warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t base = inc - run;
+    for (int w = 0; w < wid; w++) base += S.warp_tot[w];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int b = tid * 4 + q;
+        if (b < nb) {
+            S.off[b] = base;
+            if (c[q]) S.gbase[b] = atomicAdd(&cursors[b], c[q]);
+            base += c[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < SPLIT_IT; it++)
+        if (it * SPLIT_NT + tid < m) {
+            const uint32_t slot = S.off[key[it]] + rank[it];
+            S.stage[slot] = rec[it];
+            S.skey[slot] = (uint16_t)key[it];
+        }
+    __syncthreads();
+    for (int i = tid; i < m; i += SPLIT_NT) {
+        const int b = S.skey[i];
+        out[S.gbase[b] + ((uint32_t)i - S.off[b])] = S.stage[i];
+    }
+    __syncthreads();
+}
+
+// level 1: particles (pos/w) -> temp records grouped by coarse bucket
+__global__ void __launch_bounds__(SPLIT_NT, 2)
+split_coarse_kernel(const float *__restrict__ pos, const float *__restrict__ w, int64_t N, TscParams P, int shift, int nb,
+                    uint32_t *__restrict__ cursors, float4 *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char split_raw[];
+    SplitSmem &S = *reinterpret_cast<SplitSmem *>(split_raw);
+    const int64_t nchunks = (N + SPLIT_CH - 1) / SPLIT_CH;
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t base = ch * SPLIT_CH;
+        const int m = (int)min((int64_t)SPLIT_CH, N - base);
+        float4 rec[SPLIT_IT];
+        int key[SPLIT_IT];
+#pragma unroll
+        for (int it = 0; it < SPLIT_IT; it++) {
+            const int e = it * SPLIT_NT + threadIdx.x;
+            key[it] = 0;
+            if (e < m) {
+                const int64_t i = base + e;
+                float x = __ldcs(pos + 3 * i), y = __ldcs(pos + 3 * i + 1), z = __ldcs(pos + 3 * i + 2);
+                if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
+                uint32_t tile = 0;
+                tile_of(P, x, y, z, tile);
+                rec[it] = make_float4(x, y, z, (w ? __ldcs(w + i) : 1.0f) * P.wscale);
+                key[it] = (int)(tile >> shift);
+            }
+        }
+        multisplit_chunk(S, rec, key, m, nb, cursors, out);
+    }
+}
+
+// level 2: every coarse bucket (a contiguous record range of `tmp`) is refined by `splits` CTAs; keys are tile ids
+// relative to the bucket's first tile, cursors are the global per-tile cursors
+__global__ void __launch_bounds__(SPLIT_NT, 2)
+split_fine_kernel(const float4 *__restrict__ tmp, const uint32_t *__restrict__ tile_starts, int64_t ntiles, TscParams P, int shift,
+                  int splits, uint32_t *__restrict__ cursors, float4 *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char split_raw[];
+    SplitSmem &S = *reinterpret_cast<SplitSmem *>(split_raw);
+    const int cb = blockIdx.x / splits, part = blockIdx.x % splits;
+    const int64_t t0 = (int64_t)cb << shift;
+    const int64_t t1 = min(t0 + ((int64_t)1 << shift), ntiles);
+    const int nb = (int)(t1 - t0);
+    const int64_t r0 = tile_starts[t0], r1 = tile_starts[t1];
+    const int64_t nchunks = (r1 - r0 + SPLIT_CH - 1) / SPLIT_CH;
+    for (int64_t ch = part; ch < nchunks; ch += splits) {
+        const int64_t base = r0 + ch * SPLIT_CH;
+        const int m = (int)min((int64_t)SPLIT_CH, r1 - base);
+        float4 rec[SPLIT_IT];
+        int key[SPLIT_IT];
+#pragma unroll
+        for (int it = 0; it < SPLIT_IT; it++) {
+            const int e = it * SPLIT_NT + threadIdx.x;
+            key[it] = 0;
+            if (e < m) {
+                rec[it] = __ldcs(tmp + base + e);
+                uint32_t tile = 0;
+                tile_of(P, rec[it].x, rec[it].y, rec[it].z, tile);
+                key[it] = (int)((int64_t)tile - t0);
+            }
+        }
+        multisplit_chunk(S, rec, key, m, nb, cursors + t0, out);
+    }
+}
+
+// incl[t] (inclusive scan of the tile histogram) -> starts[t] exclusive with starts[ntiles] = total, a second copy as the
+// per-tile cursors, and the coarse cursors coarse[c] = starts[c << shift]
+__global__ void __launch_bounds__(256) split_starts_kernel(const uint32_t *__restrict__ incl, int64_t ntiles, int shift,
+                                                           uint32_t *__restrict__ starts, uint32_t *__restrict__ cur_fine,
+                                                           uint32_t *__restrict__ cur_coarse)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = t ? incl[t - 1] : 0u;
+        starts[t] = v;
+        if (t < ntiles) {
+            cur_fine[t] = v;
+            if ((t & (((int64_t)1 << shift) - 1)) == 0) cur_coarse[t >> shift] = v;
+        }
+    }
+}
+
+int split_shift(int64_t ntiles)
+{
+    int bits = 0;
+    while (((int64_t)1 << bits) < ntiles) bits++;
+    return (bits + 1) / 2;
+}
+
+}  // namespace
+
+extern "C" int abk_tsc_bucket2_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes)
+{
+    ABK_REQUIRE(bytes && nx > 0 && ny > 0 && nz > 0 && N >= 0, "abk_tsc_bucket2_scratch_bytes: bad arguments");
+    const int64_t ntiles = abk_make_geom(nx, ny, nz).ntiles;
+    *bytes = abk_align_up(abk_scan_tmp_bytes(ntiles) + 256, 256) + 2 * abk_align_up((size_t)(ntiles + 1) * 4, 256) +
+             abk_align_up((size_t)SPLIT_MAXB * 4, 256) + abk_align_up((size_t)(N > 0 ? N : 1) * 16, 256);
+    return ABK_OK;
+}
+
+extern "C" int abk_tsc_bucket2(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz, double box,
+                               double offset, int wrap, void *records, uint32_t *tile_starts, void *scratch,
+                               size_t scratch_bytes)
+{
+    ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket2: null argument");
+    TscParams P;
+    int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, 0, nx);
+    if (rc) return rc;
+    const abk_tile_geom g = abk_make_geom(nx, ny, nz);
+    const int shift = split_shift(g.ntiles);
+    const int64_t ncoarse = (g.ntiles + ((int64_t)1 << shift) - 1) >> shift;
+    // meshes with more than 2^20 tiles would need a third level: use the one-level scatter there
+    if (N == 0 || ((int64_t)1 << shift) > SPLIT_MAXB || ncoarse > SPLIT_MAXB)
+        return bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
+    ABK_REQUIRE(N <= ((int64_t)1 << 30), "a bucket segment holds at most 2^30 particles (got %lld)", (long long)N);
+    size_t need = 0;
+    abk_tsc_bucket2_scratch_bytes(N, nx, ny, nz, &need);
+    if (scratch_bytes < need || ((uintptr_t)scratch & 255)) {
+        abk_set_error("abk_tsc_bucket2: scratch %zu < %zu or not 256-byte aligned", scratch_bytes, need);
+        return ABK_ERR_SCRATCH;
+    }
+    char *sp = (char *)scratch;
+    void *scan_tmp = sp;                   sp += abk_align_up(abk_scan_tmp_bytes(g.ntiles) + 256, 256);
+    uint32_t *incl = (uint32_t *)sp;       sp += abk_align_up((size_t)(g.ntiles + 1) * 4, 256);
+    uint32_t *cur_fine = (uint32_t *)sp;   sp += abk_align_up((size_t)(g.ntiles + 1) * 4, 256);
+    uint32_t *cur_coarse = (uint32_t *)sp; sp += abk_align_up((size_t)SPLIT_MAXB * 4, 256);
+    float4 *tmp = (float4 *)sp;
+
+    ABK_CHECK_CUDA(cudaMemsetAsync(incl, 0, (size_t)(g.ntiles + 1) * 4, ctx->stream));
+    const int vec_ok = (((uintptr_t)pos & 15) == 0) && (!w || ((uintptr_t)w & 15) == 0);
+    const int hblocks = grid_for(ctx, (N + 3) / 4, 256, 16);
+    ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false, false><<<hblocks, 256, 0, ctx->stream>>>(
+                                           pos, w, N, P, incl, nullptr, vec_ok, ctx->d_scalars + 1));
+    rc = abk_inclusive_scan_u32(ctx, incl, g.ntiles, scan_tmp);
+    if (rc) return rc;
+    ABK_LAUNCH(ctx, ABK_K_MISC, split_starts_kernel<<<grid_for(ctx, g.ntiles + 1, 256, 8), 256, 0, ctx->stream>>>(
+                                    incl, g.ntiles, shift, tile_starts, cur_fine, cur_coarse));
+    const size_t smem = sizeof(SplitSmem);
+    ABK_CHECK_CUDA(cudaFuncSetAttribute(split_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ABK_CHECK_CUDA(cudaFuncSetAttribute(split_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t nchunks = (N + SPLIT_CH - 1) / SPLIT_CH;
+    const int64_t cap = (int64_t)ctx->num_sms * 2;
+    ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, split_coarse_kernel<<<(unsigned)(nchunks < cap ? nchunks : cap), SPLIT_NT, smem, ctx->stream>>>(
+                                              pos, w, N, P, shift, (int)ncoarse, cur_coarse, tmp));
+    int splits = (int)((cap * 4 + ncoarse - 1) / ncoarse);
+    if (splits < 1) splits = 1;
+    ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, split_fine_kernel<<<(unsigned)(ncoarse * splits), SPLIT_NT, smem, ctx->stream>>>(
+                                              tmp, tile_starts, g.ntiles, P, shift, splits, cur_fine, (float4 *)records));
+    return ABK_OK;
+}
+
 // kernel variant (PRE, PRIV): abk_ctx_set_tile_capacity's bits 16..18 select it for experiments
 
 static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int ext, int per_sm)

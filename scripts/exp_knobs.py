@@ -5,6 +5,7 @@
 Times device-resident (and with --host, pinned-host) calc_power at config 3 for every combination of
   ABK_FUSED_NORMALIZE   0 / 1    normalize_field folded into the deposit (default 1)
   ABK_DEVICE_SEGMENTS   - / 1 / 4 number of bucket segments for device-resident input (default: 14)
+  ABK_SCATTER           1 / 2     one-level scattered stores vs two-level multisplit with coalesced runs (default 1)
   ABK_EARLY_GROUPS      1 / 2 / 3 early deposit groups while host chunks are still arriving (--host, default 1)
 and, with the best of those, the deposit kernel variants (abk_ctx_set_tile_capacity bits 16-18).
 Prints one line per configuration: CUDA-event ms per step (median of reps after 2 warm-ups) and the per-kernel stage times.
@@ -64,27 +65,29 @@ def measure(src):
 
 
 best = None
-for fused, segs in itertools.product(('1', '0'), (None, '1', '4')):
+for fused, segs, scatter in itertools.product(('1', '0'), (None, '1', '4'), ('1', '2')):
     os.environ['ABK_FUSED_NORMALIZE'] = fused
+    os.environ['ABK_SCATTER'] = scatter
     if segs is None:
         os.environ.pop('ABK_DEVICE_SEGMENTS', None)
     else:
         os.environ['ABK_DEVICE_SEGMENTS'] = segs
     eng.release_scratch()
     ms, stages, p5 = measure(pos)
-    print(f'device fused_norm={fused} segments={segs or "default"}: {ms:.1f} ms   P[5,0]={p5:.6g}   {stages}', flush=True)
+    print(f'device fused_norm={fused} segments={segs or "default"} scatter={scatter}: {ms:.1f} ms   P[5,0]={p5:.6g}   {stages}', flush=True)
     if best is None or ms < best[0]:
-        best = (ms, fused, segs)
-    if host is not None and segs is None:
+        best = (ms, fused, segs, scatter)
+    if host is not None and segs is None and scatter == '1':
         for groups in ('1', '2', '3'):
             os.environ['ABK_EARLY_GROUPS'] = groups
             ms_h, stages, _ = measure(host)
             print(f'host   fused_norm={fused} early_groups={groups}: {ms_h:.1f} ms   {stages}', flush=True)
         os.environ.pop('ABK_EARLY_GROUPS', None)
 
-print(f'best: {best[0]:.1f} ms with fused_norm={best[1]} segments={best[2] or "default"}')
+print(f'best: {best[0]:.1f} ms with fused_norm={best[1]} segments={best[2] or "default"} scatter={best[3]}')
 if args.variants:
     os.environ['ABK_FUSED_NORMALIZE'] = best[1]
+    os.environ['ABK_SCATTER'] = best[3]
     if best[2]:
         os.environ['ABK_DEVICE_SEGMENTS'] = best[2]
     for variant in (0, 1, 2, 3):
