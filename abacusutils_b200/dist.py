@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
+import os
 import time
 
 import numpy as np
@@ -297,9 +298,14 @@ class DistEngine:
             nchunk = int(t.item())
         if nchunk * self.world > 16:
             raise NotImplementedError(f'{nchunk} local chunks x {self.world} ranks exceed the 16 bucket segments of the tile kernel')
+        # ABK_SCATTER=2 (experiment knob): two-level multisplit bucketing, as in the single-GPU painter
+        two_level = os.environ.get('ABK_SCATTER', '1') == '2'
+        bucket_fn = lib.abk_tsc_bucket2 if two_level else lib.abk_tsc_bucket
         nb = C.c_size_t()
-        check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, CH), 1), n, n, n, C.byref(nb)))
-        scan_tmp = eng.scratch('bucket_scan', nb.value)
+        check((lib.abk_tsc_bucket2_scratch_bytes if two_level else lib.abk_tsc_bucket_scratch_bytes)(
+            max(min(N, CH), 1), n, n, n, C.byref(nb)))
+        scan_buf = eng.scratch('bucket_scan', nb.value + 256)
+        scan_ptr = C.c_void_p((scan_buf.data_ptr() + 255) & ~255)
         wrap = 0 if str(paste).upper() == 'CIC' else 1
         segs, keep, total = [], [], 0
         for c in range(nchunk):
@@ -311,9 +317,8 @@ class DistEngine:
             else:  # send-side buffers are dead after the exchange: plain tensors, returned to the allocator
                 rec = torch.empty(max(m, 1) * 16, dtype=torch.uint8, device=self.device)
                 starts = torch.empty(ntiles + 1, dtype=torch.int32, device=self.device)
-            check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
-                                     m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), ptr(scan_tmp),
-                                     scan_tmp.numel()))
+            check(bucket_fn(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
+                            m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), scan_ptr, nb.value))
             rows = rec[: m * 16].view(torch.float32).view(m, 4)
             if self.world == 1:
                 segs.append((rows.data_ptr(), starts.data_ptr(), m))

@@ -26,8 +26,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, build_dir, name, out_dir, force_reroute):
+def _worker(rank, world, port, build_dir, name, out_dir, force_reroute, scatter):
     os.environ['OMP_NUM_THREADS'] = '1'
+    os.environ['ABK_SCATTER'] = scatter
     os.environ['ABK_NO_P2P'] = '1'          # NVLink peer memory does not exist here: pack + all-to-all path
     for p in (ROOT, ROOT / 'tests', ROOT / 'tests' / 'golden', ROOT / 'tests' / 'emu'):
         sys.path.insert(0, str(p))
@@ -53,13 +54,14 @@ def _worker(rank, world, port, build_dir, name, out_dir, force_reroute):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,name,force_reroute', [(2, 'n32_ci', False), (3, 'n48_log', False), (2, 'n32_cross_ci', True)])
-def test_dist_calc_power_on_emulator(tmp_path, emu_build_dir, golden, world, name, force_reroute):
+@pytest.mark.parametrize('world,name,force_reroute,scatter', [(2, 'n32_ci', False, '1'), (3, 'n48_log', False, '1'),
+                                                             (2, 'n32_cross_ci', True, '1'), (2, 'n32_ci', False, '2')])
+def test_dist_calc_power_on_emulator(tmp_path, emu_build_dir, golden, world, name, force_reroute, scatter):
     import build_emu
     from common import compare_power_tables
 
     build_emu.build(emu_build_dir)          # once, before the ranks start
-    mp.spawn(_worker, args=(world, _free_port(), str(emu_build_dir), name, str(tmp_path), force_reroute), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(emu_build_dir), name, str(tmp_path), force_reroute, scatter), nprocs=world, join=True)
     got = dict(np.load(tmp_path / 'table.npz'))
     want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
     compare_power_tables(got, want)
