@@ -42,6 +42,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->scheme = 0;
     c->bin_no_sym = 0;
     c->wscale = 1.0f;
+    c->flush_v2 = 0;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -170,6 +171,7 @@ extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
     ABK_REQUIRE(cap == 0 || (cap >= 256 && cap <= 12288), "tile capacity %d out of range", cap);
     ctx->tile_capacity = capacity & 0x7ffff;
     ctx->bin_no_sym = (capacity >> 19) & 1;  // bit 19: disable the mirror-symmetric binning kernel (experiments)
+    ctx->flush_v2 = (capacity >> 20) & 1;    // bit 20: vector reductions in the tile flush (experiments)
     return ABK_OK;
 }
 

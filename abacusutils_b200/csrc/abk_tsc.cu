@@ -39,6 +39,7 @@ struct TscParams {
     int wrap;
     int cic;                       // 0: TSC (tsc.py), 1: CIC (cic.py:13-125)
     double gx_d, gy_d, gz_d;       // CIC works in double: p = (x / box) * g
+    int flush_v2;                  // experiment: flush tile rows with 8-byte vector reductions (red.global.add.v2.f32)
     float wscale;                  // multiplies every weight as the bucket records are written (1 unless the caller
                                    // folds the field normalisation into the deposit, abk_ctx_set_weight_scale)
 };
@@ -256,6 +257,17 @@ __device__ __forceinline__ void mas_w(float d, float &wm, float &w0, float &wp)
 {
     if (CIC) cic_w(d, wm, w0, wp);
     else tsc_w(d, wm, w0, wp);
+}
+
+// two adjacent floats in one 8-byte reduction (sm_90+); p must be 8-byte aligned
+__device__ __forceinline__ void red_add_v2(float *p, float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+#else
+    atomicAdd(p, a);
+    atomicAdd(p + 1, b);
+#endif
 }
 
 // Add one finished x-plane of this lane's register window to the output.
@@ -503,6 +515,8 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     // one instruction hit 32 consecutive floats.  Everything that does not depend on the plane (row
     // pointers of the <= 3 contributing slabs, wrapped y/z indices) is hoisted.
     const int64_t sx = (int64_t)P.ny * ldz;
+    // vector flush needs the whole 32-cell row inside the mesh (no z wrap inside it) and 8-byte aligned pairs
+    const bool pair_ok = !PRIV && P.flush_v2 && z0 + ABK_TZ <= P.nz && (ldz & 1) == 0 && (((uintptr_t)grid) & 7) == 0;
     const int gz = abk_wrap_cell(z0 + lane, P.nz);
     const int ozh = lane ? D::OZ - 1 : 0;
     const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
@@ -527,8 +541,21 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
                 if (lane < 2) vh = r[ozh];
             }
             float *dst = grid + gx * sx + (int64_t)gy * ldz;
-            if (v != 0.0f) atomicAdd(dst + gz, v);
-            if (lane < 2 && vh != 0.0f) atomicAdd(dst + gzh, vh);
+            if (pair_ok) {
+                // lanes 0..15 take the 32 interior cells two at a time, lanes 16/17 the two z-halo cells
+                const float *r = outbuf + (ox * D::OY + oy) * D::OZ;
+                if (lane < 16) {
+                    const float a = r[2 * lane + 1], b = r[2 * lane + 2];
+                    if (a != 0.0f || b != 0.0f) red_add_v2(dst + z0 + 2 * lane, a, b);
+                } else if (lane < 18) {
+                    const int oz = (lane == 16) ? 0 : D::OZ - 1;
+                    const float h = r[oz];
+                    if (h != 0.0f) atomicAdd(dst + abk_wrap_cell(z0 + oz - 1, P.nz), h);
+                }
+            } else {
+                if (v != 0.0f) atomicAdd(dst + gz, v);
+                if (lane < 2 && vh != 0.0f) atomicAdd(dst + gzh, vh);
+            }
             gx++;
             if (!slab && gx >= P.nx) gx -= P.nx;
         }
@@ -893,6 +920,7 @@ int make_params(const abk_ctx *ctx, TscParams &P, int nx, int ny, int nz, double
     P.cic = ctx->scheme == 1;
     P.gx_d = nx; P.gy_d = ny; P.gz_d = nz;
     P.wscale = ctx->wscale;
+    P.flush_v2 = ctx->flush_v2;
     return ABK_OK;
 }
 

@@ -94,4 +94,7 @@ if args.variants:
         check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, variant << 16))
         ms, stages, _ = measure(pos)
         print(f'deposit variant {variant}: {ms:.1f} ms   {stages}', flush=True)
+    check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, 1 << 20))
+    ms, stages, _ = measure(pos)
+    print(f'deposit variant 0 + vector flush (bit 20): {ms:.1f} ms   {stages}', flush=True)
     check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, 0))

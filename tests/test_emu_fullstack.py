@@ -209,3 +209,31 @@ def test_two_level_bucketing_matches_one_level(emu):
         a = np.sort(r1[s1[t]:s1[t + 1]].view('f4,f4,f4,f4'), axis=0)
         b = np.sort(r2[s2[t]:s2[t + 1]].view('f4,f4,f4,f4'), axis=0)
         np.testing.assert_array_equal(a, b)
+
+
+def test_vector_flush_variant(emu, golden, oracle):
+    """abk_ctx_set_tile_capacity bit 20: tile rows flushed with two-cell vector reductions.  Rows that wrap in z, odd
+    row strides and unaligned grids must take the scalar path; results unchanged either way."""
+    from abacusutils_b200._lib import check
+    from abacusutils_b200.analysis import power_spectrum as ps
+    from abacusutils_b200.analysis import tsc
+
+    try:
+        check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 1 << 20))
+        for name in ('n32_ci', 'n48_log'):                 # padded FFT grids: ldz even, 32 | n or not
+            c = cases.POWER_CASES[name]
+            pos, w, pos2, w2 = cases.power_inputs(c)
+            t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
+                              nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2,
+                              w2=w2, poles=c['poles'])
+            want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
+            compare_power_tables(t, want)
+        rng = np.random.default_rng(4)
+        for shape in ((16, 16, 64), (9, 11, 33), (8, 8, 32), (12, 10, 70)):   # even / odd strides, partial last z tile
+            pos = (rng.random((3000, 3), dtype=np.float32) * np.float32(80.0)).astype(np.float32)
+            got, want = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+            tsc.tsc_parallel(pos.copy(), got, 80.0, offset=0.3)
+            oracle.tsc_parallel(pos.copy(), want, 80.0, offset=0.3, nthread=1)
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, err_msg=str(shape))
+    finally:
+        check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
