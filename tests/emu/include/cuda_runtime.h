@@ -4,7 +4,9 @@
 // __shfl_*_sync, __match_any_sync, ...) exchange through a per-warp buffer between two warp barriers, atomics are plain
 // read-modify-writes, __shared__ variables are function-local statics (blocks run one after the other).  A thread that
 // returns no longer counts for any barrier, as on the GPU; a barrier that can never complete (reached by only part of
-// its threads) is reported as a deadlock instead of hanging.
+// its threads) is reported as a deadlock instead of hanging.  ABK_EMU_SHUFFLE=<seed> randomises the order in which the
+// fibers of a block are resumed, so code that silently relies on lane/warp execution order (a missing barrier) shows up
+// as a wrong result.
 // Kernel launches `k<<<grid, block, smem, stream>>>(args)` are rewritten to `emu::launch(grid, block, smem, stream)(k)(args)`
 // by tests/emu/build_emu.py.  Only what libabk's ctx / ingest / kfields sources use is provided.
 #pragma once
@@ -121,6 +123,11 @@ inline void run(const Cfg &c, const std::function<void()> &body)
     for (int t = 0; t < n; t++) blk.fibers[t].stack = pool[t];
     blk.warps.resize((n + 31) / 32);
     g_block = &blk;
+    static const char *shuffle_env = std::getenv("ABK_EMU_SHUFFLE");
+    const bool shuffle = shuffle_env != nullptr && shuffle_env[0] != 0;
+    static unsigned long long rng = shuffle ? std::strtoull(shuffle_env, nullptr, 10) * 2654435761ull + 1 : 1;
+    std::vector<int> order(n);
+    for (int t = 0; t < n; t++) order[t] = t;
     for (unsigned bz = 0; bz < c.g.z; bz++)
         for (unsigned by = 0; by < c.g.y; by++)
             for (unsigned bx = 0; bx < c.g.x; bx++) {
@@ -144,7 +151,14 @@ inline void run(const Cfg &c, const std::function<void()> &body)
                 }
                 while (blk.live > 0) {
                     bool progressed = false;
-                    for (int t = 0; t < n; t++) {
+                    if (shuffle) {   // ABK_EMU_SHUFFLE: visit the fibers in a fresh random order every round (race hunting)
+                        for (int t = n - 1; t > 0; t--) {
+                            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                            std::swap(order[t], order[(rng >> 33) % (unsigned)(t + 1)]);
+                        }
+                    }
+                    for (int q = 0; q < n; q++) {
+                        const int t = order[q];
                         Fiber &f = blk.fibers[t];
                         if (f.wait != RUNNABLE) continue;
                         g_cur = &f;
