@@ -8,6 +8,7 @@ block's dynamic shared memory.  Lets the `not gpu` suite execute the real launch
 barriers, header look-ups) of kernels, bit for bit, in a container without a GPU.
 """
 
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -42,7 +43,10 @@ def build(outdir):
         dst.write_text(translate((CSRC / s).read_text()))
         cpps.append(str(dst))
     gxx = '/usr/bin/g++' if Path('/usr/bin/g++').exists() else 'g++'
-    cmd = [gxx, '-std=c++20', '-O1', '-g', '-pthread', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-attributes', '-D__CUDACC__',
+    # ABK_EMU_ASAN=1: AddressSanitizer build (out-of-bounds global / shared accesses of every kernel); run the tests with
+    #   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
+    asan = ['-fsanitize=address', '-fno-omit-frame-pointer'] if os.environ.get('ABK_EMU_ASAN') == '1' else []
+    cmd = [gxx, '-std=c++20', '-O1', '-g', *asan, '-pthread', '-fPIC', '-shared', '-ffp-contract=off', '-Wno-attributes', '-D__CUDACC__',
            f'-I{HERE / "include"}', f'-I{CSRC}', f'-I{ROOT / "include"}', '-o', str(so), *cpps]
     subprocess.run(cmd, check=True)
     return so
