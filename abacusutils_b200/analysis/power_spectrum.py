@@ -28,6 +28,7 @@ import numpy as np
 
 from .._lib import (ABK_MAX_POLES, ABK_MAX_SEGMENTS, ABK_POLE_NCOEF, SEGMENT_MAX, AbkError, BinRequest, Engine, KMesh,
                     check, is_torch_tensor, ptr)
+from ..data.packed import PackedParticles
 from .tsc import padded_ldz, tsc_parallel
 
 __all__ = ['calc_power', 'calc_pk_from_deltak', 'pk_to_xi', 'project_3d_to_poles', 'get_k_mu_edges']
@@ -177,8 +178,14 @@ class _Painter:
         eng.set_scheme(self.paste)
         if self.paste == 'CIC':
             wrap = False
-        kind, psrc = _as_source(pos, np.float32)
-        N = int(psrc.shape[0])
+        packed = pos if isinstance(pos, PackedParticles) else None
+        if packed is not None:
+            if w is not None:
+                raise ValueError('packed particle records carry no weights')
+            kind, psrc, N = 'host', None, len(packed)      # N: records, an upper bound of the particle count
+        else:
+            kind, psrc = _as_source(pos, np.float32)
+            N = int(psrc.shape[0])
         wsrc = None
         if w is not None:
             wkind, wsrc = _as_source(w, np.float32)
@@ -192,23 +199,25 @@ class _Painter:
         # normalize_field (rho * n^3/N - 1, power_spectrum.py:860-901) folded into the deposit: the grid starts at -1
         # and every weight is scaled by n^3/N as the bucket records are written -- one read+write pass less per grid
         fused_norm = fft_weight is not None and os.environ.get('ABK_FUSED_NORMALIZE', '1') != '0'
+        if packed is not None and packed.n_particles is None:
+            fused_norm = False      # pack9: the particle count is only known once the last chunk has been decoded
         if fused_norm:
             grids = [eng.empty((n, n, ldz), torch.float32).fill_(-1.0) for _ in offsets]
             eng.set_weight_scale(float(np.float32(float(n) ** 3 / float(fft_weight))))
         else:
             grids = [eng.zeros((n, n, ldz), torch.float32) for _ in offsets]
         try:
-            return self._paint(psrc, wsrc, kind, N, offsets, wrap, tag, fft_weight, fused_norm, grids, compute)
+            return self._paint(psrc, wsrc, kind, N, offsets, wrap, tag, fft_weight, fused_norm, grids, compute, packed)
         finally:
             if fused_norm:
                 eng.set_weight_scale(1.0)
 
-    def _paint(self, psrc, wsrc, kind, N, offsets, wrap, tag, fft_weight, fused_norm, grids, compute):
+    def _paint(self, psrc, wsrc, kind, N, offsets, wrap, tag, fft_weight, fused_norm, grids, compute, packed=None):
         import torch
 
         eng, n, ldz = self.eng, self.n, self.ldz
         lib = eng.lib
-        if psrc.dtype != torch.float32:
+        if psrc is not None and psrc.dtype != torch.float32:
             psrc = psrc.to(torch.float32)
         if wsrc is not None and wsrc.dtype != torch.float32:
             wsrc = wsrc.to(torch.float32)
@@ -216,8 +225,12 @@ class _Painter:
         ntiles = C.c_int64()
         check(lib.abk_tsc_num_tiles(n, n, n, C.byref(ntiles)))
         ntiles = ntiles.value
-        chunks = self.chunk_plan(N, host=(kind == 'host'))
+        if packed is not None:
+            chunks = packed.chunk_plan(ABK_MAX_SEGMENTS - 2, int(os.environ.get('ABK_CHUNK_MIN', 1 << 25)))
+        else:
+            chunks = self.chunk_plan(N, host=(kind == 'host'))
         nseg = len(chunks)
+        counts = [b - a for a, b in chunks]      # particles per segment (packed input: filled in as chunks are decoded)
         # ABK_SCATTER=2 (experiment knob): two-level multisplit bucketing with coalesced record writes
         two_level = os.environ.get('ABK_SCATTER', '1') == '2'
         bucket_fn = lib.abk_tsc_bucket2 if two_level else lib.abk_tsc_bucket
@@ -244,7 +257,7 @@ class _Painter:
             m = hi - lo
             recs = (C.c_void_p * m)(*[records[ob].data_ptr() + chunks[s][0] * 16 for s in range(lo, hi)])
             sts = (C.c_void_p * m)(*[starts[ob].data_ptr() + s * starts_stride * 4 for s in range(lo, hi)])
-            cnts = (C.c_int64 * m)(*[chunks[s][1] - chunks[s][0] for s in range(lo, hi)])
+            cnts = (C.c_int64 * m)(*[counts[s] for s in range(lo, hi)])
             with torch.cuda.stream(stream):
                 eng.bind_stream()
                 check(lib.abk_tsc_deposit_tiles(eng.ctx, m, recs, sts, cnts, ptr(grids[o]), n, n, n, ldz, self.L,
@@ -270,6 +283,7 @@ class _Painter:
             # the SMs with the early tile deposits
             NSTAGE = 4
             stage_p = [eng.scratch(f'stage_p{i}', csize * 12) for i in range(NSTAGE)]
+            stage_raw = [eng.scratch(f'stage_raw{i}', csize * packed.rec_bytes) for i in range(NSTAGE)] if packed is not None else None
             stage_w = [eng.scratch(f'stage_w{i}', csize * 4) for i in range(NSTAGE)] if wsrc is not None else None
             ready = [torch.cuda.Event() for _ in range(NSTAGE)]
             done = [torch.cuda.Event() for _ in range(NSTAGE)]
@@ -282,14 +296,23 @@ class _Painter:
                 slot = s % NSTAGE
                 copy_stream.wait_event(done[slot])
                 with torch.cuda.stream(copy_stream):
-                    pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
-                    pd.copy_(psrc[a:b], non_blocking=True)
                     wd = None
-                    if wsrc is not None:
-                        wd = stage_w[slot][: m * 4].view(torch.float32)
-                        wd.copy_(wsrc[a:b], non_blocking=True)
+                    if packed is not None:
+                        raw_d = stage_raw[slot][: m * packed.rec_bytes]
+                        raw_d.copy_(packed.raw(a, b), non_blocking=True)
+                    else:
+                        pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
+                        pd.copy_(psrc[a:b], non_blocking=True)
+                        if wsrc is not None:
+                            wd = stage_w[slot][: m * 4].view(torch.float32)
+                            wd.copy_(wsrc[a:b], non_blocking=True)
                     ready[slot].record(copy_stream)
                 compute.wait_event(ready[slot])
+                if packed is not None:      # decode on the device; m becomes the number of PARTICLES of this chunk
+                    pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
+                    m = packed.decode(eng, raw_d, m, pd)
+                    counts[s] = m
+                    pd = pd[:m]
             else:
                 pd = psrc[a:b]
                 wd = None if wsrc is None else wsrc[a:b]
@@ -312,6 +335,12 @@ class _Painter:
                 early_done = torch.cuda.Event()
                 early_done.record(aux)
 
+        if packed is not None:
+            packed.n_particles = int(sum(counts))
+            if fft_weight is not None:
+                fft_weight = packed.n_particles      # normalise by the particles actually decoded
+                if fft_weight == 0:
+                    raise ValueError('cannot normalise an empty particle set')
         # ---- remaining deposits; FFT of grid o overlaps the deposit of grid o+1 ----------------------------
         fft_prev = None
         for o in range(len(offsets)):
@@ -678,6 +707,10 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
 
     g1 = _field_fft_device(eng, pos, Lbox, n, w, interlaced, tag='a', paste=paste_u)
     g2 = _field_fft_device(eng, pos2, Lbox, n, w2, interlaced, tag='a', paste=paste_u) if pos2 is not None else None
+    if isinstance(pos, PackedParticles):      # pack9: the particle count is known once the records are decoded
+        meta['N_pos'] = pos.n_particles
+    if isinstance(pos2, PackedParticles):
+        meta['N_pos2'] = pos2.n_particles
 
     poles_arr = np.asarray(poles or [], dtype=np.int64)
     kbins, mubins = get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)

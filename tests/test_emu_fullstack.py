@@ -237,3 +237,35 @@ def test_vector_flush_variant(emu, golden, oracle):
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, err_msg=str(shape))
     finally:
         check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
+
+
+@pytest.mark.parametrize('kind', ['pack9', 'rvint'])
+def test_calc_power_from_packed_records(emu, oracle, monkeypatch, kind):
+    """calc_power(PackedParticles(...)): records cross to the device packed, are decoded there chunk by chunk (pack9
+    chunks cut at cell headers) and painted; same table as decoding on the host first."""
+    from abacusutils_b200.analysis import power_spectrum as ps
+    from abacusutils_b200.data.packed import PackedParticles
+
+    monkeypatch.setenv('ABK_CHUNK_MIN', '700')          # ~14 chunks
+    L = 1000.0
+    if kind == 'pack9':
+        raw = cases.pack9_inputs(77, 9000, hdr_frac=0.03, cpd=405)
+        pos, _ = oracle.unpack_pack9(raw, L, 1.0)
+        src = PackedParticles(raw, L, velzspace_to_kms=1.0)
+        assert len(src) == 9000 and src.n_particles is None
+        plan = src.chunk_plan(14, 700)
+        assert plan[0][0] == 0 and plan[-1][1] == 9000 and all(raw[a, 0] == 0xFF for a, _ in plan)
+    else:
+        rng = np.random.default_rng(78)
+        raw = ((rng.integers(-500000, 500000, size=(8000, 3)).astype(np.int32) << 12) | rng.integers(0, 4096, size=(8000, 3)).astype(np.int32))
+        pos, _ = oracle.unpack_rvint(raw, L)
+        src = PackedParticles(raw, L)
+    kw = dict(kbins=12, mubins=3, nmesh=24, poles=[0, 2, 4])
+    got = ps.calc_power(src, L, **kw)
+    want = ps.calc_power(pos.copy(), L, **kw)
+    assert got.meta['N_pos'] == len(pos) == src.n_particles
+    assert_int_exact(got['N_mode'], want['N_mode'], 'N_mode')
+    np.testing.assert_allclose(got['power'], want['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(want['power'])).max())
+    np.testing.assert_allclose(got['poles'], want['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(want['poles'])).max())
+    with pytest.raises(ValueError):
+        ps.calc_power(src, L, w=np.ones(len(src), np.float32), **kw)
