@@ -234,6 +234,49 @@ def make_positions(torch, N, L, seed, clustered=0.0, chunk=50_000_000):
     return pos
 
 
+def packed_leg(torch, calc_power, N, L, kw, args):
+    """Optional extra (--packed pack9|rvint): the same calc_power fed with synthetic PACKED records in pinned host memory
+    (9 or 12 bytes per particle over PCIe, decoded on the GPU inside the painter).  Not the headline metric: the input
+    format differs from the reference benchmark's float32 positions."""
+    from abacusutils_b200.data.packed import PackedParticles
+
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(11)
+    if args.packed == 'rvint':
+        raw = (torch.randint(-500000, 500000, (N, 3), device='cuda', dtype=torch.int32, generator=gen) << 12) | \
+            torch.randint(0, 4096, (N, 3), device='cuda', dtype=torch.int32, generator=gen)
+        nbytes = 12
+    else:
+        # one cell header every 32 records: cpd 1000 -> fields 1..5 = (cpd, vscale, i, j, k) + 2048 in 12 bits each
+        raw = torch.randint(0, 255, (N, 9), device='cuda', dtype=torch.uint8, generator=gen)   # first byte never 0xFF
+        h = torch.arange(0, N, 32, device='cuda')
+        f = torch.stack([torch.zeros_like(h), torch.full_like(h, 1000 - 2000 + 2048), torch.full_like(h, 2048)] +
+                        [torch.randint(-2000 + 2048, 1000 - 2000 + 2048, h.shape, device='cuda', generator=gen) for _ in range(3)], 1)
+        hb = torch.empty((len(h), 9), dtype=torch.uint8, device='cuda')
+        for q in range(3):
+            a, b = f[:, 2 * q], f[:, 2 * q + 1]
+            hb[:, 3 * q] = (a >> 4) & 0xFF
+            hb[:, 3 * q + 1] = ((a & 0xF) | (((b >> 8) & 0xF) << 4)).to(torch.uint8)
+            hb[:, 3 * q + 2] = (b & 0xFF).to(torch.uint8)
+        hb[:, 0] = 0xFF
+        raw[h] = hb
+        nbytes = 9
+    host = torch.empty(raw.shape, dtype=raw.dtype, pin_memory=True)
+    host.copy_(raw)
+    torch.cuda.synchronize()
+    del raw
+    src = PackedParticles(host, L, kind=args.packed, velzspace_to_kms=1.0)
+    calc_power(src, L, **kw)
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = calc_power(src, L, **kw)
+    torch.cuda.synchronize()
+    return {'value': (time.perf_counter() - t0) / steps * 1e3, 'unit': 'ms', 'format': args.packed,
+            'h2d_bytes_per_step': int(N * nbytes), 'n_particles': int(res.meta['N_pos']), 'steps': steps}
+
+
 def run_gpu_arm(args):
     import torch
 
@@ -370,6 +413,9 @@ def run_gpu_arm(args):
 
     dep_ms = sum(stages[k]['ms_per_step'] for k in ('tsc_bucket_hist', 'tsc_bucket_scatter', 'scan', 'tsc_tile_deposit')
                  if k in stages)
+    packed_e2e = None
+    if args.packed:
+        packed_e2e = packed_leg(torch, calc_power, N, L, kw, args)
     line = {
         'metric': METRIC, 'value': ms, 'unit': 'ms', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
@@ -383,7 +429,7 @@ def run_gpu_arm(args):
                         'concurrently with the tile deposit of the second grid, so their event times include the time '
                         'they share the SMs and the stage times add up to more than the step; normalize_field is '
                         'folded into the deposit (grid starts at -1, weights scaled by n^3/N)'),
-        'config2_tsc': cfg2, 'mpart_per_s': N / ms / 1e3,
+        'config2_tsc': cfg2, 'mpart_per_s': N / ms / 1e3, 'e2e_packed': packed_e2e,
         'tsc_gpart_per_s': (2 * N / (dep_ms * 1e-3) / 1e9) if dep_ms else None,
         'N_mode_total': int(np.asarray(res['N_mode']).sum()),
     }
@@ -401,6 +447,8 @@ def main():
     ap.add_argument('--nmesh', type=int, default=0, help='override nmesh (testing only)')
     ap.add_argument('--clustered', type=float, default=0.0,
                     help='fraction of the particles placed in Gaussian blobs (testing only; the headline is uniform)')
+    ap.add_argument('--packed', choices=['pack9', 'rvint'], default=None,
+                    help='extra leg: end-to-end from packed records in pinned host memory (not the headline metric)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs only)')
     args = ap.parse_args()

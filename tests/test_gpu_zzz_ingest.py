@@ -165,3 +165,28 @@ def test_read_asdf_to_device(tmp_path, oracle):
     np.testing.assert_array_equal(t['aux'], g['pids/in'])
     for k in PID_KEYS:
         np.testing.assert_array_equal(t[k], g[f'pids/{k}'], err_msg=k)
+
+
+@pytest.mark.parametrize('kind', ['pack9', 'rvint'])
+def test_calc_power_from_packed_records(oracle, kind, monkeypatch):
+    """calc_power(PackedParticles(...)): packed records over PCIe, decoded on the device inside the painter pipeline."""
+    from abacusutils_b200.analysis import power_spectrum as ps
+    from abacusutils_b200.data.packed import PackedParticles
+
+    monkeypatch.setenv('ABK_CHUNK_MIN', '20000')        # several chunks, early deposit group included
+    L = 1000.0
+    if kind == 'pack9':
+        raw = cases.pack9_inputs(77, 300000, hdr_frac=0.03, cpd=405)
+        pos, _ = oracle.unpack_pack9(raw, L, 1.0)
+        src = PackedParticles(raw, L, velzspace_to_kms=1.0)
+    else:
+        rng = np.random.default_rng(78)
+        raw = ((rng.integers(-500000, 500000, size=(250000, 3)).astype(np.int32) << 12) | rng.integers(0, 4096, size=(250000, 3)).astype(np.int32))
+        pos, _ = oracle.unpack_rvint(raw, L)
+        src = PackedParticles(raw, L)
+    kw = dict(kbins=24, mubins=4, nmesh=64, poles=[0, 2, 4])
+    got = ps.calc_power(src, L, **kw)
+    want = ps.calc_power(pos.copy(), L, **kw)
+    assert got.meta['N_pos'] == len(pos) == src.n_particles
+    np.testing.assert_array_equal(np.asarray(got['N_mode']), np.asarray(want['N_mode']))
+    np.testing.assert_allclose(got['power'], want['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(want['power'])).max())
