@@ -70,7 +70,7 @@ def read_asdf(fn, load=None, colname=None, dtype=np.float32, verbose=True, devic
     def on_device(a):
         import torch
 
-        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        return torch.from_numpy(np.array(a, order='C')).cuda()      # a copy: the block buffer is read-only
 
     columns = {}
     want_pos, want_vel = 'pos' in load, 'vel' in load
