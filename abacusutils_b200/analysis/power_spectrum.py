@@ -290,25 +290,41 @@ class _Painter:
             for ev in done:
                 ev.record(compute)
 
+        staged = {}
+
+        def issue_copy(si):
+            """Enqueue the host->device copy of chunk si on the copy stream (waits, in stream order, for its staging slot)."""
+            a_, b_ = chunks[si]
+            m_, sl = b_ - a_, si % NSTAGE
+            copy_stream.wait_event(done[sl])
+            with torch.cuda.stream(copy_stream):
+                wd_ = None
+                if packed is not None:
+                    pd_ = stage_raw[sl][: m_ * packed.rec_bytes]
+                    pd_.copy_(packed.raw(a_, b_), non_blocking=True)
+                else:
+                    pd_ = stage_p[sl][: m_ * 12].view(torch.float32).view(m_, 3)
+                    pd_.copy_(psrc[a_:b_], non_blocking=True)
+                    if wsrc is not None:
+                        wd_ = stage_w[sl][: m_ * 4].view(torch.float32)
+                        wd_.copy_(wsrc[a_:b_], non_blocking=True)
+                ready[sl].record(copy_stream)
+            staged[si] = (pd_, wd_)
+
+        issued = 0
         for s, (a, b) in enumerate(chunks):
             m = b - a
             if host:
                 slot = s % NSTAGE
-                copy_stream.wait_event(done[slot])
-                with torch.cuda.stream(copy_stream):
-                    wd = None
-                    if packed is not None:
-                        raw_d = stage_raw[slot][: m * packed.rec_bytes]
-                        raw_d.copy_(packed.raw(a, b), non_blocking=True)
-                    else:
-                        pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
-                        pd.copy_(psrc[a:b], non_blocking=True)
-                        if wsrc is not None:
-                            wd = stage_w[slot][: m * 4].view(torch.float32)
-                            wd.copy_(wsrc[a:b], non_blocking=True)
-                    ready[slot].record(copy_stream)
+                # packed input: the header count of chunk s blocks the host, so chunk s+1 is put on the wire first
+                ahead = 1 if (packed is not None and NSTAGE > 1) else 0
+                while issued <= min(s + ahead, nseg - 1):
+                    issue_copy(issued)
+                    issued += 1
+                pd, wd = staged.pop(s)
                 compute.wait_event(ready[slot])
                 if packed is not None:      # decode on the device; m becomes the number of PARTICLES of this chunk
+                    raw_d = pd
                     pd = stage_p[slot][: m * 12].view(torch.float32).view(m, 3)
                     m = packed.decode(eng, raw_d, m, pd)
                     counts[s] = m
