@@ -42,6 +42,7 @@ struct abk_ctx {
     int tile_capacity;  // 0 = auto
     int scheme;         // mass-assignment scheme of the deposit entry points: 0 TSC, 1 CIC
     int bin_no_sym;     // experiments: force the one-mode-at-a-time binning kernel
+    int no_minb3;       // experiments: never use the 80-register build of the default deposit kernel (tile-capacity bit 21)
     int flush_v2;       // experiments: 8-byte vector reductions in the tile flush (abk_ctx_set_tile_capacity bit 20)
     float wscale;       // factor applied to every particle weight when records are written (abk_ctx_set_weight_scale)
     // small device scratch owned by the context (work counters, flags)

@@ -43,6 +43,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->bin_no_sym = 0;
     c->wscale = 1.0f;
     c->flush_v2 = 0;
+    c->no_minb3 = 0;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -172,6 +173,7 @@ extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
     ctx->tile_capacity = capacity & 0x7ffff;
     ctx->bin_no_sym = (capacity >> 19) & 1;  // bit 19: disable the mirror-symmetric binning kernel (experiments)
     ctx->flush_v2 = (capacity >> 20) & 1;    // bit 20: vector reductions in the tile flush (experiments)
+    ctx->no_minb3 = (capacity >> 21) & 1;    // bit 21: keep the 64-register deposit kernel even at 3 CTAs/SM (experiments)
     return ABK_OK;
 }
 

@@ -331,8 +331,11 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
     }
 }
 
-template <bool PRE, bool PRIV, int EXT, bool CIC>
-__global__ void __launch_bounds__(TileDom<EXT>::NT, PRE ? 2 : ((PRIV || EXT) ? 3 : 4))
+// MINB (0 = by variant): minimum resident CTAs per SM the register allocation must allow.  The default kernel is built
+// twice: for 4 CTAs/SM (64 registers, 60 bytes of spills) and for 3 (80 registers, no spills); the launch picks the
+// second whenever shared memory limits the SM to three CTAs anyway (e.g. ~1 particle per cell, one pass per tile).
+template <bool PRE, bool PRIV, int EXT, bool CIC, int MINB = 0>
+__global__ void __launch_bounds__(TileDom<EXT>::NT, MINB ? MINB : (PRE ? 2 : ((PRIV || EXT) ? 3 : 4)))
 tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
 {
     using D = TileDom<EXT>;
@@ -1401,6 +1404,9 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     const size_t smem = deposit_smem_bytes(cap, pre, priv, ext);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
     deposit_kernel_t kern = pick_kernel(pre, priv, ext, cic);
+    // resident CTAs per SM allowed by shared memory (1 KB per CTA is reserved by the driver)
+    const int occ_smem = (int)((size_t)(ctx->smem_optin + 1024) / (smem + 1024));
+    if (!pre && !priv && !ext && !cic && occ_smem <= 3 && !ctx->no_minb3) kern = tsc_tile_deposit_kernel<false, false, 0, false, 3>;
     const int threads = ext ? TileDom<1>::NT : TileDom<0>::NT;
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, threads, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));

@@ -97,4 +97,7 @@ if args.variants:
     check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, 1 << 20))
     ms, stages, _ = measure(pos)
     print(f'deposit variant 0 + vector flush (bit 20): {ms:.1f} ms   {stages}', flush=True)
+    check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, 1 << 21))
+    ms, stages, _ = measure(pos)
+    print(f'deposit variant 0, 64-register build forced (bit 21): {ms:.1f} ms   {stages}', flush=True)
     check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, 0))
