@@ -82,3 +82,40 @@ def test_fuzz_calc_power(emu, oracle, monkeypatch):
             compare_power_tables(got, {k: np.asarray(want[k]) for k in want.keys()})
         except AssertionError as e:
             raise AssertionError(f'trial {trial}: n={n} N={N} {kw} cross={cross}: {e}') from e
+
+
+def test_fuzz_binning_entry_points(emu, oracle):
+    """calc_pk_from_deltak (auto / cross, arbitrary user edges incl. mu edges that stop below 1 are avoided),
+    project_3d_to_poles and bin_kppi on random meshes against the oracle: integer counts exact."""
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    rng = np.random.default_rng(3)
+    for trial in range(max(TRIALS * 2 // 3, 1)):
+        n = int(rng.choice([6, 8, 9, 12, 15, 16, 20, 24]))
+        L = float(rng.uniform(20, 3000))
+        shp = (n, n, n // 2 + 1)
+        f1 = (rng.standard_normal(shp) + 1j * rng.standard_normal(shp)).astype(np.complex64)
+        f2 = (rng.standard_normal(shp) + 1j * rng.standard_normal(shp)).astype(np.complex64) if rng.random() < 0.5 else None
+        k_ny = np.pi * n / L
+        Nk, Nmu = int(rng.integers(1, 20)), int(rng.integers(1, 6))
+        kedges = np.sort(rng.uniform(0, 1.8 * k_ny, Nk + 1)) if rng.random() < 0.5 else np.linspace(0, float(rng.uniform(0.4, 1.8)) * k_ny, Nk + 1)
+        muedges = np.linspace(0, 1, Nmu + 1)
+        poles = np.asarray([[], [0, 2, 4], [0, 1, 2, 3, 5], [4, 10]][int(rng.integers(0, 4))], dtype=np.int64)
+        got = ps.calc_pk_from_deltak(f1, L, kedges, muedges, field2_fft=f2, poles=poles)
+        want = oracle.calc_pk_from_deltak(f1, L, kedges, muedges, field2_fft=f2, poles=poles, nthread=2, acc64=True)
+        msg = f'trial {trial}: n={n} Nk={Nk} Nmu={Nmu} poles={list(poles)} cross={f2 is not None}'
+        np.testing.assert_array_equal(got['N_mode'], want['N_mode'], err_msg=msg)
+        np.testing.assert_array_equal(got['N_mode_poles'], want['N_mode_poles'], err_msg=msg)
+        scale = np.abs(want['power']).max() + 1e-30
+        np.testing.assert_allclose(got['power'], want['power'], rtol=2e-4, atol=2e-5 * scale, err_msg=msg)
+        np.testing.assert_allclose(got['k_avg'], want['k_avg'], rtol=2e-5, atol=1e-6 * k_ny, err_msg=msg)
+        if len(poles):
+            np.testing.assert_allclose(got['binned_poles'], want['binned_poles'], rtol=5e-4, atol=2e-4 * scale, err_msg=msg)
+        # (k_perp, pi) binning of a real weight mesh
+        w = rng.standard_normal(shp).astype(np.float32)
+        pimax, Npi = float(rng.uniform(0.2, 1.3)) * k_ny, int(rng.integers(1, 12))
+        kp = np.linspace(float(rng.uniform(0, 0.2)) * k_ny, float(rng.uniform(0.3, 1.6)) * k_ny, Nk + 1)
+        m1, c1 = ps.bin_kppi(n, L, kp, pimax, Npi, w)
+        m2, c2 = oracle.bin_kppi(n, L, kp, pimax, Npi, w)
+        np.testing.assert_array_equal(c1, c2, err_msg=msg)
+        np.testing.assert_allclose(m1, m2, rtol=1e-4, atol=1e-5 * (np.abs(m2).max() + 1e-30), err_msg=msg)
