@@ -44,10 +44,26 @@ def power_scale(table_like, key_power='power', key_nmode='N_mode'):
     return m
 
 
-def compare_power_tables(got, want, rtol=RTOL, skip_dc=True):
-    """Compare two calc_power results (dict-like with the reference's column names)."""
+def legendre_conditioning(ell):
+    """(2l+1) * sum_k |c_k| of P_l written as a polynomial in mu: how much float32 round-off of the reference's power-sum
+    evaluation (power_spectrum.py:121-147) is amplified.  76 for l=4, 22911 for l=10."""
+    from math import comb
+
+    ell = int(ell)
+    return (2 * ell + 1) * sum(comb(ell, k) * comb(2 * ell - 2 * k, ell) for k in range(ell // 2 + 1)) / 2.0**ell
+
+
+def compare_power_tables(got, want, rtol=RTOL, skip_dc=True, poles=None, amp=None):
+    """Compare two calc_power results (dict-like with the reference's column names).
+
+    ``poles`` (optional): the multipole orders of the ``poles`` columns.  High orders are evaluated by the reference
+    in float32 as an alternating power sum, whose own round-off grows with the conditioning of the polynomial (measured:
+    for l=10 the reference-style evaluation is 2.4e-4 of the monopole away from the exact float64 value, the GPU's Horner
+    evaluation 4e-5); the absolute tolerance of a column grows accordingly.
+    ``amp`` (optional): per-k-bin amplitude that sets the absolute tolerance instead of |power| itself -- needed for
+    cross-spectra of independent catalogues, whose value is a near-zero residual of sqrt(P11 P22)."""
     assert_int_exact(got['N_mode'], want['N_mode'], 'N_mode')
-    scale = power_scale(want)
+    scale = power_scale(want) if amp is None else np.maximum(power_scale(want), np.asarray(amp, dtype=np.float64))
     # a global floor: the smallest meaningful amplitude is ~1e-6 of the typical power (f32 noise)
     floor = 1e-2 * np.median(scale[scale > 0]) if (scale > 0).any() else 0.0
     pw, pg = np.asarray(want['power'], 'f8'), np.asarray(got['power'], 'f8')
@@ -67,5 +83,8 @@ def compare_power_tables(got, want, rtol=RTOL, skip_dc=True):
     if 'poles' in want:
         assert_int_exact(got['N_mode_poles'], want['N_mode_poles'], 'N_mode_poles')
         wp, gp = np.asarray(want['poles'], 'f8')[sl], np.asarray(got['poles'], 'f8')[sl]
-        scp = (scale[sl] + floor)[:, None] * 11.0  # (2l+1) <= 11 for l <= 5; generous for higher l
+        scp = (scale[sl] + floor)[:, None] * 11.0  # (2l+1) <= 11 for l <= 5
+        if poles is not None and len(poles) == gp.shape[1]:
+            # float32 eps * conditioning, relative to the 1e-4 * 1.1 baseline; only matters from l = 8 on
+            scp = scp * np.maximum(1.0, np.array([legendre_conditioning(l) for l in poles]) * 1.2e-3 / 11.0)[None, :]
         assert_close_scaled(gp, wp, scale=scp * 0.1, rtol=rtol, what='poles')
