@@ -101,6 +101,50 @@ def get_W_compensated(Lbox, nmesh, paste, interlaced):
     return W
 
 
+# ---------------------------------------------------------------------------------------------
+# small scalar helpers of the reference module (host side; the kernels evaluate the same polynomials on the device)
+def factorial(n):
+    """n! for 0 <= n <= 20 (power_spectrum.py:58-77)."""
+    if n > 20 or n < 0:
+        raise ValueError
+    return np.int64(math.factorial(int(n)))
+
+
+def factorial_slow(x):
+    """n! by repeated multiplication (power_spectrum.py:80-98)."""
+    return math.factorial(int(x)) if x >= 0 else 1
+
+
+def n_choose_k(n, k):
+    """Binomial coefficient (power_spectrum.py:101-119)."""
+    return factorial(n) // (factorial(k) * factorial(n - k))
+
+
+def P_n(x, n, dtype=np.float32):
+    """Legendre polynomial of order ``n`` for the SQUARED argument ``x = mu^2`` (power_spectrum.py:122-147), evaluated
+    like the reference: an alternating power sum in ``dtype``; valid up to n = 10."""
+    dtype = np.dtype(dtype).type
+    x = dtype(x)
+    total = dtype(0.0)
+    for k in range(n // 2 + 1):
+        factor = dtype(int(n_choose_k(n, k)) * int(n_choose_k(2 * n - 2 * k, n)))
+        term = factor * x ** dtype(0.5 * (n - 2 * k))
+        total = dtype(total + term) if k % 2 == 0 else dtype(total - term)
+    return dtype(total * dtype(0.5**n))
+
+
+def linear_interp(xd, x, y):
+    """Linear interpolation on an equidistant grid, clamped to ``y[0]`` / ``y[-1]`` outside (power_spectrum.py:509-536)."""
+    if xd <= x[0]:
+        return y[0]
+    elif xd >= x[-1]:
+        return y[-1]
+    dx = x[1] - x[0]
+    f = (xd - x[0]) / dx
+    fl = np.int64(f)
+    return y[fl] + (f - fl) * (y[fl + 1] - y[fl])
+
+
 def legendre_coefficients(poles):
     """(2l+1) P_l(mu) as polynomial coefficients in mu (degree <= 10), float32[Np][11].
 

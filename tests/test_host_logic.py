@@ -163,3 +163,20 @@ def test_bin_kppi_wrapper_marshalling(monkeypatch):
         assert mean.dtype == want.dtype and cnt.dtype == np.int64
         np.testing.assert_array_equal(cnt, g[f'kppi/{name}/counts'], err_msg=name)
         np.testing.assert_allclose(mean, want, rtol=1e-5, atol=2e-6, err_msg=name)
+
+
+def test_scalar_helpers_match_reference(golden):
+    """factorial / n_choose_k / P_n / linear_interp (power_spectrum.py:58-147, 509-536) against the reference's P_n table."""
+    import cases
+    from abacusutils_b200.analysis import power_spectrum as ps
+
+    assert ps.factorial(0) == 1 and ps.factorial(20) == 2432902008176640000 and ps.factorial_slow(5) == 120
+    with pytest.raises(ValueError):
+        ps.factorial(21)
+    assert ps.n_choose_k(10, 3) == 120 and ps.n_choose_k(20, 10) == 184756
+    for ell in range(0, 11):
+        got = np.array([ps.P_n(np.float32(x), ell) for x in cases.PN_X], dtype=np.float32)
+        np.testing.assert_allclose(got, golden[f'P_n/{ell}'], rtol=2e-5, atol=2e-5 * max(1.0, np.abs(golden[f'P_n/{ell}']).max()))
+    x, y = np.linspace(1.0, 3.0, 5), np.array([0.0, 1.0, 4.0, 9.0, 16.0])
+    assert ps.linear_interp(0.5, x, y) == 0.0 and ps.linear_interp(3.5, x, y) == 16.0
+    assert np.isclose(ps.linear_interp(1.75, x, y), 2.5)
