@@ -52,7 +52,7 @@ def padded_ldz(nz):
     return 2 * (nz // 2 + 1)
 
 
-def deposit_device(eng, pos_d, w_d, grid_d, shape, ldz, box, offset, wrap):
+def deposit_device(eng, pos_d, w_d, grid_d, shape, ldz, box, offset, wrap, scheme='TSC'):
     """Bucket + deposit device-resident particles into a device grid (accumulating)."""
     import torch
 
@@ -65,7 +65,7 @@ def deposit_device(eng, pos_d, w_d, grid_d, shape, ldz, box, offset, wrap):
     check(lib.abk_tsc_deposit_scratch_bytes(N, nx, ny, nz, C.byref(nb)))
     scratch = eng.scratch('deposit', nb.value)
     eng.bind_stream()
-    eng.set_scheme('TSC')
+    eng.set_scheme(scheme)
     assert pos_d.dtype == torch.float32 and pos_d.is_contiguous()
     check(lib.abk_tsc_deposit(eng.ctx, ptr(pos_d), ptr(w_d), N, ptr(grid_d), nx, ny, nz, ldz, float(box),
                               float(offset), int(bool(wrap)), ptr(scratch), scratch.numel()))

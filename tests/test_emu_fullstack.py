@@ -269,3 +269,19 @@ def test_calc_power_from_packed_records(emu, oracle, monkeypatch, kind):
     np.testing.assert_allclose(got['poles'], want['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(want['poles'])).max())
     with pytest.raises(ValueError):
         ps.calc_power(src, L, w=np.ones(len(src), np.float32), **kw)
+
+
+def test_cic_serial(emu):
+    """abacusutils_b200.analysis.cic.cic_serial against get_field(paste='CIC') of the unmodified reference."""
+    from abacusutils_b200.analysis.cic import cic_serial
+
+    g = np.load(cases.__file__.replace('cases.py', 'reference_cic.npz'))
+    for name, c in cases.CIC_FIELD_CASES.items():
+        if c['d'] != 0.0:
+            continue
+        pos, w = cases.cic_field_inputs(c)
+        n = c['nmesh']
+        dens = np.zeros((n, n, n), dtype=np.float32)
+        assert cic_serial(pos, dens, c['L'], weights=w) is None
+        field = dens * np.float32(n**3 / len(pos)) - 1       # get_field normalises by len(pos) (power_spectrum.py:856)
+        np.testing.assert_allclose(field, g[f'field/{name}'], rtol=1e-4, atol=1e-5)
