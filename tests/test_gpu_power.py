@@ -284,3 +284,18 @@ def test_fused_normalisation_matches_separate_pass(ps, monkeypatch):
     assert_int_exact(a['N_mode'], b['N_mode'])
     np.testing.assert_allclose(a['power'], b['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(b['power'])).max())
     np.testing.assert_allclose(a['poles'], b['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(b['poles'])).max())
+
+
+def test_cic_serial_drop_in():
+    """abacusutils_b200.analysis.cic.cic_serial (cic.py:13-125) against the reference's CIC field."""
+    from abacusutils_b200.analysis.cic import cic_serial
+
+    g = np.load(cases.__file__.replace('cases.py', 'reference_cic.npz'))
+    name = 'cicf24'
+    c = cases.CIC_FIELD_CASES[name]
+    pos, w = cases.cic_field_inputs(c)
+    n = c['nmesh']
+    dens = np.full((n, n, n), 2.0, dtype=np.float32)                   # accumulates into the caller's grid
+    assert cic_serial(pos, dens, c['L'], weights=w) is None
+    field = (dens - 2.0) * np.float32(n**3 / len(pos)) - 1
+    np.testing.assert_allclose(field, g[f'field/{name}'], rtol=1e-4, atol=2e-5)
