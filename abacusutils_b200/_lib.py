@@ -9,6 +9,7 @@ There is no CPU fallback: if the library or a CUDA device is missing, calls rais
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 
@@ -167,6 +168,9 @@ class Engine:
         self.ctx = h
         self._plans = {}
         self._bufs = {}
+        knob = os.environ.get('ABK_TILE_KNOBS')      # experiments: raw argument of abk_ctx_set_tile_capacity
+        if knob:
+            check(self.lib.abk_ctx_set_tile_capacity(self.ctx, int(knob, 0)))
 
     # -- stream / memory plumbing ---------------------------------------------------------------
     def bind_stream(self):

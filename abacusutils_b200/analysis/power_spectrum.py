@@ -243,8 +243,15 @@ class _Painter:
         # normalize_field (rho * n^3/N - 1, power_spectrum.py:860-901) folded into the deposit: the grid starts at -1
         # and every weight is scaled by n^3/N as the bucket records are written -- one read+write pass less per grid
         fused_norm = fft_weight is not None and os.environ.get('ABK_FUSED_NORMALIZE', '1') != '0'
-        if packed is not None and packed.n_particles is None:
-            fused_norm = False      # pack9: the particle count is only known once the last chunk has been decoded
+        if packed is not None:
+            if packed.n_particles is None:
+                fused_norm = False      # pack9: the particle count is only known once the last chunk has been decoded
+            elif fft_weight is not None:
+                # len(packed) counts RECORDS (pack9: cell headers included); the field is normalised by the
+                # number of particles, known from an earlier decode of the same object
+                fft_weight = packed.n_particles
+                if fft_weight == 0:
+                    raise ValueError('cannot normalise an empty particle set')
         if fused_norm:
             grids = [eng.empty((n, n, ldz), torch.float32).fill_(-1.0) for _ in offsets]
             eng.set_weight_scale(float(np.float32(float(n) ** 3 / float(fft_weight))))

@@ -565,112 +565,239 @@ tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// "Row streaming" variant of the tile deposit: no output tile in shared memory at all.
-// After each x-step a warp holds, for the finished plane, the z-combined contributions of ITS cell row to
-// the three output rows w-1, w, w+1.  The two side rows go through a small double-buffered exchange array;
-// after ONE block barrier every warp adds what its two neighbours sent to its own centre row and reduces
-// the finished 34-float row straight into the grid (coalesced REDG).  Compared with the shared-tile
-// variant this drops the tile zero-fill, two of the three barriers per x-step, the read-modify-writes
-// and the final flush pass, and frees 13.6 KB of shared memory.
-template <int EXT, bool CIC>
-__global__ void __launch_bounds__(TileDom<EXT>::NT, EXT ? 3 : 4)
-tsc_tile_deposit_stream_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
+// ==============================================================================================
+// Tile deposit, round-2 formulation ("walk" kernel; the default).
+//   phase 1 (lane <-> particle): records of the tile are loaded once, converted to (dx, dy, dz, W) + local cell, and
+//            threaded onto per-cell lists with one shared-memory exchange each (ATOMS.EXCH runs at ~1.3e12 lane-ops/s on
+//            B200, scripts/micro/deposit_micro.cu -- it is not the cost centre round 1 took it for);
+//   phase 2 (lane <-> cell): warp = y-row of the tile, lane = z-cell, x walked serially.  Every lane sums the clouds of
+//            the particles of ITS cell into a rolling window of three x-planes held in registers, stored as packed
+//            float pairs so the 27 multiply-adds of a particle are 12 FFMA2 + 3 FFMA with scalar-broadcast operands
+//            (36 scalar FP instructions in round 1).  A finished plane is combined with the neighbouring lanes by two
+//            shuffles per row and added STRAIGHT to the grid: three coalesced 32-float reductions per x-step.  There is
+//            no shared-memory output tile and no block barrier inside the walk: the warps of a CTA run independently, so
+//            an x-step costs the longest of the warp's 32 lists, not of the CTA's 256.  The two z-halo cells of every
+//            row go through a 60-float per-warp stash and are reduced at the end of the walk (the reduction rate is per
+//            instruction, ~7 SM-cycles each whether 2 or 32 lanes are active).
+// Plane layout (9 floats): p[b] = (S[b][z-1], S[b][z+1]) for the three rows b = y-1, y, y+1; q = (S[y-1][z], S[y+1][z]);
+// s = S[y][z].  TSC weights come as natural pairs (w-, w+) from one packed square, w0 = 0.75 - d^2.
+struct Plane {
+    float2 p[3];
+    float2 q;
+    float s;
+};
+
+__device__ __forceinline__ void plane_zero(Plane &P)
 {
-    using D = TileDom<EXT>;
+    P.p[0] = P.p[1] = P.p[2] = P.q = make_float2(0.0f, 0.0f);
+    P.s = 0.0f;
+}
+
+// P += xa * (cloud of one particle in the y-z plane): T[b] = (y_b z-, y_b z+), U = (y- z0, y+ z0), u0 = y0 z0
+__device__ __forceinline__ void plane_fma(Plane &P, float xa, const float2 (&T)[3], float2 U, float u0)
+{
+    const float2 xx = make_float2(xa, xa);
+    P.p[0] = __ffma2_rn(T[0], xx, P.p[0]);
+    P.p[1] = __ffma2_rn(T[1], xx, P.p[1]);
+    P.p[2] = __ffma2_rn(T[2], xx, P.p[2]);
+    P.q = __ffma2_rn(U, xx, P.q);
+    P.s = fmaf(u0, xa, P.s);
+}
+
+// (w-, w+) and w0 of tsc.py:442-451 / cic.py:43-67 for d = i - p, optionally scaled by W
+template <bool CIC>
+__device__ __forceinline__ void mas_pair(float d, float W, float2 &wmp, float &w0)
+{
+    if (CIC) {
+        wmp = make_float2(fmaxf(d, 0.0f) * W, fmaxf(-d, 0.0f) * W);
+        w0 = (1.0f - fabsf(d)) * W;
+    } else {
+        const float2 a = __fadd2_rn(make_float2(d, -d), make_float2(0.5f, 0.5f));
+        const float h = 0.5f * W;
+        wmp = __fmul2_rn(__fmul2_rn(a, a), make_float2(h, h));
+        w0 = fmaf(-d, d, 0.75f) * W;
+    }
+}
+
+template <bool CIC>
+__device__ __forceinline__ void accumulate_particle(const float4 r, Plane &A, Plane &B, Plane &C)
+{
+    float2 X2, Y2, Z2;
+    float x0, y0, z0;
+    mas_pair<CIC>(r.x, 1.0f, X2, x0);
+    mas_pair<CIC>(r.y, r.w, Y2, y0);
+    mas_pair<CIC>(r.z, 1.0f, Z2, z0);
+    float2 T[3];
+    T[0] = __fmul2_rn(Z2, make_float2(Y2.x, Y2.x));
+    T[1] = __fmul2_rn(Z2, make_float2(y0, y0));
+    T[2] = __fmul2_rn(Z2, make_float2(Y2.y, Y2.y));
+    const float2 U = __fmul2_rn(Y2, make_float2(z0, z0));
+    const float u0 = y0 * z0;
+    plane_fma(A, X2.x, T, U, u0);
+    plane_fma(B, x0, T, U, u0);
+    plane_fma(C, X2.y, T, U, u0);
+}
+
+template <int EXT>
+struct WalkDom {
+    static constexpr int NXC = ABK_TX + EXT, NYC = ABK_TY + EXT;  // cells with particle lists (x, y); z: one per lane
+    static constexpr int NCELL = NXC * NYC * 32;
+    static constexpr int NW = NYC, NT = NW * 32;                  // one warp per y-row
+    static constexpr int NPL = NXC + 2;                           // x-planes a row walk emits (1-cell halo either side)
+    static constexpr int STASH = NPL * 3 * 2;                     // z-halo values of one walk: [plane][row][side]
+};
+
+static size_t walk_smem_bytes(int cap, int ext)
+{
+    const size_t ncell = ext ? WalkDom<1>::NCELL : WalkDom<0>::NCELL;
+    const size_t stash = ext ? (size_t)WalkDom<1>::NW * WalkDom<1>::STASH : (size_t)WalkDom<0>::NW * WalkDom<0>::STASH;
+    return abk_align_up((ncell + stash) * 4, 16) + (size_t)cap * 18 + 64;
+}
+
+// ---- bulk global -> shared copies completing on an mbarrier (cp.async.bulk; SASS: UBLKCP + SYNCS) ---------------
+// One elected thread stages the tile's records: no register round trip, no LSU issue slots, and the tile's 256+ threads
+// are free to initialise the list heads meanwhile.  The CPU emulator build (tests/emu) copies with a plain loop.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+// i in [-n, 2n): one conditional step instead of abk_wrap_cell's general modulo (plane / row indices next to a tile)
+__device__ __forceinline__ int wrap_near(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
+template <int EXT, bool CIC>
+__global__ void __launch_bounds__(WalkDom<EXT>::NT, EXT ? 3 : 4)
+tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
+{
+    using D = WalkDom<EXT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int XROW = D::OZ;                           // 34 floats per exchanged row
-    constexpr int XCH_WORDS = 2 * D::NW * 2 * XROW;       // [parity][warp][side 0/2][z]
-    constexpr int REC_OFF_BYTES = ((XCH_WORDS + D::NCELL) * 4 + 15) / 16 * 16;
-    float *xch = reinterpret_cast<float *>(smem_raw);
-    uint32_t *head = reinterpret_cast<uint32_t *>(xch + XCH_WORDS);
+    constexpr int REC_OFF_BYTES = ((D::NCELL + D::NW * D::STASH) * 4 + 15) / 16 * 16;
+    uint32_t *head = reinterpret_cast<uint32_t *>(smem_raw);
+    float *stash_all = reinterpret_cast<float *>(head + D::NCELL);
     float4 *srec = reinterpret_cast<float4 *>(smem_raw + REC_OFF_BYTES);
     uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);
-    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
-    __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
-    constexpr int MAX_OVF = 512;
+    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
+    __shared__ __align__(8) uint64_t bar;
+    // particles whose cell falls just outside the tile's cell domain (z overflow of the shifted deposit):
+    // queued here and deposited warp-cooperatively, one lane per stencil point
+    constexpr int MAX_OVF = 256;
     __shared__ uint16_t ovf_v[MAX_OVF], ovf_xyz[MAX_OVF];
     __shared__ unsigned ovf_cnt;
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    if (tid < segs.nseg) {
-        const uint32_t b = segs.starts[tid][tile], e = segs.starts[tid][tile + 1];
-        seg_beg[tid] = b;
-        seg_cnt[tid] = e - b;
-        seg_rec[tid] = segs.rec[tid];
-    }
-    __syncthreads();
-    uint32_t total = 0;
-    for (int s = 0; s < segs.nseg; s++) total += seg_cnt[s];
-    if (total == 0) return;
     if (tid == 0) {
         uint32_t run = 0;
-        for (int s = 0; s < segs.nseg; s++) { seg_off[s] = run; run += seg_cnt[s]; }
+        for (int s = 0; s < segs.nseg; s++) {
+            const uint32_t b = segs.starts[s][tile], e = segs.starts[s][tile + 1];
+            seg_beg[s] = b;
+            seg_off[s] = run;
+            run += e - b;
+        }
         seg_off[segs.nseg] = run;
+#if defined(__CUDA_ARCH__)
+        mbar_init(&bar, 1);
+#endif
     }
+    __syncthreads();
+    const uint32_t total = seg_off[segs.nseg];
+    if (total == 0) return;
 
     const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
-
-    // plane-independent pieces of the output addresses of this warp's rows
     const int64_t sx = (int64_t)P.ny * ldz;
+
+    // plane-independent pieces of this warp's output addresses: rows y0+wy-1 .. y0+wy+1, column z0+lane.  Rows or columns
+    // beyond the mesh (ragged last tile, meshes smaller than a tile) only ever carry zeros, which are not written.
     const int gz = abk_wrap_cell(z0 + lane, P.nz);
-    const int ozh = lane ? D::OZ - 1 : 0;
-    const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
-    const int gy_c = abk_wrap_cell(y0 + wy, P.ny);  // centre row oy = wy + 1
-    int emit_no = 0;
+    int rowo[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) rowo[b] = (int)((int64_t)abk_wrap_cell(y0 + wy + b - 1, P.ny) * ldz) + gz;
+    float *stash = stash_all + wy * D::STASH;
+    const int gx_first = slab ? x0 : wrap_near(x0 - 1, P.nx);  // global x of plane 0 (local x = -1)
+    uint32_t parity = 0;
 
     for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
         const int m = (int)min((uint32_t)cap, total - chunk0);
+        if (chunk0) __syncthreads();  // the previous pass' walks are done with the lists and records
+        // ---- stage the raw records of this pass: one bulk copy per segment that overlaps [chunk0, chunk0 + m) ----
+#if defined(__CUDA_ARCH__)
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, (uint32_t)m * 16u);
+            for (int s = 0; s < segs.nseg; s++) {
+                const uint32_t lo = max(seg_off[s], chunk0), hi = min(seg_off[s + 1], chunk0 + (uint32_t)m);
+                if (lo < hi) bulk_g2s(srec + (lo - chunk0), segs.rec[s] + seg_beg[s] + (lo - seg_off[s]), (hi - lo) * 16u, &bar);
+            }
+        }
+#else
+        for (int s = 0; s < segs.nseg; s++) {
+            const uint32_t lo = max(seg_off[s], chunk0), hi = min(seg_off[s + 1], chunk0 + (uint32_t)m);
+            for (uint32_t u = lo + tid; u < hi; u += D::NT) srec[u - chunk0] = segs.rec[s][seg_beg[s] + (u - seg_off[s])];
+        }
+#endif
         for (int c = tid; c < D::NCELL; c += D::NT) head[c] = NIL;
         if (tid == 0) ovf_cnt = 0;
         __syncthreads();
-        const int ox_g = P.x_lo + x0;
-        {
-            int sg = 0;
-            for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
-                float4 rr[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int vq = v0 + q * D::NT;
-                    if (vq < m) {
-                        const uint32_t u = chunk0 + vq;
-                        while (u >= seg_off[sg + 1]) sg++;
-                        rr[q] = __ldcs(seg_rec[sg] + seg_beg[sg] + (u - seg_off[sg]));
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int v = v0 + q * D::NT;
-                    if (v >= m) break;
-                    const float4 r = rr[q];
-                    int lx, ly, lz;
-                    float dx, dy, dz;
-                    local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_g >= P.nx ? ox_g - P.nx : ox_g, D::NXC, lx, dx);
-                    local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
-                    local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, ABK_TZ, lz, dz);
-                    if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
-                        const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
-                        srec[v] = make_float4(dx, dy, dz, r.w);
-                        next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
-                    } else {
-                        unsigned slot = MAX_OVF;
-                        if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
-                        if (slot < (unsigned)MAX_OVF) {
-                            srec[v] = make_float4(dx, dy, dz, r.w);
-                            ovf_v[slot] = (uint16_t)v;
-                            ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
-                        } else {
-                            deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
-                                           abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
-                        }
-                    }
+#if defined(__CUDA_ARCH__)
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+#endif
+        // ---- phase 1, lane <-> particle: (dx, dy, dz, W) records in place, per-cell lists --------------------------
+        const int ox_g = P.x_lo + x0;  // global cell index of the tile origin in x (slab: may exceed nx, handled by wrap)
+        const int ox_w = ox_g >= P.nx ? ox_g - P.nx : ox_g;
+#pragma unroll 2
+        for (int v = tid; v < m; v += D::NT) {
+            const float4 r = srec[v];
+            int lx, ly, lz;
+            float dx, dy, dz;
+            local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_w, D::NXC, lx, dx);
+            local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
+            local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, 32, lz, dz);
+            srec[v] = make_float4(dx, dy, dz, r.w);
+            if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < 32u) {
+                next16[v] = (uint16_t)atomicExch(&head[(lx * D::NYC + ly) * 32 + lz], (uint32_t)v);
+            } else {
+                unsigned slot = MAX_OVF;
+                if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
+                if (slot < (unsigned)MAX_OVF) {
+                    ovf_v[slot] = (uint16_t)v;
+                    ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
+                } else {
+                    // far outside the tile (arbitrary offset difference): global cell = origin + local
+                    deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
+                                   abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
                 }
             }
         }
         __syncthreads();
-        {   // queued out-of-domain particles: one warp per particle, one lane per stencil point
+        // ---- queued out-of-domain particles: one warp per particle, one lane per stencil point -----------
+        {
             const int novf = (int)min(ovf_cnt, (unsigned)MAX_OVF);
             const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
             for (int q = wy; q < novf; q += D::NW) {
@@ -687,101 +814,69 @@ tsc_tile_deposit_stream_kernel(SegList segs, float *__restrict__ grid, TscParams
                                       (c == 0 ? wz[0] : (c == 1 ? wz[1] : wz[2])) * r.w;
                     const int64_t gx = slab ? (int64_t)(x0 + lx + a) : (int64_t)abk_wrap_cell(x0 + lx + a - 1, P.nx);
                     const int gy = abk_wrap_cell(y0 + ly + b - 1, P.ny);
-                    const int gzz = abk_wrap_cell(z0 + lz + c - 1, P.nz);
-                    atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gzz, val);
+                    const int gzo = abk_wrap_cell(z0 + lz + c - 1, P.nz);
+                    atomicAdd(grid + gx * sx + (int64_t)gy * ldz + gzo, val);
                 }
             }
         }
-        // ---- lane <-> cell (row wy, z = lane); rolling 3-plane register window along x ---------------
-        float S0[3][3], S1[3][3], S2[3][3];
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) S0[b][c] = S1[b][c] = S2[b][c] = 0.0f;
-
-        // emit plane x (local index, -1 .. NXC): exchange side rows, add neighbours, reduce into the grid
-        auto emit = [&](const float (&S)[3][3], int x) {
-            float v[3], h0[3], h1[3];
+        // ---- phase 2, lane <-> cell (row wy, z = lane): rolling 3-plane register window along x --------------
+        Plane S0, S1, S2;
+        plane_zero(S0); plane_zero(S1); plane_zero(S2);
+        int gx = gx_first;
+        float *pl = grid + (int64_t)gx * sx;
+        const uint32_t *hp = head + wy * 32 + lane;
+        // sum the lists of cell column cx into (A, B, C) = planes cx-1, cx, cx+1 (plane index cx, cx+1, cx+2); then
+        // plane index cx is complete: combine across lanes, add to the grid, hand the registers back zeroed
+        auto step = [&](int cx, Plane &A, Plane &B, Plane &C) {
+            if (cx < D::NXC) {
+                uint32_t i = hp[cx * (D::NYC * 32)];
+                while (i != NIL) {
+                    const float4 r = srec[i];
+                    const uint16_t nxt = next16[i];
+                    i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
+                    accumulate_particle<CIC>(r, A, B, C);
+                }
+            }
+            const float ctr[3] = {A.q.x, A.s, A.q.y};
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
-                const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
-                v[b] = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
-                h0[b] = S[b][0];  // lane 0: z = -1
-                h1[b] = S[b][2];  // lane 31: z = 32
+                const float up = __shfl_up_sync(0xffffffffu, A.p[b].y, 1);    // lane z-1's contribution to z
+                const float dn = __shfl_down_sync(0xffffffffu, A.p[b].x, 1);  // lane z+1's contribution to z
+                const float v = ctr[b] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
+                if (v != 0.0f) atomicAdd(pl + rowo[b], v);
+                if (lane == 0) stash[(cx * 3 + b) * 2] = A.p[b].x;        // z = -1
+                if (lane == 31) stash[(cx * 3 + b) * 2 + 1] = A.p[b].y;   // z = 32
             }
-            float *buf = xch + (emit_no & 1) * (D::NW * 2 * XROW) + wy * (2 * XROW);
-            buf[lane + 1] = v[0];
-            buf[XROW + lane + 1] = v[2];
-            if (lane == 0) { buf[0] = h0[0]; buf[XROW] = h0[2]; }
-            if (lane == 31) { buf[XROW - 1] = h1[0]; buf[2 * XROW - 1] = h1[2]; }
-            __syncthreads();
-            // centre row of this warp: own b=1 + (warp wy-1).b=2 + (warp wy+1).b=0
-            const float *base = xch + (emit_no & 1) * (D::NW * 2 * XROW);
-            float tot = v[1];
-            const float h1c = __shfl_sync(0xffffffffu, h1[1], 31);
-            float toth = (lane == 0) ? h0[1] : h1c;  // lanes 0 / 1 carry the halo cells z = -1 / 32
-            if (wy > 0) {
-                const float *nb = base + (wy - 1) * (2 * XROW) + XROW;  // b = 2 row of the warp below
-                tot += nb[lane + 1];
-                if (lane < 2) toth += nb[ozh];
-            }
-            if (wy < D::NW - 1) {
-                const float *nb = base + (wy + 1) * (2 * XROW);         // b = 0 row of the warp above
-                tot += nb[lane + 1];
-                if (lane < 2) toth += nb[ozh];
-            }
-            const int64_t gx = slab ? (int64_t)(x0 + x + 1) : (int64_t)abk_wrap_cell(x0 + x, P.nx);
-            float *plane = grid + gx * sx;
-            {
-                float *row = plane + (int64_t)gy_c * ldz;
-                if (tot != 0.0f) atomicAdd(row + gz, tot);
-                if (lane < 2 && toth != 0.0f) atomicAdd(row + gzh, toth);
-            }
-            if (wy == 0 || wy == D::NW - 1) {  // the two halo rows oy = 0 / NW + 1 have a single contributor each
-                const int bsel = (wy == 0) ? 0 : 2;
-                const float vv = (bsel == 0) ? v[0] : v[2];
-                const float hh0 = (bsel == 0) ? h0[0] : h0[2], hh1 = (bsel == 0) ? h1[0] : h1[2];
-                const float hh1_31 = __shfl_sync(0xffffffffu, hh1, 31);  // all lanes take part (warp-uniform branch)
-                const float e = (lane == 0) ? hh0 : hh1_31;
-                float *row = plane + (int64_t)abk_wrap_cell(wy == 0 ? y0 - 1 : y0 + D::NW, P.ny) * ldz;
-                if (vv != 0.0f) atomicAdd(row + gz, vv);
-                if (lane < 2 && e != 0.0f) atomicAdd(row + gzh, e);
-            }
-            emit_no++;
+            plane_zero(A);
+            gx++;
+            pl += sx;
+            if (!slab && gx >= P.nx) { gx -= P.nx; pl -= (int64_t)P.nx * sx; }
         };
-
+        {
+            int cx = 0;
 #pragma unroll 1
-        for (int cx = 0; cx < D::NXC; cx++) {
-            uint32_t i = head[(cx * D::NYC + wy) * ABK_TZ + lane];
-            while (i != NIL) {
-                float wx[3], wyW[3], wz[3];
-                const float4 r = srec[i];
-                const uint16_t nxt = next16[i];
-                i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
-                mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
-                mas_w<CIC>(r.y, wyW[0], wyW[1], wyW[2]);
-                mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
-                wyW[0] *= r.w; wyW[1] *= r.w; wyW[2] *= r.w;
-#pragma unroll
-                for (int b = 0; b < 3; b++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float t = wyW[b] * wz[c];
-                        S0[b][c] = fmaf(wx[0], t, S0[b][c]);
-                        S1[b][c] = fmaf(wx[1], t, S1[b][c]);
-                        S2[b][c] = fmaf(wx[2], t, S2[b][c]);
-                    }
+            for (; cx + 3 <= D::NPL; cx += 3) {
+                step(cx, S0, S1, S2);
+                step(cx + 1, S1, S2, S0);
+                step(cx + 2, S2, S0, S1);
             }
-            emit(S0, cx - 1);
-#pragma unroll
-            for (int b = 0; b < 3; b++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
+            if (D::NPL % 3 >= 1) step(cx, S0, S1, S2);
+            if (D::NPL % 3 == 2) step(cx + 1, S1, S2, S0);
         }
-        emit(S0, D::NXC - 1);
-        emit(S1, D::NXC);
-        __syncthreads();  // the lists are rebuilt by the next pass
+        // ---- the z-halo cells of this walk: [plane][row][side] -----------------------------------------------
+        __syncwarp();
+        {
+            const int gzm = abk_wrap_cell(z0 - 1, P.nz), gzp = abk_wrap_cell(z0 + 32, P.nz);
+            for (int e = lane; e < D::STASH; e += 32) {
+                const float v = stash[e];
+                if (v != 0.0f) {
+                    const int side = e & 1, b = (e >> 1) % 3, px = (e >> 1) / 3;
+                    const int hx = slab ? gx_first + px : abk_wrap_cell(gx_first + px, P.nx);
+                    atomicAdd(grid + (int64_t)hx * sx + (rowo[b == 0 ? 0 : (b == 1 ? 1 : 2)] - gz) + (side ? gzp : gzm), v);
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1340,15 +1435,10 @@ static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bo
 
 typedef void (*deposit_kernel_t)(SegList, float *, TscParams, int64_t, int, int);
 
-static deposit_kernel_t pick_kernel(bool pre, bool priv, int ext, bool cic)
+static deposit_kernel_t pick_kernel(bool, bool, int ext, bool cic)
 {
     if (cic) return ext ? tsc_tile_deposit_kernel<false, false, 1, true> : tsc_tile_deposit_kernel<false, false, 0, true>;
-    if (ext) {
-        if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 1, false> : tsc_tile_deposit_kernel<true, false, 1, false>;
-        return priv ? tsc_tile_deposit_kernel<false, true, 1, false> : tsc_tile_deposit_kernel<false, false, 1, false>;
-    }
-    if (pre) return priv ? tsc_tile_deposit_kernel<true, true, 0, false> : tsc_tile_deposit_kernel<true, false, 0, false>;
-    return priv ? tsc_tile_deposit_kernel<false, true, 0, false> : tsc_tile_deposit_kernel<false, false, 0, false>;
+    return ext ? tsc_tile_deposit_kernel<false, false, 1, false> : tsc_tile_deposit_kernel<false, false, 0, false>;
 }
 
 extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
@@ -1373,40 +1463,41 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     }
     // records bucketed at another offset: widen the tile's cell domain by one cell in x and y
     const int ext = ((float)bucket_offset != (float)offset) ? 1 : 0;
-    const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = default
-    if (variant == 5) {  // row-streaming kernel
-        const bool cic5 = ctx->scheme == 1;
-        const size_t xch = (size_t)2 * (ext ? TileDom<1>::NW : TileDom<0>::NW) * 2 * (ABK_TZ + 2) * 4;
-        const size_t ncell = ext ? TileDom<1>::NCELL : TileDom<0>::NCELL;
-        const size_t fixed5 = abk_align_up(xch + ncell * 4, 16) + 64;
-        const double mean = g.ntiles > 0 ? (double)n_total / (double)g.ntiles : 0.0;
-        int cap5 = (ctx->tile_capacity & 0xffff) ? (ctx->tile_capacity & 0xffff)
-                                                 : (int)((mean + 5.0 * sqrt(mean + 1.0) + 32.0 + 63.0) / 64.0) * 64;
-        const int occ5 = ext ? 3 : 4;
-        int fit5 = (int)(((size_t)(ctx->smem_optin + 1024) / occ5 - 1024 - fixed5) / 18) / 64 * 64;
-        if (cap5 > fit5) {
-            const int fit5b = (int)(((size_t)(ctx->smem_optin + 1024) / (occ5 - 1) - 1024 - fixed5) / 18) / 64 * 64;
-            cap5 = cap5 <= fit5b ? cap5 : fit5b;
+    const bool cic = ctx->scheme == 1;
+    const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = walk kernel (default), 1 = round-1 shared-tile kernel (A/B)
+    if (variant == 0) {
+        deposit_kernel_t kern = ext ? (cic ? tsc_tile_walk_kernel<1, true> : tsc_tile_walk_kernel<1, false>)
+                                    : (cic ? tsc_tile_walk_kernel<0, true> : tsc_tile_walk_kernel<0, false>);
+        cudaFuncAttributes fa;
+        ABK_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
+        const size_t fixed = walk_smem_bytes(0, ext) + fa.sharedSizeBytes;
+        int cap = ctx->tile_capacity & 0xffff;
+        if (!cap) {
+            // mean occupancy + 5 sigma (Poisson): a uniform catalogue then needs ONE pass per tile; never more than what
+            // keeps the target number of CTAs resident (denser tiles take several passes)
+            const double mean = g.ntiles > 0 ? (double)n_total / (double)g.ntiles : 0.0;
+            cap = (int)((mean + 5.0 * sqrt(mean + 1.0) + 32.0 + 63.0) / 64.0) * 64;
+            const int occ = ext ? 3 : 4;
+            const int fit = (int)((((size_t)ctx->smem_optin + 1024) / occ - 1024 - fixed) / 18) / 64 * 64;
+            if (cap > fit) cap = fit;
+            if (cap < 256) cap = 256;
         }
-        if (cap5 < 256) cap5 = 256;
-        const size_t smem5 = fixed5 + (size_t)cap5 * 18;
-        deposit_kernel_t k5 = ext ? (cic5 ? tsc_tile_deposit_stream_kernel<1, true> : tsc_tile_deposit_stream_kernel<1, false>)
-                                  : (cic5 ? tsc_tile_deposit_stream_kernel<0, true> : tsc_tile_deposit_stream_kernel<0, false>);
-        ABK_CHECK_CUDA(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-        ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, k5<<<(unsigned)g.ntiles, ext ? TileDom<1>::NT : TileDom<0>::NT, smem5, ctx->stream>>>(segs, grid, P, ldz, cap5, slab));
+        const size_t smem = walk_smem_bytes(cap, ext);
+        ABK_REQUIRE(smem + fa.sharedSizeBytes <= (size_t)ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap,
+                    smem + fa.sharedSizeBytes, ctx->smem_optin);
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, ext ? WalkDom<1>::NT : WalkDom<0>::NT, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
         return ABK_OK;
     }
-    const bool cic = ctx->scheme == 1;
-    const bool pre = (variant && !cic) ? ((variant - 1) & 1) : false;
-    const bool priv = (variant && !cic) ? (((variant - 1) >> 1) & 1) : false;
-    const int per_sm = pre ? 2 : ((priv || ext) ? 3 : 4);
+    const bool pre = false, priv = false;
+    const int per_sm = ext ? 3 : 4;
     const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, ext, per_sm);
     const size_t smem = deposit_smem_bytes(cap, pre, priv, ext);
     ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
     deposit_kernel_t kern = pick_kernel(pre, priv, ext, cic);
     // resident CTAs per SM allowed by shared memory (1 KB per CTA is reserved by the driver)
     const int occ_smem = (int)((size_t)(ctx->smem_optin + 1024) / (smem + 1024));
-    if (!pre && !priv && !ext && !cic && occ_smem <= 3 && !ctx->no_minb3) kern = tsc_tile_deposit_kernel<false, false, 0, false, 3>;
+    if (!ext && !cic && occ_smem <= 3 && !ctx->no_minb3) kern = tsc_tile_deposit_kernel<false, false, 0, false, 3>;
     const int threads = ext ? TileDom<1>::NT : TileDom<0>::NT;
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, threads, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));

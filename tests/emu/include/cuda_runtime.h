@@ -335,10 +335,17 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 4096; int numRegs = 0; };
+template <class F>
+inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, F) { *a = cudaFuncAttributes(); return cudaSuccess; }
 
 // ---- vector types ----------------------------------------------------------------------------------
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
+// packed float32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two independent IEEE operations
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }

@@ -45,7 +45,7 @@ def test_tile_capacity_passes_and_variants(emu, oracle):
     want = np.zeros((n, n, n), np.float32)
     oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
     try:
-        for variant in (0, 1, 2, 3, 5):
+        for variant in (0, 1):      # 0: walk kernel (default), 1: round-1 shared-tile kernel kept for A/B timing
             check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 256 | (variant << 16)))
             got = tsc.tsc_parallel(pos.copy(), (n, n, n), box, weights=w)
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5, err_msg=f'variant {variant}')
@@ -211,32 +211,27 @@ def test_two_level_bucketing_matches_one_level(emu):
         np.testing.assert_array_equal(a, b)
 
 
-def test_vector_flush_variant(emu, golden, oracle):
-    """abk_ctx_set_tile_capacity bit 20: tile rows flushed with two-cell vector reductions.  Rows that wrap in z, odd
-    row strides and unaligned grids must take the scalar path; results unchanged either way."""
-    from abacusutils_b200._lib import check
+def test_ragged_and_odd_grids(emu, golden, oracle):
+    """Padded FFT grids (32 | n or not) and grids with odd row strides / a partial last z tile: rows that wrap in z inside a
+    warp, z-halo cells that wrap, meshes smaller than a tile."""
     from abacusutils_b200.analysis import power_spectrum as ps
     from abacusutils_b200.analysis import tsc
 
-    try:
-        check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 1 << 20))
-        for name in ('n32_ci', 'n48_log'):                 # padded FFT grids: ldz even, 32 | n or not
-            c = cases.POWER_CASES[name]
-            pos, w, pos2, w2 = cases.power_inputs(c)
-            t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
-                              nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2,
-                              w2=w2, poles=c['poles'])
-            want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
-            compare_power_tables(t, want)
-        rng = np.random.default_rng(4)
-        for shape in ((16, 16, 64), (9, 11, 33), (8, 8, 32), (12, 10, 70)):   # even / odd strides, partial last z tile
-            pos = (rng.random((3000, 3), dtype=np.float32) * np.float32(80.0)).astype(np.float32)
-            got, want = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
-            tsc.tsc_parallel(pos.copy(), got, 80.0, offset=0.3)
-            oracle.tsc_parallel(pos.copy(), want, 80.0, offset=0.3, nthread=1)
-            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, err_msg=str(shape))
-    finally:
-        check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
+    for name in ('n32_ci', 'n48_log'):
+        c = cases.POWER_CASES[name]
+        pos, w, pos2, w2 = cases.power_inputs(c)
+        t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
+                          nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2,
+                          w2=w2, poles=c['poles'])
+        want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
+        compare_power_tables(t, want)
+    rng = np.random.default_rng(4)
+    for shape in ((16, 16, 64), (9, 11, 33), (8, 8, 32), (12, 10, 70), (5, 40, 3), (33, 7, 2)):
+        pos = (rng.random((3000, 3), dtype=np.float32) * np.float32(80.0)).astype(np.float32)
+        got, want = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+        tsc.tsc_parallel(pos.copy(), got, 80.0, offset=0.3)
+        oracle.tsc_parallel(pos.copy(), want, 80.0, offset=0.3, nthread=1)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, err_msg=str(shape))
 
 
 @pytest.mark.parametrize('kind', ['pack9', 'rvint'])
@@ -267,6 +262,13 @@ def test_calc_power_from_packed_records(emu, oracle, monkeypatch, kind):
     assert_int_exact(got['N_mode'], want['N_mode'], 'N_mode')
     np.testing.assert_allclose(got['power'], want['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(want['power'])).max())
     np.testing.assert_allclose(got['poles'], want['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(want['poles'])).max())
+    # a second call on the same object takes the fused-normalisation path (the particle count is known by now): it must
+    # normalise by the particle count, not by the record count (pack9 records include cell headers)
+    again = ps.calc_power(src, L, **kw)
+    assert again.meta['N_pos'] == len(pos)
+    assert_int_exact(again['N_mode'], want['N_mode'], 'N_mode (second call)')
+    np.testing.assert_allclose(again['power'], got['power'], rtol=2e-5, atol=2e-6 * np.abs(np.asarray(want['power'])).max())
+    np.testing.assert_allclose(again['poles'], got['poles'], rtol=1e-4, atol=2e-5 * np.abs(np.asarray(want['poles'])).max())
     with pytest.raises(ValueError):
         ps.calc_power(src, L, w=np.ones(len(src), np.float32), **kw)
 
