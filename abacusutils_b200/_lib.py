@@ -65,10 +65,9 @@ SIGNATURES = {
     'abk_partition_scratch_bytes': (_i32, [_i64, _i32, _psz]),
     'abk_partition': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _sz]),
     'abk_tsc_num_tiles': (_i32, [_i32, _i32, _i32, C.POINTER(_i64)]),
+    'abk_tsc_tile_shape': (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'abk_tsc_bucket_scratch_bytes': (_i32, [_i64, _i32, _i32, _i32, _psz]),
     'abk_tsc_bucket': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp, _vp, _sz]),
-    'abk_tsc_bucket2': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp, _vp, _sz]),
-    'abk_tsc_bucket2_scratch_bytes': (_i32, [_i64, _i32, _i32, _i32, _psz]),
     'abk_tsc_bucket_slab': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _dbl, _dbl, _i32, _i32, _i32, _vp, _vp,
                                    _vp, _sz, C.POINTER(C.c_ulonglong)]),
     'abk_route_particles': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _i32, C.POINTER(C.c_int32), _vp,

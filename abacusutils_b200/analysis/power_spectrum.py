@@ -282,12 +282,9 @@ class _Painter:
             chunks = self.chunk_plan(N, host=(kind == 'host'))
         nseg = len(chunks)
         counts = [b - a for a, b in chunks]      # particles per segment (packed input: filled in as chunks are decoded)
-        # ABK_SCATTER=2 (experiment knob): two-level multisplit bucketing with coalesced record writes
-        two_level = os.environ.get('ABK_SCATTER', '1') == '2'
-        bucket_fn = lib.abk_tsc_bucket2 if two_level else lib.abk_tsc_bucket
+        bucket_fn = lib.abk_tsc_bucket
         nb = C.c_size_t()
-        check((lib.abk_tsc_bucket2_scratch_bytes if two_level else lib.abk_tsc_bucket_scratch_bytes)(
-            chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
+        check(lib.abk_tsc_bucket_scratch_bytes(chunks[0][1] - chunks[0][0], n, n, n, C.byref(nb)))
         scan_buf = eng.scratch('bucket_scan', nb.value + 256)
         scan_ptr = C.c_void_p((scan_buf.data_ptr() + 255) & ~255)
         starts_stride = (ntiles + 1 + 63) // 64 * 64

@@ -42,8 +42,6 @@ struct abk_ctx {
     int tile_capacity;  // 0 = auto
     int scheme;         // mass-assignment scheme of the deposit entry points: 0 TSC, 1 CIC
     int bin_no_sym;     // experiments: force the one-mode-at-a-time binning kernel
-    int no_minb3;       // experiments: never use the 80-register build of the default deposit kernel (tile-capacity bit 21)
-    int flush_v2;       // experiments: 8-byte vector reductions in the tile flush (abk_ctx_set_tile_capacity bit 20)
     float wscale;       // factor applied to every particle weight when records are written (abk_ctx_set_weight_scale)
     // small device scratch owned by the context (work counters, flags)
     unsigned long long *d_scalars;
@@ -99,11 +97,11 @@ void abk_set_error(const char *fmt, ...);
 static inline size_t abk_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- deposit tile geometry (cells per tile) -------------------------------------------------
-// One warp per y-row of the tile, one lane per z-cell, x walked serially with a rolling
-// 3-plane register window.  See abk_tsc.cu.
+// One warp per y-row of the tile, one lane per z-cell plus one halo lane either side, x walked serially
+// with a rolling 3-plane register window.  See abk_tsc.cu.
 constexpr int ABK_TX = 8;
 constexpr int ABK_TY = 8;
-constexpr int ABK_TZ = 32;
+constexpr int ABK_TZ = 30;
 
 struct abk_tile_geom {
     int nx, ny, nz;

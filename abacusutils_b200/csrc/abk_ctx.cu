@@ -42,8 +42,6 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     c->scheme = 0;
     c->bin_no_sym = 0;
     c->wscale = 1.0f;
-    c->flush_v2 = 0;
-    c->no_minb3 = 0;
     c->d_scalars = nullptr;
     c->prof_on = 0;
     c->prof_recs = nullptr;
@@ -168,12 +166,10 @@ extern "C" int abk_ctx_set_weight_scale(abk_ctx *ctx, double scale)
 extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
 {
     ABK_REQUIRE(ctx != nullptr, "null context");
-    const int cap = capacity & 0xffff;  // bits 16..18: deposit kernel variant (experiments), 0 = default
+    const int cap = capacity & 0xffff;
     ABK_REQUIRE(cap == 0 || (cap >= 256 && cap <= 12288), "tile capacity %d out of range", cap);
-    ctx->tile_capacity = capacity & 0x7ffff;
+    ctx->tile_capacity = cap;
     ctx->bin_no_sym = (capacity >> 19) & 1;  // bit 19: disable the mirror-symmetric binning kernel (experiments)
-    ctx->flush_v2 = (capacity >> 20) & 1;    // bit 20: vector reductions in the tile flush (experiments)
-    ctx->no_minb3 = (capacity >> 21) & 1;    // bit 21: keep the 64-register deposit kernel even at 3 CTAs/SM (experiments)
     return ABK_OK;
 }
 

@@ -7,23 +7,19 @@
 //   _tsc_scatter         analysis/tsc.py:394-507   (27 read-modify-writes per particle)
 //
 // Design:
-//   A. bucket particles by the (8 x 8 x 32)-cell tile of their cloud's centre cell: histogram
+//   A. bucket particles by the (8 x 8 x 30)-cell tile of their cloud's centre cell: histogram
 //      (one 4-byte reduction per particle), scan, scatter of 16-byte (x,y,z,w) records.  The open
 //      write frontier is one 128-byte line per tile; it stays (mostly) resident in the 126 MB L2.
-//   B. one CTA per tile: per-cell particle lists are built in shared memory with one integer
-//      exchange per particle; then warp = y-row, lane = z-cell, x walked serially: every lane sums
-//      the 27 stencil weights of ITS cell's particles in registers (a rolling 3-plane window along
-//      x), neighbouring lanes are combined with two shuffles, neighbouring rows through a
-//      shared-memory tile written without atomics (each (plane,row) is owned by exactly one warp
-//      per phase).  Shared-memory float atomics are a CAS loop on sm_100a (ATOMS.CAST.SPIN), so the
-//      kernel uses none.  The finished tile + 1-cell halo is added to the grid with coalesced float
-//      reductions (REDG.ADD.F32): ~1.7 per CELL instead of 27 per PARTICLE.
+//   B. one CTA per tile ("walk" kernel): per-cell particle lists are built in shared memory with one
+//      integer exchange per particle; then warp = y-row, lane = z-cell (+ one halo lane either side),
+//      x walked serially: every lane sums the 27 stencil weights of ITS cell's particles in registers
+//      (a rolling 3-plane window along x, packed FFMA2 arithmetic), neighbouring lanes are combined with
+//      two shuffles per row, and each finished row goes straight to the grid as ONE coalesced 32-float
+//      reduction (REDG.ADD.F32).  No shared-memory output tile, no block barrier inside the walk, no
+//      float shared-memory atomics (a CAS loop on sm_100a).
 //   C. interlacing: the half-cell-shifted deposit reuses the records bucketed for the unshifted grid
-//      (template EXT: one more cell row/plane per tile; z overflow is queued and deposited
-//      warp-cooperatively).  CIC (analysis/cic.py) is the same update with other weights (template CIC).
-// Kernel variants kept for measurement (abk_ctx_set_tile_capacity bits 16-18): precomputed 32-byte
-// records (PRE), private per-warp slabs (PRIV), row streaming without an output tile; the default
-// (16-byte records, shared tile) is the fastest on B200 (profiles/r1_ncu_summary.md).
+//      (template EXT: one more cell per tile in x, y and z).  CIC (analysis/cic.py) is the same update
+//      with other weights (template CIC).
 #include "abk_common.cuh"
 
 namespace {
@@ -39,7 +35,6 @@ struct TscParams {
     int wrap;
     int cic;                       // 0: TSC (tsc.py), 1: CIC (cic.py:13-125)
     double gx_d, gy_d, gz_d;       // CIC works in double: p = (x / box) * g
-    int flush_v2;                  // experiment: flush tile rows with 8-byte vector reductions (red.global.add.v2.f32)
     float wscale;                  // multiplies every weight as the bucket records are written (1 unless the caller
                                    // folds the field normalisation into the deposit, abk_ctx_set_weight_scale)
 };
@@ -193,26 +188,6 @@ __global__ void __launch_bounds__(256) tsc_bucket_kernel(const float *__restrict
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Tile deposit.  Geometry of the shared-memory working set of one CTA (= one tile of 8 x 8 x 32 cells):
-//   slab[w]   : warp w (= y-row w of the tile) owns a PRIVATE float slab [TX+2 planes][3 rows][TZ+2],
-//               the image of its row's clouds on rows w-1, w, w+1 (+1-cell halo in x and z).  Private
-//               slabs make the main loop free of block barriers and of atomics.
-//   head[c]   : first particle of cell c's list (index into srec) or NIL
-//   srec[2v]  : (wx-, wx0, wx+, dz)            precomputed in the lane<->particle load pass, so the
-//   srec[2v+1]: (wy- W, wy0 W, wy+ W, next)     divergent lane<->cell loop is 2 LDS.128 + 43 FP ops
-// EXT = 1 widens the cell domain of a tile by one cell in x and y (and treats z-overflow with direct
-// reductions): that is what the half-cell-shifted (interlaced) deposit needs when it REUSES the records
-// bucketed for the unshifted grid -- the shifted centre cell is the unshifted one or its +1 neighbour.
-template <int EXT>
-struct TileDom {
-    static constexpr int NXC = ABK_TX + EXT, NYC = ABK_TY + EXT;       // cells with particle lists
-    static constexpr int OX = NXC + 2, OY = NYC + 2, OZ = ABK_TZ + 2;  // output region incl. 1-cell halo
-    static constexpr int OUT_N = OX * OY * OZ;
-    static constexpr int SLAB_PLANE = 3 * OZ, SLAB_WORDS = OX * SLAB_PLANE;
-    static constexpr int NCELL = NXC * NYC * ABK_TZ;
-    static constexpr int NW = NYC, NT = NW * 32;  // one warp per y-row
-};
 constexpr uint32_t NIL = 0xffffffffu;
 
 struct SegList {
@@ -220,20 +195,6 @@ struct SegList {
     const float4 *rec[ABK_MAX_SEGMENTS];
     const uint32_t *starts[ABK_MAX_SEGMENTS];
 };
-
-// PRE : 32-byte records with precomputed x/y weights (fewer instructions in the divergent loop)
-//       vs 16-byte (dx,dy,dz,W) records + u16 links (less shared memory -> more resident CTAs)
-// PRIV: private per-warp slabs (no barriers in the main loop) vs one shared output tile with a
-//       block barrier after every row phase
-static size_t deposit_smem_bytes(int cap, bool pre, bool priv, int ext)
-{
-    const size_t out_n = ext ? TileDom<1>::OUT_N : TileDom<0>::OUT_N;
-    const size_t slab = ext ? (size_t)TileDom<1>::NW * TileDom<1>::SLAB_WORDS : (size_t)TileDom<0>::NW * TileDom<0>::SLAB_WORDS;
-    const size_t ncell = ext ? TileDom<1>::NCELL : TileDom<0>::NCELL;
-    const size_t out = (priv ? slab : out_n) * 4;
-    const size_t rec = pre ? (size_t)cap * 32 : (size_t)cap * 16 + (size_t)cap * 2;
-    return abk_align_up(out + ncell * 4, 16) + rec + 64;
-}
 
 // tsc.py:442-451: the three 1-D TSC weights for cells i-1, i, i+1 given d = i - p
 __device__ __forceinline__ void tsc_w(float d, float &wm, float &w0, float &wp)
@@ -257,47 +218,6 @@ __device__ __forceinline__ void mas_w(float d, float &wm, float &w0, float &wp)
 {
     if (CIC) cic_w(d, wm, w0, wp);
     else tsc_w(d, wm, w0, wp);
-}
-
-// two adjacent floats in one 8-byte reduction (sm_90+); p must be 8-byte aligned
-__device__ __forceinline__ void red_add_v2(float *p, float a, float b)
-{
-#if defined(__CUDA_ARCH__)
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-#else
-    atomicAdd(p, a);
-    atomicAdd(p + 1, b);
-#endif
-}
-
-// Add one finished x-plane of this lane's register window to the output.
-// S[b][c]: contribution of cell (row w, z = lane) to row w-1+b, cell z-1+c.  Lane z receives the
-// c=+1 term of lane z-1 and the c=-1 term of lane z+1; the two halo cells are lanes 0 / 31's.
-// PRIV: `dst` is the warp's private slab [plane][3 rows][OZ] and the first pass stores instead of adding.
-// shared: `dst` is the CTA's tile [plane][OY][OZ]; rows of different warps are distinct within a
-//         phase (b) but not across phases, hence the block barrier after each phase.
-template <typename D, bool PRIV>
-__device__ __forceinline__ void emit_plane(float *__restrict__ dst, const float (&S)[3][3], int x, int wy, int lane,
-                                           bool first)
-{
-    float *plane = dst + (x + 1) * (PRIV ? D::SLAB_PLANE : D::OY * D::OZ);
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-        const float up = __shfl_up_sync(0xffffffffu, S[b][2], 1);
-        const float dn = __shfl_down_sync(0xffffffffu, S[b][0], 1);
-        const float v = S[b][1] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
-        float *row = plane + (PRIV ? b : wy + b) * D::OZ;
-        if (PRIV && first) {  // the first pass writes every slab entry exactly once: no zero-fill, no RMW
-            row[lane + 1] = v;
-            if (lane == 0) row[0] = S[b][0];
-            if (lane == 31) row[D::OZ - 1] = S[b][2];
-        } else {
-            row[lane + 1] += v;
-            if (lane == 0) row[0] += S[b][0];
-            if (lane == 31) row[D::OZ - 1] += S[b][2];
-        }
-        if (!PRIV) __syncthreads();
-    }
 }
 
 // 27 global reductions for a particle whose centre cell lies outside the cell domain of the tile it
@@ -331,254 +251,22 @@ __device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscP
     }
 }
 
-// MINB (0 = by variant): minimum resident CTAs per SM the register allocation must allow.  The default kernel is built
-// twice: for 4 CTAs/SM (64 registers, 60 bytes of spills) and for 3 (80 registers, no spills); the launch picks the
-// second whenever shared memory limits the SM to three CTAs anyway (e.g. ~1 particle per cell, one pass per tile).
-template <bool PRE, bool PRIV, int EXT, bool CIC, int MINB = 0>
-__global__ void __launch_bounds__(TileDom<EXT>::NT, MINB ? MINB : (PRE ? 2 : ((PRIV || EXT) ? 3 : 4)))
-tsc_tile_deposit_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_t ldz, int cap, int slab)
-{
-    using D = TileDom<EXT>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int OUT_WORDS = PRIV ? D::NW * D::SLAB_WORDS : D::OUT_N;
-    constexpr int HEAD_OFF = OUT_WORDS;
-    constexpr int REC_OFF_BYTES = ((OUT_WORDS + D::NCELL) * 4 + 15) / 16 * 16;
-    float *outbuf = reinterpret_cast<float *>(smem_raw);
-    uint32_t *head = reinterpret_cast<uint32_t *>(outbuf + HEAD_OFF);
-    float4 *srec = reinterpret_cast<float4 *>(smem_raw + REC_OFF_BYTES);
-    uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);  // !PRE only
-    __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_cnt[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
-    __shared__ const float4 *seg_rec[ABK_MAX_SEGMENTS];
-    // particles whose cell falls just outside the tile's cell domain (z overflow of the shifted deposit):
-    // queued here and deposited warp-cooperatively, one lane per stencil point
-    constexpr int MAX_OVF = 512;
-    __shared__ uint16_t ovf_v[MAX_OVF], ovf_xyz[MAX_OVF];
-    __shared__ unsigned ovf_cnt;
-
-    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    if (tid < segs.nseg) {
-        const uint32_t b = segs.starts[tid][tile], e = segs.starts[tid][tile + 1];
-        seg_beg[tid] = b;
-        seg_cnt[tid] = e - b;
-        seg_rec[tid] = segs.rec[tid];
-    }
-    __syncthreads();
-    uint32_t total = 0;
-    for (int s = 0; s < segs.nseg; s++) total += seg_cnt[s];
-    if (total == 0) return;
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (int s = 0; s < segs.nseg; s++) { seg_off[s] = run; run += seg_cnt[s]; }
-        seg_off[segs.nseg] = run;
-    }
-
-    const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
-    const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
-
-    float *myslab = outbuf + wy * D::SLAB_WORDS;  // PRIV only
-    if (!PRIV)
-        for (int i = tid; i < D::OUT_N; i += D::NT) outbuf[i] = 0.0f;
-
-    for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
-        const int m = (int)min((uint32_t)cap, total - chunk0);
-        const bool first = (chunk0 == 0);
-        for (int c = tid; c < D::NCELL; c += D::NT) head[c] = NIL;
-        if (tid == 0) ovf_cnt = 0;
-        __syncthreads();
-        // ---- lane <-> particle: per-cell lists (and, PRE, the x/y weights once per particle) -------
-        const int ox_g = P.x_lo + x0;  // global cell index of the tile origin in x (slab: may exceed nx, handled by wrap)
-        {
-            int sg = 0;  // this thread's virtual indices only grow: the segment lookup is incremental
-            for (int v0 = tid; v0 < m; v0 += 4 * D::NT) {
-                float4 rr[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {  // issue the (streaming) record loads of four particles first
-                    const int vq = v0 + q * D::NT;
-                    if (vq < m) {
-                        const uint32_t u = chunk0 + vq;
-                        while (u >= seg_off[sg + 1]) sg++;
-                        rr[q] = __ldcs(seg_rec[sg] + seg_beg[sg] + (u - seg_off[sg]));
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int v = v0 + q * D::NT;
-                    if (v >= m) break;
-                    const float4 r = rr[q];
-                    int lx, ly, lz;
-                    float dx, dy, dz;
-                    local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_g >= P.nx ? ox_g - P.nx : ox_g, D::NXC, lx, dx);
-                    local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
-                    local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, ABK_TZ, lz, dz);
-                    if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)ABK_TZ) {
-                        const int c = (lx * D::NYC + ly) * ABK_TZ + lz;
-                        if (PRE) {
-                            float wxm, wx0, wxp, wym, wy0, wyp;
-                            mas_w<CIC>(dx, wxm, wx0, wxp);
-                            mas_w<CIC>(dy, wym, wy0, wyp);
-                            srec[2 * v] = make_float4(wxm, wx0, wxp, dz);
-                            const uint32_t old = atomicExch(&head[c], (uint32_t)v);
-                            srec[2 * v + 1] = make_float4(wym * r.w, wy0 * r.w, wyp * r.w, __uint_as_float(old));
-                        } else {
-                            srec[v] = make_float4(dx, dy, dz, r.w);
-                            next16[v] = (uint16_t)atomicExch(&head[c], (uint32_t)v);
-                        }
-                    } else {
-                        unsigned slot = MAX_OVF;
-                        if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
-                        if (slot < (unsigned)MAX_OVF) {
-                            srec[PRE ? 2 * v : v] = make_float4(dx, dy, dz, r.w);
-                            ovf_v[slot] = (uint16_t)v;
-                            ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
-                        } else {
-                            // far outside the tile (arbitrary offset difference): global cell = origin + local
-                            deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
-                                           abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- queued out-of-domain particles: one warp per particle, one lane per stencil point -----------
-        {
-            const int novf = (int)min(ovf_cnt, (unsigned)MAX_OVF);
-            const int64_t sxo = (int64_t)P.ny * ldz;
-            const int a = lane / 9, b = (lane / 3) % 3, c = lane % 3;
-            for (int q = wy; q < novf; q += D::NW) {
-                const float4 r = srec[PRE ? 2 * ovf_v[q] : ovf_v[q]];
-                const int xyz = ovf_xyz[q];
-                const int lx = xyz >> 10, ly = (xyz >> 6) & 15, lz = xyz & 63;
-                float wx[3], wyv[3], wz[3];
-                mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
-                mas_w<CIC>(r.y, wyv[0], wyv[1], wyv[2]);
-                mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
-                if (lane < 27) {
-                    const float val = (a == 0 ? wx[0] : (a == 1 ? wx[1] : wx[2])) *
-                                      (b == 0 ? wyv[0] : (b == 1 ? wyv[1] : wyv[2])) *
-                                      (c == 0 ? wz[0] : (c == 1 ? wz[1] : wz[2])) * r.w;
-                    const int64_t gx = slab ? (int64_t)(x0 + lx + a) : (int64_t)abk_wrap_cell(x0 + lx + a - 1, P.nx);
-                    const int gy = abk_wrap_cell(y0 + ly + b - 1, P.ny);
-                    const int gz = abk_wrap_cell(z0 + lz + c - 1, P.nz);
-                    atomicAdd(grid + gx * sxo + (int64_t)gy * ldz + gz, val);
-                }
-            }
-        }
-        // ---- lane <-> cell (row wy, z = lane); rolling 3-plane register window along x ---------------
-        float S0[3][3], S1[3][3], S2[3][3];
-#pragma unroll
-        for (int b = 0; b < 3; b++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) S0[b][c] = S1[b][c] = S2[b][c] = 0.0f;
-
-#pragma unroll 1
-        for (int cx = 0; cx < D::NXC; cx++) {
-            uint32_t i = head[(cx * D::NYC + wy) * ABK_TZ + lane];
-            while (i != NIL) {
-                float wx[3], wyW[3], wz[3];
-                if (PRE) {
-                    const float4 A = srec[2 * i], B = srec[2 * i + 1];
-                    i = __float_as_uint(B.w);
-                    wx[0] = A.x; wx[1] = A.y; wx[2] = A.z;
-                    wyW[0] = B.x; wyW[1] = B.y; wyW[2] = B.z;
-                    mas_w<CIC>(A.w, wz[0], wz[1], wz[2]);
-                } else {
-                    const float4 r = srec[i];
-                    const uint16_t nxt = next16[i];
-                    i = (nxt == 0xffffu) ? NIL : (uint32_t)nxt;
-                    mas_w<CIC>(r.x, wx[0], wx[1], wx[2]);
-                    mas_w<CIC>(r.y, wyW[0], wyW[1], wyW[2]);
-                    mas_w<CIC>(r.z, wz[0], wz[1], wz[2]);
-                    wyW[0] *= r.w; wyW[1] *= r.w; wyW[2] *= r.w;
-                }
-#pragma unroll
-                for (int b = 0; b < 3; b++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float t = wyW[b] * wz[c];
-                        S0[b][c] = fmaf(wx[0], t, S0[b][c]);
-                        S1[b][c] = fmaf(wx[1], t, S1[b][c]);
-                        S2[b][c] = fmaf(wx[2], t, S2[b][c]);
-                    }
-            }
-            emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S0, cx - 1, wy, lane, first);
-#pragma unroll
-            for (int b = 0; b < 3; b++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) { S0[b][c] = S1[b][c]; S1[b][c] = S2[b][c]; S2[b][c] = 0.0f; }
-        }
-        emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S0, D::NXC - 1, wy, lane, first);
-        emit_plane<D, PRIV>(PRIV ? myslab : outbuf, S1, D::NXC, wy, lane, first);
-        if (PRIV) __syncthreads();  // lists are rebuilt by the next pass; slabs are complete for the flush
-    }
-
-    // ---- flush tile + halo with float reductions -----------------------------------------------------
-    // Warp w owns output rows oy = w, w + NW, ... of every x-plane; lanes on z, so the reductions of
-    // one instruction hit 32 consecutive floats.  Everything that does not depend on the plane (row
-    // pointers of the <= 3 contributing slabs, wrapped y/z indices) is hoisted.
-    const int64_t sx = (int64_t)P.ny * ldz;
-    // vector flush needs the whole 32-cell row inside the mesh (no z wrap inside it) and 8-byte aligned pairs
-    const bool pair_ok = !PRIV && P.flush_v2 && z0 + ABK_TZ <= P.nz && (ldz & 1) == 0 && (((uintptr_t)grid) & 7) == 0;
-    const int gz = abk_wrap_cell(z0 + lane, P.nz);
-    const int ozh = lane ? D::OZ - 1 : 0;
-    const int gzh = abk_wrap_cell(z0 + ozh - 1, P.nz);
-    for (int oy = wy; oy < D::OY; oy += D::NW) {
-        const int gy = abk_wrap_cell(y0 + oy - 1, P.ny);
-        // PRIV: contributing (warp, row) pairs: w = oy - b for b = 0..2 with 0 <= w < NW
-        const bool ok0 = oy < D::NW, ok1 = oy >= 1 && oy - 1 < D::NW, ok2 = oy >= 2 && oy - 2 < D::NW;
-        const float *p0 = outbuf + (ok0 ? oy : 0) * D::SLAB_WORDS;
-        const float *p1 = outbuf + (ok1 ? oy - 1 : 0) * D::SLAB_WORDS + D::OZ;
-        const float *p2 = outbuf + (ok2 ? oy - 2 : 0) * D::SLAB_WORDS + 2 * D::OZ;
-        int gx = slab ? x0 : abk_wrap_cell(x0 - 1, P.nx);
-        for (int ox = 0; ox < D::OX; ox++) {
-            float v = 0.0f, vh = 0.0f;
-            if (PRIV) {
-                const int o = ox * D::SLAB_PLANE;
-                if (ok0) { v += p0[o + lane + 1]; if (lane < 2) vh += p0[o + ozh]; }
-                if (ok1) { v += p1[o + lane + 1]; if (lane < 2) vh += p1[o + ozh]; }
-                if (ok2) { v += p2[o + lane + 1]; if (lane < 2) vh += p2[o + ozh]; }
-            } else {
-                const float *r = outbuf + (ox * D::OY + oy) * D::OZ;
-                v = r[lane + 1];
-                if (lane < 2) vh = r[ozh];
-            }
-            float *dst = grid + gx * sx + (int64_t)gy * ldz;
-            if (pair_ok) {
-                // lanes 0..15 take the 32 interior cells two at a time, lanes 16/17 the two z-halo cells
-                const float *r = outbuf + (ox * D::OY + oy) * D::OZ;
-                if (lane < 16) {
-                    const float a = r[2 * lane + 1], b = r[2 * lane + 2];
-                    if (a != 0.0f || b != 0.0f) red_add_v2(dst + z0 + 2 * lane, a, b);
-                } else if (lane < 18) {
-                    const int oz = (lane == 16) ? 0 : D::OZ - 1;
-                    const float h = r[oz];
-                    if (h != 0.0f) atomicAdd(dst + abk_wrap_cell(z0 + oz - 1, P.nz), h);
-                }
-            } else {
-                if (v != 0.0f) atomicAdd(dst + gz, v);
-                if (lane < 2 && vh != 0.0f) atomicAdd(dst + gzh, vh);
-            }
-            gx++;
-            if (!slab && gx >= P.nx) gx -= P.nx;
-        }
-    }
-}
-
 // ==============================================================================================
-// Tile deposit, round-2 formulation ("walk" kernel; the default).
-//   phase 1 (lane <-> particle): records of the tile are loaded once, converted to (dx, dy, dz, W) + local cell, and
-//            threaded onto per-cell lists with one shared-memory exchange each (ATOMS.EXCH runs at ~1.3e12 lane-ops/s on
-//            B200, scripts/micro/deposit_micro.cu -- it is not the cost centre round 1 took it for);
-//   phase 2 (lane <-> cell): warp = y-row of the tile, lane = z-cell, x walked serially.  Every lane sums the clouds of
-//            the particles of ITS cell into a rolling window of three x-planes held in registers, stored as packed
-//            float pairs so the 27 multiply-adds of a particle are 12 FFMA2 + 3 FFMA with scalar-broadcast operands
-//            (36 scalar FP instructions in round 1).  A finished plane is combined with the neighbouring lanes by two
-//            shuffles per row and added STRAIGHT to the grid: three coalesced 32-float reductions per x-step.  There is
+// Tile deposit ("walk" kernel).  One CTA per tile of 8 x 8 x 30 cells.
+//   phase 1 (lane <-> particle): the tile's records arrive in shared memory by bulk copy (cp.async.bulk + mbarrier), are
+//            converted in place to (dx, dy, dz, W) and threaded onto per-cell lists with one shared-memory exchange
+//            each (ATOMS.EXCH runs at ~1.3e12 lane-ops/s on B200, scripts/micro/deposit_micro.cu);
+//   phase 2 (lane <-> cell): warp = y-row of the tile, lanes 1..30 = its z-cells, lanes 0 and 31 = the z-halo cells;
+//            x walked serially.  Every lane sums the clouds of the particles of ITS cell into a rolling window of three
+//            x-planes held in registers, stored as packed float pairs so the 27 multiply-adds of a particle are
+//            12 FFMA2 + 3 FFMA with scalar-broadcast operands.  A finished plane is combined with the neighbouring lanes
+//            by two rotating shuffles per row (the halo lanes hold no particles, so the wrap-around terms are zero) and
+//            added STRAIGHT to the grid: three coalesced 32-float reductions per x-step, halo cells included.  There is
 //            no shared-memory output tile and no block barrier inside the walk: the warps of a CTA run independently, so
-//            an x-step costs the longest of the warp's 32 lists, not of the CTA's 256.  The two z-halo cells of every
-//            row go through a 60-float per-warp stash and are reduced at the end of the walk (the reduction rate is per
-//            instruction, ~7 SM-cycles each whether 2 or 32 lanes are active).
+//            an x-step costs the longest of the warp's 30 lists, not of the CTA's 240.
+// EXT = 1 (records bucketed at offset 0, deposit at +half a cell): the centre cell is the bucketed one or its +1
+//            neighbour, so the tile's cell domain grows to 9 x 9 x 31; lane 31 then owns a cell and its upper z-term
+//            goes through a small per-warp stash that is reduced at the end of the walk.
 // Plane layout (9 floats): p[b] = (S[b][z-1], S[b][z+1]) for the three rows b = y-1, y, y+1; q = (S[y-1][z], S[y+1][z]);
 // s = S[y][z].  TSC weights come as natural pairs (w-, w+) from one packed square, w0 = 0.75 - d^2.
 struct Plane {
@@ -640,17 +328,18 @@ __device__ __forceinline__ void accumulate_particle(const float4 r, Plane &A, Pl
 
 template <int EXT>
 struct WalkDom {
-    static constexpr int NXC = ABK_TX + EXT, NYC = ABK_TY + EXT;  // cells with particle lists (x, y); z: one per lane
-    static constexpr int NCELL = NXC * NYC * 32;
+    static constexpr int NXC = ABK_TX + EXT, NYC = ABK_TY + EXT, NZC = ABK_TZ + EXT;  // cells with particle lists
+    static constexpr int NCELL = NXC * NYC * 32;                  // list heads: [x][y][lane], lane = local z + 1
     static constexpr int NW = NYC, NT = NW * 32;                  // one warp per y-row
     static constexpr int NPL = NXC + 2;                           // x-planes a row walk emits (1-cell halo either side)
-    static constexpr int STASH = NPL * 3 * 2;                     // z-halo values of one walk: [plane][row][side]
+    static constexpr int STASH = EXT ? NPL * 3 : 0;               // upper z-halo values of one walk: [plane][row]
 };
+static_assert(ABK_TZ + 1 + 1 <= 32, "a tile's z-cells and its two halo cells must fit one warp");
 
 static size_t walk_smem_bytes(int cap, int ext)
 {
     const size_t ncell = ext ? WalkDom<1>::NCELL : WalkDom<0>::NCELL;
-    const size_t stash = ext ? (size_t)WalkDom<1>::NW * WalkDom<1>::STASH : (size_t)WalkDom<0>::NW * WalkDom<0>::STASH;
+    const size_t stash = ext ? (size_t)WalkDom<1>::NW * WalkDom<1>::STASH : 0;
     return abk_align_up((ncell + stash) * 4, 16) + (size_t)cap * 18 + 64;
 }
 
@@ -703,9 +392,9 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
     uint16_t *next16 = reinterpret_cast<uint16_t *>(srec + cap);
     __shared__ uint32_t seg_beg[ABK_MAX_SEGMENTS], seg_off[ABK_MAX_SEGMENTS + 1];
     __shared__ __align__(8) uint64_t bar;
-    // particles whose cell falls just outside the tile's cell domain (z overflow of the shifted deposit):
-    // queued here and deposited warp-cooperatively, one lane per stencil point
-    constexpr int MAX_OVF = 256;
+    // particles whose cell lies outside the tile's cell domain (only possible when the deposit offset is not the
+    // bucketing offset or that plus half a cell): queued here and deposited warp-cooperatively, one lane per stencil point
+    constexpr int MAX_OVF = 128;
     __shared__ uint16_t ovf_v[MAX_OVF], ovf_xyz[MAX_OVF];
     __shared__ unsigned ovf_cnt;
 
@@ -732,14 +421,16 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
     const int64_t sx = (int64_t)P.ny * ldz;
 
-    // plane-independent pieces of this warp's output addresses: rows y0+wy-1 .. y0+wy+1, column z0+lane.  Rows or columns
-    // beyond the mesh (ragged last tile, meshes smaller than a tile) only ever carry zeros, which are not written.
-    const int gz = abk_wrap_cell(z0 + lane, P.nz);
-    int rowo[3];
-#pragma unroll
-    for (int b = 0; b < 3; b++) rowo[b] = (int)((int64_t)abk_wrap_cell(y0 + wy + b - 1, P.ny) * ldz) + gz;
+    // plane-independent pieces of this warp's output addresses: rows y0+wy-1 .. y0+wy+1, column z0-1+lane.  Rows or
+    // columns beyond the mesh (ragged last tile, meshes smaller than a tile) only ever carry zeros, which are not written.
+    const int sx32 = (int)sx;  // ny * ldz < 2^31 for every mesh the reference's int16 cell indices allow
+    const int ldz32 = (int)ldz;
+    const int gy0 = abk_wrap_cell(y0 + wy - 1, P.ny), gy1 = wrap_near(gy0 + 1, P.ny), gy2 = wrap_near(gy1 + 1, P.ny);
+    const int rowo0 = gy0 * ldz32 + abk_wrap_cell(z0 - 1 + lane, P.nz);
+    const int d01 = (gy1 - gy0) * ldz32, d12 = (gy2 - gy1) * ldz32;  // warp-uniform row steps (ldz, or back to row 0)
+    const int gx_first = slab ? x0 : wrap_near(x0 - 1, P.nx);        // global x of plane 0 (local x = -1)
+    const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
     float *stash = stash_all + wy * D::STASH;
-    const int gx_first = slab ? x0 : wrap_near(x0 - 1, P.nx);  // global x of plane 0 (local x = -1)
     uint32_t parity = 0;
 
     for (uint32_t chunk0 = 0; chunk0 < total; chunk0 += cap) {
@@ -771,17 +462,16 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
         // ---- phase 1, lane <-> particle: (dx, dy, dz, W) records in place, per-cell lists --------------------------
         const int ox_g = P.x_lo + x0;  // global cell index of the tile origin in x (slab: may exceed nx, handled by wrap)
         const int ox_w = ox_g >= P.nx ? ox_g - P.nx : ox_g;
-#pragma unroll 2
         for (int v = tid; v < m; v += D::NT) {
             const float4 r = srec[v];
             int lx, ly, lz;
             float dx, dy, dz;
             local_cell<CIC>(r.x, P.off, P.inv_hx, P.box, P.gx_d, P.nx, ox_w, D::NXC, lx, dx);
             local_cell<CIC>(r.y, P.off, P.inv_hy, P.box, P.gy_d, P.ny, y0, D::NYC, ly, dy);
-            local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, 32, lz, dz);
+            local_cell<CIC>(r.z, P.off, P.inv_hz, P.box, P.gz_d, P.nz, z0, D::NZC, lz, dz);
             srec[v] = make_float4(dx, dy, dz, r.w);
-            if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < 32u) {
-                next16[v] = (uint16_t)atomicExch(&head[(lx * D::NYC + ly) * 32 + lz], (uint32_t)v);
+            if ((unsigned)lx < (unsigned)D::NXC && (unsigned)ly < (unsigned)D::NYC && (unsigned)lz < (unsigned)D::NZC) {
+                next16[v] = (uint16_t)atomicExch(&head[(lx * D::NYC + ly) * 32 + lz + 1], (uint32_t)v);
             } else {
                 unsigned slot = MAX_OVF;
                 if ((unsigned)lx < 16u && (unsigned)ly < 16u && (unsigned)lz < 64u) slot = atomicAdd(&ovf_cnt, 1u);
@@ -819,11 +509,10 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
                 }
             }
         }
-        // ---- phase 2, lane <-> cell (row wy, z = lane): rolling 3-plane register window along x --------------
+        // ---- phase 2, lane <-> cell (row wy, lane = local z + 1): rolling 3-plane register window along x --------
         Plane S0, S1, S2;
         plane_zero(S0); plane_zero(S1); plane_zero(S2);
         int gx = gx_first;
-        float *pl = grid + (int64_t)gx * sx;
         const uint32_t *hp = head + wy * 32 + lane;
         // sum the lists of cell column cx into (A, B, C) = planes cx-1, cx, cx+1 (plane index cx, cx+1, cx+2); then
         // plane index cx is complete: combine across lanes, add to the grid, hand the registers back zeroed
@@ -837,20 +526,22 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
                     accumulate_particle<CIC>(r, A, B, C);
                 }
             }
+            float *row = grid + (int64_t)gx * sx32 + rowo0;
             const float ctr[3] = {A.q.x, A.s, A.q.y};
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                const float up = __shfl_up_sync(0xffffffffu, A.p[b].y, 1);    // lane z-1's contribution to z
-                const float dn = __shfl_down_sync(0xffffffffu, A.p[b].x, 1);  // lane z+1's contribution to z
-                const float v = ctr[b] + (lane > 0 ? up : 0.0f) + (lane < 31 ? dn : 0.0f);
-                if (v != 0.0f) atomicAdd(pl + rowo[b], v);
-                if (lane == 0) stash[(cx * 3 + b) * 2] = A.p[b].x;        // z = -1
-                if (lane == 31) stash[(cx * 3 + b) * 2 + 1] = A.p[b].y;   // z = 32
+                // rotating shuffles: the halo lanes hold no particles, so what wraps around is zero -- except, EXT, the
+                // upper term of lane 31 (local z = 31), which lands on lane 0 and is stashed
+                const float up = __shfl_sync(0xffffffffu, A.p[b].y, lane_up);  // lane z-1's contribution to z
+                const float dn = __shfl_sync(0xffffffffu, A.p[b].x, lane_dn);  // lane z+1's contribution to z
+                const float v = ctr[b] + ((EXT && lane == 0) ? 0.0f : up) + dn;
+                if (__any_sync(0xffffffffu, v != 0.0f)) atomicAdd(row, v);
+                if (EXT && lane == 0) stash[cx * 3 + b] = up;
+                row += (b == 0 ? d01 : d12);
             }
             plane_zero(A);
             gx++;
-            pl += sx;
-            if (!slab && gx >= P.nx) { gx -= P.nx; pl -= (int64_t)P.nx * sx; }
+            if (!slab && gx >= P.nx) gx -= P.nx;
         };
         {
             int cx = 0;
@@ -863,20 +554,20 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
             if (D::NPL % 3 >= 1) step(cx, S0, S1, S2);
             if (D::NPL % 3 == 2) step(cx + 1, S1, S2, S0);
         }
-        // ---- the z-halo cells of this walk: [plane][row][side] -----------------------------------------------
-        __syncwarp();
-        {
-            const int gzm = abk_wrap_cell(z0 - 1, P.nz), gzp = abk_wrap_cell(z0 + 32, P.nz);
+        // ---- EXT: the upper z-halo cells of this walk (local z = 31): [plane][row] -------------------------------
+        if (EXT) {
+            __syncwarp();
+            const int gzp = abk_wrap_cell(z0 + 31, P.nz);
             for (int e = lane; e < D::STASH; e += 32) {
                 const float v = stash[e];
                 if (v != 0.0f) {
-                    const int side = e & 1, b = (e >> 1) % 3, px = (e >> 1) / 3;
+                    const int b = e % 3, px = e / 3;
                     const int hx = slab ? gx_first + px : abk_wrap_cell(gx_first + px, P.nx);
-                    atomicAdd(grid + (int64_t)hx * sx + (rowo[b == 0 ? 0 : (b == 1 ? 1 : 2)] - gz) + (side ? gzp : gzm), v);
+                    atomicAdd(grid + (int64_t)hx * sx + (int64_t)(b == 0 ? gy0 : (b == 1 ? gy1 : gy2)) * ldz + gzp, v);
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -1018,7 +709,6 @@ int make_params(const abk_ctx *ctx, TscParams &P, int nx, int ny, int nz, double
     P.cic = ctx->scheme == 1;
     P.gx_d = nx; P.gy_d = ny; P.gz_d = nz;
     P.wscale = ctx->wscale;
-    P.flush_v2 = ctx->flush_v2;
     return ABK_OK;
 }
 
@@ -1117,6 +807,13 @@ extern "C" int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles)
     return ABK_OK;
 }
 
+extern "C" int abk_tsc_tile_shape(int *tx, int *ty, int *tz)
+{
+    ABK_REQUIRE(tx && ty && tz, "abk_tsc_tile_shape: null argument");
+    *tx = ABK_TX; *ty = ABK_TY; *tz = ABK_TZ;
+    return ABK_OK;
+}
+
 extern "C" int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes)
 {
     ABK_REQUIRE(bytes && nx > 0 && ny > 0 && nz > 0 && N >= 0, "abk_tsc_bucket_scratch_bytes: bad arguments");
@@ -1183,263 +880,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
     return ABK_OK;
 }
 
-// ==============================================================================================
-// Two-level bucketing (experiment, abk_tsc_bucket2): same result layout as abk_tsc_bucket (records grouped by
-// tile, tile_starts exclusive), but the 16-byte records reach memory in coalesced runs instead of one scattered
-// store per particle -- the classic scatter is bound by the rate of scattered store requests, not by bandwidth.
-//   level 1: tile id >> shift  (<= 1024 coarse buckets, each a contiguous range of tiles)
-//   level 2: tile id within the coarse bucket (<= 1024 tiles)
-// Each level is a CTA-local multisplit of a 4096-record chunk: rank inside (chunk, bucket) with one shared-memory
-// atomic per record, one global cursor reservation per (chunk, non-empty bucket), records staged in shared memory
-// in bucket order and written out as runs of consecutive addresses.
-namespace {
-
-constexpr int SPLIT_CH = 4096, SPLIT_NT = 256, SPLIT_IT = SPLIT_CH / SPLIT_NT, SPLIT_MAXB = 1024;
-
-struct SplitSmem {
-    float4 stage[SPLIT_CH];
-    uint16_t skey[SPLIT_CH];
-    uint32_t cnt[SPLIT_MAXB], off[SPLIT_MAXB], gbase[SPLIT_MAXB];
-    uint32_t warp_tot[SPLIT_NT / 32];
-};
-
-// One chunk: `rec[it]`/`key[it]` are this thread's items (item it of thread t is chunk element it*256 + t, valid if
-// below m).  cursors[key] hands out positions in `out`.
-__device__ __forceinline__ void multisplit_chunk(SplitSmem &S, const float4 (&rec)[SPLIT_IT], const int (&key)[SPLIT_IT], int m,
-                                                 int nb, uint32_t *__restrict__ cursors, float4 *__restrict__ out)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int b = tid; b < nb; b += SPLIT_NT) S.cnt[b] = 0;
-    __syncthreads();
-    uint32_t rank[SPLIT_IT];
-#pragma unroll
-    for (int it = 0; it < SPLIT_IT; it++)
-        if (it * SPLIT_NT + tid < m) rank[it] = atomicAdd(&S.cnt[key[it]], 1u);
-    __syncthreads();
-    // exclusive scan of cnt[0..nb) (4 buckets per thread), and the global reservation of every non-empty bucket
-    uint32_t c[4], run = 0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int b = tid * 4 + q;
-        c[q] = b < nb ? S.cnt[b] : 0u;
-        run += c[q];
-    }
-    uint32_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) S.warp_tot[wid] = inc;
-    __syncthreads();
-    uint32_t base = inc - run;
-    for (int w = 0; w < wid; w++) base += S.warp_tot[w];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int b = tid * 4 + q;
-        if (b < nb) {
-            S.off[b] = base;
-            if (c[q]) S.gbase[b] = atomicAdd(&cursors[b], c[q]);
-            base += c[q];
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < SPLIT_IT; it++)
-        if (it * SPLIT_NT + tid < m) {
-            const uint32_t slot = S.off[key[it]] + rank[it];
-            S.stage[slot] = rec[it];
-            S.skey[slot] = (uint16_t)key[it];
-        }
-    __syncthreads();
-    for (int i = tid; i < m; i += SPLIT_NT) {
-        const int b = S.skey[i];
-        out[S.gbase[b] + ((uint32_t)i - S.off[b])] = S.stage[i];
-    }
-    __syncthreads();
-}
-
-// level 1: particles (pos/w) -> temp records grouped by coarse bucket
-__global__ void __launch_bounds__(SPLIT_NT, 2)
-split_coarse_kernel(const float *__restrict__ pos, const float *__restrict__ w, int64_t N, TscParams P, int shift, int nb,
-                    uint32_t *__restrict__ cursors, float4 *__restrict__ out)
-{
-    extern __shared__ __align__(16) unsigned char split_raw[];
-    SplitSmem &S = *reinterpret_cast<SplitSmem *>(split_raw);
-    const int64_t nchunks = (N + SPLIT_CH - 1) / SPLIT_CH;
-    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const int64_t base = ch * SPLIT_CH;
-        const int m = (int)min((int64_t)SPLIT_CH, N - base);
-        float4 rec[SPLIT_IT];
-        int key[SPLIT_IT];
-#pragma unroll
-        for (int it = 0; it < SPLIT_IT; it++) {
-            const int e = it * SPLIT_NT + threadIdx.x;
-            key[it] = 0;
-            if (e < m) {
-                const int64_t i = base + e;
-                float x = __ldcs(pos + 3 * i), y = __ldcs(pos + 3 * i + 1), z = __ldcs(pos + 3 * i + 2);
-                if (P.wrap) { x = wrap_coord(x, P.box); y = wrap_coord(y, P.box); z = wrap_coord(z, P.box); }
-                uint32_t tile = 0;
-                tile_of(P, x, y, z, tile);
-                rec[it] = make_float4(x, y, z, (w ? __ldcs(w + i) : 1.0f) * P.wscale);
-                key[it] = (int)(tile >> shift);
-            }
-        }
-        multisplit_chunk(S, rec, key, m, nb, cursors, out);
-    }
-}
-
-// level 2: every coarse bucket (a contiguous record range of `tmp`) is refined by `splits` CTAs; keys are tile ids
-// relative to the bucket's first tile, cursors are the global per-tile cursors
-__global__ void __launch_bounds__(SPLIT_NT, 2)
-split_fine_kernel(const float4 *__restrict__ tmp, const uint32_t *__restrict__ tile_starts, int64_t ntiles, TscParams P, int shift,
-                  int splits, uint32_t *__restrict__ cursors, float4 *__restrict__ out)
-{
-    extern __shared__ __align__(16) unsigned char split_raw[];
-    SplitSmem &S = *reinterpret_cast<SplitSmem *>(split_raw);
-    const int cb = blockIdx.x / splits, part = blockIdx.x % splits;
-    const int64_t t0 = (int64_t)cb << shift;
-    const int64_t t1 = min(t0 + ((int64_t)1 << shift), ntiles);
-    const int nb = (int)(t1 - t0);
-    const int64_t r0 = tile_starts[t0], r1 = tile_starts[t1];
-    const int64_t nchunks = (r1 - r0 + SPLIT_CH - 1) / SPLIT_CH;
-    for (int64_t ch = part; ch < nchunks; ch += splits) {
-        const int64_t base = r0 + ch * SPLIT_CH;
-        const int m = (int)min((int64_t)SPLIT_CH, r1 - base);
-        float4 rec[SPLIT_IT];
-        int key[SPLIT_IT];
-#pragma unroll
-        for (int it = 0; it < SPLIT_IT; it++) {
-            const int e = it * SPLIT_NT + threadIdx.x;
-            key[it] = 0;
-            if (e < m) {
-                rec[it] = __ldcs(tmp + base + e);
-                uint32_t tile = 0;
-                tile_of(P, rec[it].x, rec[it].y, rec[it].z, tile);
-                key[it] = (int)((int64_t)tile - t0);
-            }
-        }
-        multisplit_chunk(S, rec, key, m, nb, cursors + t0, out);
-    }
-}
-
-// incl[t] (inclusive scan of the tile histogram) -> starts[t] exclusive with starts[ntiles] = total, a second copy as the
-// per-tile cursors, and the coarse cursors coarse[c] = starts[c << shift]
-__global__ void __launch_bounds__(256) split_starts_kernel(const uint32_t *__restrict__ incl, int64_t ntiles, int shift,
-                                                           uint32_t *__restrict__ starts, uint32_t *__restrict__ cur_fine,
-                                                           uint32_t *__restrict__ cur_coarse)
-{
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t v = t ? incl[t - 1] : 0u;
-        starts[t] = v;
-        if (t < ntiles) {
-            cur_fine[t] = v;
-            if ((t & (((int64_t)1 << shift) - 1)) == 0) cur_coarse[t >> shift] = v;
-        }
-    }
-}
-
-int split_shift(int64_t ntiles)
-{
-    int bits = 0;
-    while (((int64_t)1 << bits) < ntiles) bits++;
-    return (bits + 1) / 2;
-}
-
-}  // namespace
-
-extern "C" int abk_tsc_bucket2_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes)
-{
-    ABK_REQUIRE(bytes && nx > 0 && ny > 0 && nz > 0 && N >= 0, "abk_tsc_bucket2_scratch_bytes: bad arguments");
-    const int64_t ntiles = abk_make_geom(nx, ny, nz).ntiles;
-    *bytes = abk_align_up(abk_scan_tmp_bytes(ntiles) + 256, 256) + 2 * abk_align_up((size_t)(ntiles + 1) * 4, 256) +
-             abk_align_up((size_t)SPLIT_MAXB * 4, 256) + abk_align_up((size_t)(N > 0 ? N : 1) * 16, 256);
-    return ABK_OK;
-}
-
-extern "C" int abk_tsc_bucket2(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz, double box,
-                               double offset, int wrap, void *records, uint32_t *tile_starts, void *scratch,
-                               size_t scratch_bytes)
-{
-    ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket2: null argument");
-    TscParams P;
-    int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, 0, nx);
-    if (rc) return rc;
-    const abk_tile_geom g = abk_make_geom(nx, ny, nz);
-    const int shift = split_shift(g.ntiles);
-    const int64_t ncoarse = (g.ntiles + ((int64_t)1 << shift) - 1) >> shift;
-    // meshes with more than 2^20 tiles would need a third level: use the one-level scatter there
-    if (N == 0 || ((int64_t)1 << shift) > SPLIT_MAXB || ncoarse > SPLIT_MAXB)
-        return bucket_impl(ctx, pos, w, N, P, records, tile_starts, scratch, scratch_bytes);
-    ABK_REQUIRE(N <= ((int64_t)1 << 30), "a bucket segment holds at most 2^30 particles (got %lld)", (long long)N);
-    size_t need = 0;
-    abk_tsc_bucket2_scratch_bytes(N, nx, ny, nz, &need);
-    if (scratch_bytes < need || ((uintptr_t)scratch & 255)) {
-        abk_set_error("abk_tsc_bucket2: scratch %zu < %zu or not 256-byte aligned", scratch_bytes, need);
-        return ABK_ERR_SCRATCH;
-    }
-    char *sp = (char *)scratch;
-    void *scan_tmp = sp;                   sp += abk_align_up(abk_scan_tmp_bytes(g.ntiles) + 256, 256);
-    uint32_t *incl = (uint32_t *)sp;       sp += abk_align_up((size_t)(g.ntiles + 1) * 4, 256);
-    uint32_t *cur_fine = (uint32_t *)sp;   sp += abk_align_up((size_t)(g.ntiles + 1) * 4, 256);
-    uint32_t *cur_coarse = (uint32_t *)sp; sp += abk_align_up((size_t)SPLIT_MAXB * 4, 256);
-    float4 *tmp = (float4 *)sp;
-
-    ABK_CHECK_CUDA(cudaMemsetAsync(incl, 0, (size_t)(g.ntiles + 1) * 4, ctx->stream));
-    const int vec_ok = (((uintptr_t)pos & 15) == 0) && (!w || ((uintptr_t)w & 15) == 0);
-    const int hblocks = grid_for(ctx, (N + 3) / 4, 256, 16);
-    ABK_LAUNCH(ctx, ABK_K_BUCKET_HIST, tsc_bucket_kernel<false, false><<<hblocks, 256, 0, ctx->stream>>>(
-                                           pos, w, N, P, incl, nullptr, vec_ok, ctx->d_scalars + 1));
-    rc = abk_inclusive_scan_u32(ctx, incl, g.ntiles, scan_tmp);
-    if (rc) return rc;
-    ABK_LAUNCH(ctx, ABK_K_MISC, split_starts_kernel<<<grid_for(ctx, g.ntiles + 1, 256, 8), 256, 0, ctx->stream>>>(
-                                    incl, g.ntiles, shift, tile_starts, cur_fine, cur_coarse));
-    const size_t smem = sizeof(SplitSmem);
-    ABK_CHECK_CUDA(cudaFuncSetAttribute(split_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_CHECK_CUDA(cudaFuncSetAttribute(split_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t nchunks = (N + SPLIT_CH - 1) / SPLIT_CH;
-    const int64_t cap = (int64_t)ctx->num_sms * 2;
-    ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, split_coarse_kernel<<<(unsigned)(nchunks < cap ? nchunks : cap), SPLIT_NT, smem, ctx->stream>>>(
-                                              pos, w, N, P, shift, (int)ncoarse, cur_coarse, tmp));
-    int splits = (int)((cap * 4 + ncoarse - 1) / ncoarse);
-    if (splits < 1) splits = 1;
-    ABK_LAUNCH(ctx, ABK_K_BUCKET_SCATTER, split_fine_kernel<<<(unsigned)(ncoarse * splits), SPLIT_NT, smem, ctx->stream>>>(
-                                              tmp, tile_starts, g.ntiles, P, shift, splits, cur_fine, (float4 *)records));
-    return ABK_OK;
-}
-
-// kernel variant (PRE, PRIV): abk_ctx_set_tile_capacity's bits 16..18 select it for experiments
-
-static int pick_capacity(const abk_ctx *ctx, int64_t n_total, int64_t ntiles, bool pre, bool priv, int ext, int per_sm)
-{
-    if (ctx->tile_capacity & 0xffff) return ctx->tile_capacity & 0xffff;
-    // mean occupancy + 5 sigma (Poisson): a uniform catalogue then needs ONE pass per tile.  A second pass
-    // repeats the whole per-cell work, which costs more than one resident CTA less per SM (measured on
-    // B200, config 3: 64 ms with 3 CTAs/SM and one pass vs 68 ms with 4 CTAs/SM and two passes for 40%
-    // of the tiles), so the capacity may take one CTA/SM; denser tiles simply take several passes.
-    const double mean = ntiles > 0 ? (double)n_total / (double)ntiles : 0.0;
-    const double want = mean + 5.0 * sqrt(mean + 1.0) + 32.0;
-    int cap = (int)((want + 63.0) / 64.0) * 64;
-    const size_t fixed = deposit_smem_bytes(0, pre, priv, ext);
-    int fit = 256;
-    for (int occ = per_sm; occ >= (per_sm > 2 ? per_sm - 1 : per_sm); occ--) {
-        const size_t per_cta = (size_t)(ctx->smem_optin + 1024) / occ - 1024;
-        fit = (int)((per_cta - fixed) / (pre ? 32 : 18)) / 64 * 64;
-        if (cap <= fit) break;
-    }
-    if (cap > fit) cap = fit;
-    if (cap < 256) cap = 256;
-    return cap;
-}
-
 typedef void (*deposit_kernel_t)(SegList, float *, TscParams, int64_t, int, int);
-
-static deposit_kernel_t pick_kernel(bool, bool, int ext, bool cic)
-{
-    if (cic) return ext ? tsc_tile_deposit_kernel<false, false, 1, true> : tsc_tile_deposit_kernel<false, false, 0, true>;
-    return ext ? tsc_tile_deposit_kernel<false, false, 1, false> : tsc_tile_deposit_kernel<false, false, 0, false>;
-}
 
 extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *records_seg_h,
                                      const uint32_t *const *tile_starts_seg_h, const int64_t *seg_counts_h,
@@ -1461,46 +902,30 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
         segs.starts[s] = tile_starts_seg_h[s];
         n_total += seg_counts_h ? seg_counts_h[s] : 0;
     }
-    // records bucketed at another offset: widen the tile's cell domain by one cell in x and y
+    // records bucketed at another offset: widen the tile's cell domain by one cell per axis
     const int ext = ((float)bucket_offset != (float)offset) ? 1 : 0;
     const bool cic = ctx->scheme == 1;
-    const int variant = (ctx->tile_capacity >> 16) & 7;  // 0 = walk kernel (default), 1 = round-1 shared-tile kernel (A/B)
-    if (variant == 0) {
-        deposit_kernel_t kern = ext ? (cic ? tsc_tile_walk_kernel<1, true> : tsc_tile_walk_kernel<1, false>)
-                                    : (cic ? tsc_tile_walk_kernel<0, true> : tsc_tile_walk_kernel<0, false>);
-        cudaFuncAttributes fa;
-        ABK_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
-        const size_t fixed = walk_smem_bytes(0, ext) + fa.sharedSizeBytes;
-        int cap = ctx->tile_capacity & 0xffff;
-        if (!cap) {
-            // mean occupancy + 5 sigma (Poisson): a uniform catalogue then needs ONE pass per tile; never more than what
-            // keeps the target number of CTAs resident (denser tiles take several passes)
-            const double mean = g.ntiles > 0 ? (double)n_total / (double)g.ntiles : 0.0;
-            cap = (int)((mean + 5.0 * sqrt(mean + 1.0) + 32.0 + 63.0) / 64.0) * 64;
-            const int occ = ext ? 3 : 4;
-            const int fit = (int)((((size_t)ctx->smem_optin + 1024) / occ - 1024 - fixed) / 18) / 64 * 64;
-            if (cap > fit) cap = fit;
-            if (cap < 256) cap = 256;
-        }
-        const size_t smem = walk_smem_bytes(cap, ext);
-        ABK_REQUIRE(smem + fa.sharedSizeBytes <= (size_t)ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap,
-                    smem + fa.sharedSizeBytes, ctx->smem_optin);
-        ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, ext ? WalkDom<1>::NT : WalkDom<0>::NT, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
-        return ABK_OK;
+    deposit_kernel_t kern = ext ? (cic ? tsc_tile_walk_kernel<1, true> : tsc_tile_walk_kernel<1, false>)
+                                : (cic ? tsc_tile_walk_kernel<0, true> : tsc_tile_walk_kernel<0, false>);
+    cudaFuncAttributes fa;
+    ABK_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t fixed = walk_smem_bytes(0, ext) + fa.sharedSizeBytes;
+    int cap = ctx->tile_capacity & 0xffff;
+    if (!cap) {
+        // mean occupancy + 5 sigma (Poisson): a uniform catalogue then needs ONE pass per tile; never more than what
+        // keeps the target number of CTAs resident (denser tiles take several passes)
+        const double mean = g.ntiles > 0 ? (double)n_total / (double)g.ntiles : 0.0;
+        cap = (int)((mean + 5.0 * sqrt(mean + 1.0) + 32.0 + 63.0) / 64.0) * 64;
+        const int occ = ext ? 3 : 4;
+        const int fit = (int)((((size_t)ctx->smem_optin + 1024) / occ - 1024 - fixed) / 18) / 64 * 64;
+        if (cap > fit) cap = fit;
+        if (cap < 256) cap = 256;
     }
-    const bool pre = false, priv = false;
-    const int per_sm = ext ? 3 : 4;
-    const int cap = pick_capacity(ctx, n_total, g.ntiles, pre, priv, ext, per_sm);
-    const size_t smem = deposit_smem_bytes(cap, pre, priv, ext);
-    ABK_REQUIRE((int)smem <= ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap, smem, ctx->smem_optin);
-    deposit_kernel_t kern = pick_kernel(pre, priv, ext, cic);
-    // resident CTAs per SM allowed by shared memory (1 KB per CTA is reserved by the driver)
-    const int occ_smem = (int)((size_t)(ctx->smem_optin + 1024) / (smem + 1024));
-    if (!ext && !cic && occ_smem <= 3 && !ctx->no_minb3) kern = tsc_tile_deposit_kernel<false, false, 0, false, 3>;
-    const int threads = ext ? TileDom<1>::NT : TileDom<0>::NT;
+    const size_t smem = walk_smem_bytes(cap, ext);
+    ABK_REQUIRE(smem + fa.sharedSizeBytes <= (size_t)ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap,
+                smem + fa.sharedSizeBytes, ctx->smem_optin);
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, threads, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
+    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, ext ? WalkDom<1>::NT : WalkDom<0>::NT, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
     return ABK_OK;
 }
 

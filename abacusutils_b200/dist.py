@@ -34,7 +34,7 @@ from .analysis import power_spectrum as ps
 from .analysis.tsc import padded_ldz
 
 
-TILE_X, TILE_Y, TILE_Z = 8, 8, 32  # deposit tile (abk_common.cuh: ABK_TX, ABK_TY, ABK_TZ)
+TILE_X, TILE_Y, TILE_Z = 8, 8, 30  # deposit tile (abk_common.cuh: ABK_TX, ABK_TY, ABK_TZ; checked in tests/test_abi.py)
 
 
 # ------------------------------------------------------------------------------------------- plan
@@ -298,12 +298,9 @@ class DistEngine:
             nchunk = int(t.item())
         if nchunk * self.world > 16:
             raise NotImplementedError(f'{nchunk} local chunks x {self.world} ranks exceed the 16 bucket segments of the tile kernel')
-        # ABK_SCATTER=2 (experiment knob): two-level multisplit bucketing, as in the single-GPU painter
-        two_level = os.environ.get('ABK_SCATTER', '1') == '2'
-        bucket_fn = lib.abk_tsc_bucket2 if two_level else lib.abk_tsc_bucket
+        bucket_fn = lib.abk_tsc_bucket
         nb = C.c_size_t()
-        check((lib.abk_tsc_bucket2_scratch_bytes if two_level else lib.abk_tsc_bucket_scratch_bytes)(
-            max(min(N, CH), 1), n, n, n, C.byref(nb)))
+        check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, CH), 1), n, n, n, C.byref(nb)))
         scan_buf = eng.scratch('bucket_scan', nb.value + 256)
         scan_ptr = C.c_void_p((scan_buf.data_ptr() + 255) & ~255)
         wrap = 0 if str(paste).upper() == 'CIC' else 1

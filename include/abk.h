@@ -104,18 +104,12 @@ int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int
  * If `wrap` is non-zero the one-shot periodic wrap (tsc.py:219-226) is applied on the fly to the
  * values that are bucketed (the input array is not modified). */
 int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles);
+/* cells per deposit tile along x, y, z (tile id = (tx * nty + ty) * ntz + tz, n?t = ceil(n? / t?)) */
+int abk_tsc_tile_shape(int *tx, int *ty, int *tz);
 int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);
 int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz,
                    double box, double offset, int wrap, void *records, uint32_t *tile_starts,
                    void *scratch, size_t scratch_bytes);
-/* Same contract and result layout as abk_tsc_bucket, produced by a two-level CTA-local multisplit (coarse tile
- * groups, then tiles) whose record writes are coalesced runs instead of one scattered 16-byte store per particle
- * (experiment; selected by ABK_SCATTER=2 in the Python layer).  Needs N*16 bytes more scratch for the intermediate
- * records: abk_tsc_bucket2_scratch_bytes(), 256-byte aligned.  Meshes with more than 2^20 tiles fall back to the
- * one-level scatter. */
-int abk_tsc_bucket2_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);
-int abk_tsc_bucket2(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int nx, int ny, int nz, double box,
-                    double offset, int wrap, void *records, uint32_t *tile_starts, void *scratch, size_t scratch_bytes);
 /* Slab mode (mesh sharded over GPUs by x-planes): only particles whose centre cell lies in planes
  * [x_lo, x_lo+nxe) (mod nx) are bucketed; tiles cover that x-range.  The number of particles that
  * fell outside is returned in *n_dropped_h (host; the call then synchronises the stream). */

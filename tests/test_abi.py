@@ -146,3 +146,18 @@ def test_header_prototypes_match_definitions_and_bindings():
     for name, sig in protos.items():
         assert _param_types(sig) == _param_types(defs[name]), name
         assert len(_param_types(sig)) == len(_lib.SIGNATURES[name][1]), name
+
+
+def test_tile_shape_matches_the_sharded_path_constants():
+    """dist.py cuts slab boundaries on tile columns and slices tile-offset tables: its constants must be the library's."""
+    import ctypes as C
+
+    from abacusutils_b200 import _lib, dist
+
+    lib = _lib.load_library()
+    tx, ty, tz = C.c_int(), C.c_int(), C.c_int()
+    assert lib.abk_tsc_tile_shape(C.byref(tx), C.byref(ty), C.byref(tz)) == 0
+    assert (tx.value, ty.value, tz.value) == (dist.TILE_X, dist.TILE_Y, dist.TILE_Z)
+    nt = C.c_int64()
+    assert lib.abk_tsc_num_tiles(100, 50, 61, C.byref(nt)) == 0
+    assert nt.value == -(-100 // tx.value) * -(-50 // ty.value) * -(-61 // tz.value)

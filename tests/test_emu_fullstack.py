@@ -33,8 +33,7 @@ def test_tsc_parallel(emu, golden, name):
 
 
 def test_tile_capacity_passes_and_variants(emu, oracle):
-    """Clustered input that overflows the per-tile record capacity (several passes per tile), and the alternative
-    deposit kernels (bits 16-18 of abk_ctx_set_tile_capacity) -- all against the oracle."""
+    """Clustered input that overflows the per-tile record capacity (several passes per tile) against the oracle."""
     from abacusutils_b200._lib import check
     from abacusutils_b200.analysis import tsc
 
@@ -45,10 +44,10 @@ def test_tile_capacity_passes_and_variants(emu, oracle):
     want = np.zeros((n, n, n), np.float32)
     oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
     try:
-        for variant in (0, 1):      # 0: walk kernel (default), 1: round-1 shared-tile kernel kept for A/B timing
-            check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 256 | (variant << 16)))
+        for cap in (256, 512):      # 7500 particles in a handful of tiles: many passes per tile
+            check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, cap))
             got = tsc.tsc_parallel(pos.copy(), (n, n, n), box, weights=w)
-            np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5, err_msg=f'variant {variant}')
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5, err_msg=f'capacity {cap}')
     finally:
         check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
 
@@ -161,54 +160,6 @@ def test_multi_segment_early_deposit_groups(emu, golden, monkeypatch, groups):
                       poles=c['poles'])
     want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
     compare_power_tables(t, want)
-
-
-@pytest.mark.parametrize('name', ['n32_ci', 'n48_log'])
-def test_two_level_bucketing(emu, golden, monkeypatch, name):
-    """ABK_SCATTER=2: the two-level multisplit bucketing (abk_tsc_bucket2) feeds the same tile deposit."""
-    from abacusutils_b200.analysis import power_spectrum as ps
-
-    monkeypatch.setenv('ABK_SCATTER', '2')
-    monkeypatch.setenv('ABK_CHUNK_MIN', '3000')        # several segments, several 4096-record chunks per segment
-    c = cases.POWER_CASES[name]
-    pos, w, pos2, w2 = cases.power_inputs(c)
-    t = ps.calc_power(pos, c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'],
-                      nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=w, pos2=pos2, w2=w2,
-                      poles=c['poles'])
-    want = {k[len(f'power/{name}/'):]: golden[k] for k in golden.files if k.startswith(f'power/{name}/')}
-    compare_power_tables(t, want)
-
-
-def test_two_level_bucketing_matches_one_level(emu):
-    """Same tile_starts and the same multiset of records per tile as abk_tsc_bucket, with wrapping and weights."""
-    import ctypes as C
-
-    import torch
-
-    rng = np.random.default_rng(9)
-    n, N, box = 96, 30001, 100.0
-    pos = torch.from_numpy((rng.random((N, 3), dtype=np.float32) * np.float32(1.2 * box) - np.float32(0.1 * box)))
-    w = torch.from_numpy(rng.random(N, dtype=np.float32))
-    nt = C.c_int64()
-    emu.lib.abk_tsc_num_tiles(n, n, n, C.byref(nt))
-    out = []
-    for fn, sz in ((emu.lib.abk_tsc_bucket, emu.lib.abk_tsc_bucket_scratch_bytes),
-                   (emu.lib.abk_tsc_bucket2, emu.lib.abk_tsc_bucket2_scratch_bytes)):
-        nb = C.c_size_t()
-        assert sz(N, n, n, n, C.byref(nb)) == 0
-        scratch = torch.zeros(nb.value + 256, dtype=torch.uint8)
-        sp = C.c_void_p((scratch.data_ptr() + 255) & ~255)
-        rec, st = torch.zeros((N, 4), dtype=torch.float32), torch.zeros(nt.value + 1, dtype=torch.int32)
-        assert fn(emu.ctx, C.c_void_p(pos.data_ptr()), C.c_void_p(w.data_ptr()), N, n, n, n, box, 0.25, 1,
-                  C.c_void_p(rec.data_ptr()), C.c_void_p(st.data_ptr()), sp, nb.value) == 0, emu.lib.abk_last_error()
-        out.append((rec.numpy(), st.numpy()))
-    (r1, s1), (r2, s2) = out
-    np.testing.assert_array_equal(s1, s2)
-    assert s1[-1] == N
-    for t in range(nt.value):
-        a = np.sort(r1[s1[t]:s1[t + 1]].view('f4,f4,f4,f4'), axis=0)
-        b = np.sort(r2[s2[t]:s2[t + 1]].view('f4,f4,f4,f4'), axis=0)
-        np.testing.assert_array_equal(a, b)
 
 
 def test_ragged_and_odd_grids(emu, golden, oracle):

@@ -41,13 +41,13 @@ def test_fuzz_tsc_parallel(emu, oracle):
                 pos[:k] = (pos[0] + rng.normal(0, box / 200, size=(k, 3))).astype(np.float32)
             pos = np.clip(pos, lo, hi).astype(np.float32)
             w = rng.random(N, dtype=np.float32) if weighted else None
-            cap, variant = int(rng.choice([0, 256, 512])), int(rng.choice([0, 0, 0, 1]))
-            check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, cap | (variant << 16)))
+            cap = int(rng.choice([0, 256, 512]))
+            check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, cap))
             got, want = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
             tsc.tsc_parallel(pos.copy(), got, box, weights=w, offset=off, wrap=wrap)
             oracle.tsc_parallel(pos.copy(), want, box, weights=w, offset=off, wrap=wrap, nthread=1)
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 + 1e-5 * np.abs(want).max(),
-                                       err_msg=f'trial {trial}: shape={shape} N={N} off={off} wrap={wrap} cap={cap} variant={variant}')
+                                       err_msg=f'trial {trial}: shape={shape} N={N} off={off} wrap={wrap} cap={cap}')
     finally:
         check(emu.lib.abk_ctx_set_tile_capacity(emu.ctx, 0))
 
