@@ -65,6 +65,7 @@ SIGNATURES = {
     'abk_partition_scratch_bytes': (_i32, [_i64, _i32, _psz]),
     'abk_partition': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _sz]),
     'abk_tsc_num_tiles': (_i32, [_i32, _i32, _i32, C.POINTER(_i64)]),
+    'abk_bench_red_rate': (_i32, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double)]),
     'abk_tsc_tile_shape': (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'abk_tsc_bucket_scratch_bytes': (_i32, [_i64, _i32, _i32, _i32, _psz]),
     'abk_tsc_bucket': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _dbl, _dbl, _i32, _vp, _vp, _vp, _sz]),
@@ -209,6 +210,18 @@ class Engine:
         self.bind_stream()
         check(self.lib.abk_ctx_profile_collect(self.ctx, ms, cnt))
         return {self.lib.abk_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(nk) if cnt[i]}
+
+    def red_rate(self, nfloats=1 << 28):
+        """Measured float-reduction rates of this GPU (1e9 adds/s): {'coalesced': rows of 32 floats, 'scattered': ...}."""
+        torch = _torch()
+        buf = torch.zeros(nfloats, dtype=torch.float32, device=self.device)
+        out = {}
+        self.bind_stream()
+        for mode, name in ((0, 'coalesced'), (1, 'scattered')):
+            r = C.c_double()
+            check(self.lib.abk_bench_red_rate(self.ctx, C.c_void_p(buf.data_ptr()), nfloats, mode, C.byref(r)))
+            out[name] = r.value
+        return out
 
     def empty(self, shape, dtype):
         return _torch().empty(shape, dtype=dtype, device=self.device)

@@ -617,6 +617,27 @@ __global__ void __launch_bounds__(256) wrap_inplace_kernel(float *__restrict__ p
     if (n_changed && changed) atomicAdd(n_changed, changed);
 }
 
+// ---- measurement helper ("micro-benchmarked peak red.global.add.f32 rate ... as the denominator") -----
+// Every warp issues `iters` float reductions of 32 lanes into `buf`: mode 0 = coalesced 32-float rows spread over the
+// buffer (what the deposit emits), mode 1 = 32 scattered cells per instruction (what one reduction per stencil point,
+// the reference's formulation, would be).
+__global__ void __launch_bounds__(256) red_rate_kernel(float *__restrict__ buf, int64_t nfloats, int iters, int mode)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nrows = nfloats / 32;
+    uint32_t h = (uint32_t)(warp * 32 + lane) * 2654435761u + 12345u;
+    for (int it = 0; it < iters; it++) {
+        if (mode == 0) {
+            const int64_t row = (warp * 7919 + (int64_t)it * nwarps) % nrows;
+            atomicAdd(buf + row * 32 + lane, 1.0f);
+        } else {
+            h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+            atomicAdd(buf + (int64_t)(h % (uint32_t)min(nfloats, (int64_t)0x7fffffff)), 1.0f);
+        }
+    }
+}
+
 // ---- particle routing for an x-slab sharded mesh -------------------------------------------------------
 // owner(p) = rank r with xsplit[r] <= cell_x(p) < xsplit[r+1], cell_x = rint(x * f32(nx/box)) mod nx (the
 // centre cell of the UNSHIFTED cloud; the half-cell-shifted cloud is handled with one more ghost plane).
@@ -804,6 +825,26 @@ extern "C" int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles)
 {
     ABK_REQUIRE(ntiles && nx > 0 && ny > 0 && nz > 0, "abk_tsc_num_tiles: bad arguments");
     *ntiles = abk_make_geom(nx, ny, nz).ntiles;
+    return ABK_OK;
+}
+
+extern "C" int abk_bench_red_rate(abk_ctx *ctx, float *buf, int64_t nfloats, int mode, double *gadds_per_s)
+{
+    ABK_REQUIRE(ctx && buf && gadds_per_s && nfloats >= 1024 && (mode == 0 || mode == 1), "abk_bench_red_rate: bad arguments");
+    const int blocks = ctx->num_sms * 8, iters = 256;
+    cudaEvent_t a, b;
+    ABK_CHECK_CUDA(cudaEventCreate(&a));
+    ABK_CHECK_CUDA(cudaEventCreate(&b));
+    red_rate_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, nfloats, iters, mode);  // warm-up
+    ABK_CHECK_CUDA(cudaEventRecord(a, ctx->stream));
+    ABK_LAUNCH(ctx, ABK_K_MISC, red_rate_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, nfloats, iters, mode));
+    ABK_CHECK_CUDA(cudaEventRecord(b, ctx->stream));
+    ABK_CHECK_CUDA(cudaEventSynchronize(b));
+    float ms = 0.0f;
+    ABK_CHECK_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *gadds_per_s = (double)blocks * 256 * iters / (ms * 1e-3) / 1e9;
     return ABK_OK;
 }
 

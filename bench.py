@@ -13,10 +13,11 @@ particles in pinned HOST memory, so the host->device copies and the device->host
 binned result are inside the timed region.  Per-kernel times come from CUDA events recorded by
 libabk on its launch stream inside the timed region (abk_ctx_profile_*).
 
---impl reference times the CPU implementation of the same path (the oracle port of the reference's
-Numba kernels, C + OpenMP on all host threads + scipy.fft) on a bounded sample of the same
-workload and reports the extrapolated full-workload number.  The unmodified reference cannot travel
-to the GPU box (pure-Python package living under /root/reference, no wheel), see DESIGN.md.
+--impl reference times the CPU implementation of the same path on a bounded sample of the same workload and reports
+the extrapolated full-workload number: the reference's OWN Numba modules (staged byte for byte under oracle/_ref/ by
+oracle/make_ref.py, NUMBA_NUM_THREADS = all host cores; cpu_baseline.kind = "reference") when they and numba are
+available, else the oracle port (C + OpenMP + scipy.fft; kind = "port").  `--cpu-full` adds ONE run at full size so the
+extrapolation can be checked.  The `parity` block compares the GPU result with the CPU result on that very sample.
 """
 
 import argparse
@@ -39,12 +40,23 @@ WORKLOAD = ('configs[2]: calc_power, 1e9 uniform random particles, Lbox=2000, nm
             'interlaced, 100 k x 10 mu bins, poles 0/2/4')
 
 
-# DRAM traffic per launch of the kernels at the default workload, from `ncu --set full` captures of this very
-# command (profiles/r1_ncu_summary.md): dram__bytes_read.sum + dram__bytes_write.sum.
-# warp instructions per launch of the tile deposit at the default workload (ncu smsp__inst_executed.sum, same captures)
-NCU_WARP_INST_CONFIG3 = {'tsc_tile_deposit': 2.4e10}
-NCU_TRAFFIC_CONFIG3 = {'tsc_tile_deposit': 25.2e9, 'tsc_bucket_scatter': 3.54e9, 'tsc_bucket_hist': 0.86e9,
-                       'normalize_field': 8.55e9}
+def ncu_metrics():
+    """Per-launch ncu numbers of the kernels at the default workload (dram bytes, warp instructions), read from
+    profiles/r2_ncu_metrics.json -- written by scripts/ncu_extract.py from an `ncu --set full` capture of this very command.
+    They are only reported while the kernel sources still hash to what was profiled."""
+    import hashlib
+
+    f = ROOT / 'profiles' / 'r2_ncu_metrics.json'
+    if not f.exists():
+        return {}
+    try:
+        d = json.loads(f.read_text())
+        h = hashlib.sha256()
+        for src in sorted((ROOT / 'abacusutils_b200' / 'csrc').glob('abk_*.cu*')):
+            h.update(src.read_bytes())
+        return d['kernels'] if d.get('csrc_sha256') == h.hexdigest() else {}
+    except Exception:
+        return {}
 
 
 def peaks():
@@ -116,24 +128,63 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(level, cfg, nthread=None):
-    """Run the CPU oracle on 1/8^level of the workload volume at equal particle density and identical
-    options (nmesh/2^level, N/8^level, L/2^level); returns (seconds, description)."""
-    from oracle import abk_oracle as O
+_REF = {}
 
-    O.build()
+
+def reference_modules():
+    """The reference's own (tsc, power_spectrum) modules with Numba on all host cores, or None (-> oracle port)."""
+    if 'mods' not in _REF:
+        _REF['mods'] = None
+        if os.environ.get('ABK_CPU_IMPL', '') != 'port':
+            try:
+                ncore = len(os.sched_getaffinity(0))
+                os.environ['NUMBA_NUM_THREADS'] = str(ncore)      # read by numba at import; the interlaced paints use it
+                from oracle import ref_shim
+
+                if ref_shim.available():
+                    import numba  # noqa: F401
+
+                    _REF['mods'] = ref_shim.load(ncore)
+                    _REF['cores'] = ncore
+            except Exception as e:  # numba missing, reference not staged, ...
+                _REF['why'] = repr(e)
+    return _REF['mods']
+
+
+def cpu_sample(level, cfg, nthread=None, keep=False):
+    """Run the CPU implementation on 1/8^level of the workload volume at equal particle density and identical
+    options (nmesh/2^level, N/8^level, L/2^level); returns (seconds, description, threads, kind, table, pos)."""
     f = 2**level
     nmesh = cfg['nmesh'] // f
     N = cfg['N'] // f**3
     L = cfg['L'] / f
     rng = np.random.default_rng(cfg['seed'])
     pos = rng.random((N, 3), dtype=np.float32) * np.float32(L)
-    nt = nthread or O.MAX_THREADS
-    t0 = time.perf_counter()
-    O.calc_power(pos, L, kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=nmesh, compensated=True, interlaced=True,
-                 poles=cfg['poles'], nthread=nt)
-    dt = time.perf_counter() - t0
-    return dt, f'1/{f**3} of the volume at equal density: N={N}, nmesh={nmesh}, L={L:g}, same options; time x {f**3}', nt
+    mods = reference_modules()
+    kw = dict(kbins=cfg['kbins'], mubins=cfg['mubins'], nmesh=nmesh, compensated=True, interlaced=True, poles=cfg['poles'])
+    if mods is not None:
+        nt = nthread or _REF['cores']
+        if not _REF.get('warm'):      # JIT-compile every kernel of the path at a tiny size with identical dtypes / options
+            tiny = rng.random((20000, 3), dtype=np.float32) * np.float32(L)
+            mods[1].calc_power(tiny, L, **dict(kw, nmesh=64), nthread=nt)
+            _REF['warm'] = True
+        work = pos.copy() if keep else pos       # the reference wraps its input in place
+        t0 = time.perf_counter()
+        tab = mods[1].calc_power(work, L, nthread=nt, **kw)
+        dt = time.perf_counter() - t0
+        kind = 'reference'
+    else:
+        from oracle import abk_oracle as O
+
+        O.build()
+        nt = nthread or O.MAX_THREADS
+        t0 = time.perf_counter()
+        tab = O.calc_power(pos, L, nthread=nt, **kw)
+        dt = time.perf_counter() - t0
+        kind = 'port'
+    desc = (f'1/{f**3} of the volume at equal density: N={N}, nmesh={nmesh}, L={L:g}, same options; time x {f**3}'
+            if level else f'full size: N={N}, nmesh={nmesh}, L={L:g}')
+    return dt, desc, nt, kind, (tab if keep else None), (pos if keep else None)
 
 
 def pick_cpu_level(cfg, budget_s):
@@ -141,13 +192,21 @@ def pick_cpu_level(cfg, budget_s):
     max_level = 0
     while cfg['nmesh'] // 2**(max_level + 1) >= 64:
         max_level += 1
-    cal_level = max(max_level, 0)
-    dt, _, _ = cpu_sample(cal_level, cfg)  # also warms page cache / OpenMP
-    dt, _, _ = cpu_sample(cal_level, cfg)
+    cal_level = min(max_level, 2)      # calibrate on a sample big enough that fixed overheads do not dominate
+    cpu_sample(cal_level, cfg)  # also warms the JIT / page cache / OpenMP
+    dt = cpu_sample(cal_level, cfg)[0]
     level = cal_level
     while level > 1 and dt * 8 ** (cal_level - (level - 1)) <= budget_s:
         level -= 1
     return level
+
+
+def cpu_kind_note(kind):
+    if kind == 'reference':
+        import numba
+
+        return f'unmodified reference modules (oracle/_ref), numba {numba.__version__}, threading layer {numba.threading_layer()}'
+    return 'oracle port (C + OpenMP + scipy.fft): ' + _REF.get('why', 'reference modules or numba not available')
 
 
 def run_reference_arm(args):
@@ -160,24 +219,27 @@ def run_reference_arm(args):
     if args.nmesh:
         cfg['nmesh'] = args.nmesh
     nsteps = args.steps + args.warmup
-    budget = min(30.0, 200.0 / max(nsteps, 1))
+    budget = min(30.0, 150.0 / max(nsteps, 1))
     level = pick_cpu_level(cfg, budget)
     times = []
-    desc = ''
-    nt = 1
+    desc, nt, kind = '', 1, 'port'
     for i in range(nsteps):
-        dt, desc, nt = cpu_sample(level, cfg)
+        dt, desc, nt, kind = cpu_sample(level, cfg)[:4]
         if i >= args.warmup:
             times.append(dt)
     scale = 8**level
     ms_full = float(np.mean(times)) * scale * 1e3
+    cpu = {'value': ms_full, 'unit': 'ms', 'cores': nt, 'kind': kind, 'sample': desc,
+           'sample_seconds': float(np.mean(times)), 'impl': cpu_kind_note(kind)}
+    if args.cpu_full:
+        dtf, descf = cpu_sample(0, cfg)[:2]
+        cpu['full_size_check'] = {'seconds': dtf, 'what': descf, 'extrapolated_over_measured': ms_full / (dtf * 1e3)}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': ms_full, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_full, 'higher_is_better': False, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD if not (args.nparticles or args.nmesh) else f'override N={cfg["N"]} nmesh={cfg["nmesh"]}'},
-        'cpu_baseline': {'value': ms_full, 'unit': 'ms', 'cores': nt, 'kind': 'port', 'sample': desc,
-                         'sample_seconds': float(np.mean(times))},
+        'cpu_baseline': cpu,
         'e2e': {'value': ms_full, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'mpart_per_s': cfg['N'] / ms_full / 1e3,
     }
@@ -194,7 +256,7 @@ def algorithmic_bytes(name, cfg, nseg, n_used_entries):
     return {
         'tsc_bucket_hist': N / nseg * 12,
         'tsc_bucket_scatter': N / nseg * (12 + 4 * w + 16),
-        'tsc_tile_deposit': N * 16 + 4 * n**3,
+        'tsc_tile_deposit': N * 12 + 4 * n**3,          # N (12 + 4 [weighted]) + 4 n^3 per painted grid
         'normalize_field': 8 * n**3,
         'cufft': 4 * n**3 + 8 * n * n * nzc,
         'power_bin': n_used_entries * 8 * 2,
@@ -275,6 +337,22 @@ def packed_leg(torch, calc_power, N, L, kw, args):
     torch.cuda.synchronize()
     return {'value': (time.perf_counter() - t0) / steps * 1e3, 'unit': 'ms', 'format': args.packed,
             'h2d_bytes_per_step': int(N * nbytes), 'n_particles': int(res.meta['N_pos']), 'steps': steps}
+
+
+def parity_block(got, want):
+    """GPU table vs CPU table of the same particles: integer mode counts bit-exact, worst relative difference of P(k,mu)
+    over the bins that hold more than the k=0 mode, worst multipole difference in units of the monopole of its k-bin."""
+    nm_g, nm_c = np.asarray(got['N_mode']), np.asarray(want['N_mode'])
+    exact = bool(np.array_equal(nm_g, nm_c) and np.array_equal(np.asarray(got['N_mode_poles']), np.asarray(want['N_mode_poles'])))
+    pg, pc = np.asarray(got['power'], 'f8'), np.asarray(want['power'], 'f8')
+    rows = nm_c.reshape(len(pc), -1).sum(axis=1) > 1
+    ok = (nm_c > 0) & rows.reshape(-1, *([1] * (pc.ndim - 1)))
+    rel = np.abs(pg - pc)[ok] / np.abs(pc)[ok]
+    poles_g, poles_c = np.asarray(got['poles'], 'f8'), np.asarray(want['poles'], 'f8')
+    p0 = np.abs(poles_c[:, 0])
+    dp = np.abs(poles_g - poles_c)[rows] / p0[rows, None]
+    return {'n_mode_exact': exact, 'max_rel_power': float(rel.max()), 'max_abs_poles_over_P0': float(dp.max()),
+            'n_bins': int(ok.sum()), 'tolerance': 'north_star: counts bit-exact, 1e-4 relative per bin'}
 
 
 def run_gpu_arm(args):
@@ -359,25 +437,53 @@ def run_gpu_arm(args):
     peak, peak_src = peaks()
     nseg = max(1, prof.get('tsc_bucket_hist', (0, 2 * args.steps))[1] // (2 * args.steps))
     n_used = used_entries(n, L, np.pi * n / L)
+    default_workload = not (args.nparticles or args.nmesh or args.clustered)
+    ncu = ncu_metrics() if default_workload else {}
     stages = {}
     for name, (tot_ms, cnt) in prof.items():
         b = algorithmic_bytes(name, cfg, nseg, n_used)
         stages[name] = {'ms_per_step': tot_ms / args.steps, 'launches_per_step': cnt / args.steps,
                         'avg_launch_ms': tot_ms / cnt,
                         'achieved_gbs': (b / (tot_ms / cnt * 1e-3) / 1e9) if b else None}
+        if name in ncu:
+            stages[name]['ncu'] = ncu[name]
     top = max(stages, key=lambda k: stages[k]['ms_per_step'])
     roof = {'bound': 'hbm', 'kernel': top, 'achieved': stages[top]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
             'frac': (stages[top]['achieved_gbs'] / peak) if stages[top]['achieved_gbs'] else None,
-            'traffic': (NCU_TRAFFIC_CONFIG3.get(top) if not (args.nparticles or args.nmesh) else None),
-            'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms}
-    if top in NCU_WARP_INST_CONFIG3 and not (args.nparticles or args.nmesh):
-        # the deposit is bound by instruction issue and LSU (ATOMS / RED) cost, not by HBM: report the issue-rate view too
+            'traffic': ncu.get(top, {}).get('dram_bytes_per_launch'),
+            'traffic_source': ('profiles/r2_ncu_metrics.json (ncu --set full of this command; kernel sources unchanged since)'
+                               if top in ncu else 'no ncu capture of the current kernel sources committed'),
+            'peak_source': peak_src, 'share_of_step': stages[top]['ms_per_step'] / ms,
+            'algorithmic_bytes_per_launch': algorithmic_bytes(top, cfg, nseg, n_used)}
+    # the deposit STAGE as SURVEY 8(d) charges it: bucketing (histogram + scan + scatter, once) + both tile deposits,
+    # against the algorithmic bytes of two painted grids that share one read of the particles
+    dep_ms = sum(stages[k]['ms_per_step'] for k in ('tsc_bucket_hist', 'tsc_bucket_scatter', 'scan', 'tsc_tile_deposit')
+                 if k in stages)
+    if dep_ms:
+        dep_bytes = N * 12 + 2 * 4 * n**3
+        roof['deposit_stage'] = {'ms': dep_ms, 'algorithmic_bytes': dep_bytes, 'achieved_gbs': dep_bytes / dep_ms / 1e6,
+                                 'frac_of_hbm': dep_bytes / dep_ms / 1e6 / peak, 'gpart_per_s': 2 * N / dep_ms / 1e6}
+    # atomic view of the deposit: the reference formulation is 27 N float adds per grid; the ceiling is the
+    # float-reduction rate of this GPU, micro-benchmarked HERE (abk_bench_red_rate: coalesced 32-float rows / scattered)
+    try:
+        red = eng.red_rate()
+        t_dep = stages['tsc_tile_deposit']['avg_launch_ms'] * 1e-3
+        roof['atomic_view'] = {'equivalent_gadds_per_s': 27 * N / t_dep / 1e9,
+                               'peak_red_coalesced_gadds_per_s': red['coalesced'], 'peak_red_scattered_gadds_per_s': red['scattered'],
+                               'frac_of_scattered_peak': 27 * N / t_dep / 1e9 / red['scattered'],
+                               'note': ('27 N / t of one tile-deposit launch against the measured red.global.add.f32 rates (coalesced '
+                                        '32-float rows; 32 scattered cells over 1 GiB, i.e. one reduction per stencil point of '
+                                        'unsorted particles): > 1 because per-cell register sums replace 27 reductions per '
+                                        'particle by 3 row reductions per 30 cells')}
+    except Exception as e:  # pragma: no cover
+        roof['atomic_view'] = {'error': repr(e)}
+    if 'warp_inst_per_launch' in ncu.get(top, {}):
+        # the deposit is bound by instruction issue / the FMA pipe, not by HBM: report the issue-rate view too
         sm_mhz = clocks.get('sm_mhz') or 1965.0
         peak_issue = 148 * 4 * sm_mhz * 1e6          # warp instructions / s: 4 schedulers per SM, 1 per clock
-        ach = NCU_WARP_INST_CONFIG3[top] / (stages[top]['avg_launch_ms'] * 1e-3)
-        roof['issue_view'] = {'warp_inst_per_launch': NCU_WARP_INST_CONFIG3[top], 'achieved_ginst_s': ach / 1e9,
-                              'peak_ginst_s': peak_issue / 1e9, 'frac': ach / peak_issue,
-                              'source': 'profiles/r1_ncu_summary.md (ncu smsp__inst_executed.sum)'}
+        ach = ncu[top]['warp_inst_per_launch'] / (stages[top]['avg_launch_ms'] * 1e-3)
+        roof['issue_view'] = {'warp_inst_per_launch': ncu[top]['warp_inst_per_launch'], 'achieved_ginst_s': ach / 1e9,
+                              'peak_ginst_s': peak_issue / 1e9, 'frac': ach / peak_issue}
 
     # ---- configs[1]: tsc_parallel of 1e8 weighted particles onto a 512^3 float32 mesh (extra, device-resident) ----
     cfg2 = None
@@ -403,16 +509,23 @@ def run_gpu_arm(args):
                 'mass_check': float(g2.sum(dtype=torch.float64).item() / (5 * w2.sum(dtype=torch.float64).item()))}
         del p2, w2, g2
 
-    # ---- CPU baseline on a bounded sample ---------------------------------------------------------------
-    cpu = None
+    # ---- CPU baseline on a bounded sample, and parity of the GPU result on that very sample ---------------
+    cpu, parity = None, None
     if not args.no_cpu:
         level = pick_cpu_level(cfg, 25.0)
-        dt, desc, nt = cpu_sample(level, cfg)
-        cpu = {'value': dt * 8**level * 1e3, 'unit': 'ms', 'cores': nt, 'kind': 'port', 'sample': desc,
-               'sample_seconds': dt}
+        dt, desc, nt, kind, tab_c, pos_c = cpu_sample(level, cfg, keep=True)
+        cpu = {'value': dt * 8**level * 1e3, 'unit': 'ms', 'cores': nt, 'kind': kind, 'sample': desc,
+               'sample_seconds': dt, 'impl': cpu_kind_note(kind)}
+        f = 2**level
+        tab_g = calc_power(pos_c, L / f, **dict(kw, nmesh=n // f))
+        parity = parity_block(tab_g, tab_c)
+        parity['sample'] = desc.split(';')[0]
+        parity['against'] = kind
+        del pos_c
+        if args.cpu_full:
+            dtf, descf = cpu_sample(0, cfg)[:2]
+            cpu['full_size_check'] = {'seconds': dtf, 'what': descf, 'extrapolated_over_measured': cpu['value'] / (dtf * 1e3)}
 
-    dep_ms = sum(stages[k]['ms_per_step'] for k in ('tsc_bucket_hist', 'tsc_bucket_scatter', 'scan', 'tsc_tile_deposit')
-                 if k in stages)
     packed_e2e = None
     if args.packed:
         packed_e2e = packed_leg(torch, calc_power, N, L, kw, args)
@@ -424,6 +537,7 @@ def run_gpu_arm(args):
                                 f'override N={N} nmesh={n} clustered={args.clustered}'),
                    'l2': 'inputs (12 GB particles, 4.3 GB grids) are larger than the 126 MB L2'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        'parity': parity,
         'stages': stages,
         'stages_note': ('per-kernel CUDA-event times; the cufft of the first grid runs on an auxiliary stream '
                         'concurrently with the tile deposit of the second grid, so their event times include the time '
@@ -450,6 +564,7 @@ def main():
     ap.add_argument('--packed', choices=['pack9', 'rvint'], default=None,
                     help='extra leg: end-to-end from packed records in pinned host memory (not the headline metric)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--cpu-full', action='store_true', help='also run the CPU implementation ONCE at full size (checks the extrapolation; ~1-2 min, ~50 GB host)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the end-to-end leg (profiling runs only)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -104,6 +104,10 @@ int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int
  * If `wrap` is non-zero the one-shot periodic wrap (tsc.py:219-226) is applied on the fly to the
  * values that are bucketed (the input array is not modified). */
 int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles);
+/* Measurement helper: float-reduction rate of this GPU in 1e9 adds/s into `buf` (device, nfloats floats, is
+ * overwritten): mode 0 = coalesced rows of 32 consecutive floats per warp instruction, mode 1 = 32 scattered cells per
+ * instruction.  Synchronises the stream. */
+int abk_bench_red_rate(abk_ctx *ctx, float *buf, int64_t nfloats, int mode, double *gadds_per_s);
 /* cells per deposit tile along x, y, z (tile id = (tx * nty + ty) * ntz + tz, n?t = ceil(n? / t?)) */
 int abk_tsc_tile_shape(int *tx, int *ty, int *tz);
 int abk_tsc_bucket_scratch_bytes(int64_t N, int nx, int ny, int nz, size_t *bytes);

@@ -1,10 +1,12 @@
 """
 Import the UNMODIFIED reference (abacusnbody.analysis.{tsc,power_spectrum}) from /root/reference.
 
-Build-container only: /root/reference does not exist on the GPU box, so nothing under
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` may call this.  It is used by
-``tests/golden/make_golden.py`` (to generate the committed fixtures) and by the ``not gpu``
-oracle-vs-reference tests, which skip when the reference tree is absent.
+/root/reference does not exist on the GPU box; there the modules staged by ``oracle/make_ref.py``
+under ``oracle/_ref/`` (git-ignored build output, byte-for-byte copies) are used instead.  Callers:
+``tests/golden/make_golden.py`` (generates the committed fixtures), the ``not gpu`` oracle-vs-reference
+tests (skip when no reference is available) and ``bench.py --impl reference`` / the ``cpu_baseline`` leg,
+which time the reference's own Numba path on the box's host cores.  Nothing under ``-m gpu`` tests or
+``smoke()`` calls this.
 
 Two shims, neither of which touches the reference sources:
   * ``abacusnbody/__init__.py`` imports a setuptools_scm-generated ``version`` module that does not
@@ -20,7 +22,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('ABK_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')   # oracle/make_ref.py: travels to the GPU box
+
+
+def _pick_root():
+    env = os.environ.get('ABK_REFERENCE_ROOT')
+    for root in ([env] if env else []) + ['/root/reference', _STAGED]:
+        if os.path.isfile(os.path.join(root, 'abacusnbody', 'analysis', 'tsc.py')):
+            return root
+    return env or '/root/reference'
+
+
+REF_ROOT = _pick_root()
 
 
 def available():

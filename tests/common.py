@@ -83,8 +83,10 @@ def compare_power_tables(got, want, rtol=RTOL, skip_dc=True, poles=None, amp=Non
     if 'poles' in want:
         assert_int_exact(got['N_mode_poles'], want['N_mode_poles'], 'N_mode_poles')
         wp, gp = np.asarray(want['poles'], 'f8')[sl], np.asarray(got['poles'], 'f8')[sl]
-        scp = (scale[sl] + floor)[:, None] * 11.0  # (2l+1) <= 11 for l <= 5
+        # absolute term: 2e-5 of the monopole of the k-bin (the reference itself moves by ~1e-6 of P0 between thread
+        # counts); where a multipole is O(P0) (anisotropic input) the relative 1e-4 is what binds
+        scp = (scale[sl] + floor)[:, None] * 2.0
         if poles is not None and len(poles) == gp.shape[1]:
-            # float32 eps * conditioning, relative to the 1e-4 * 1.1 baseline; only matters from l = 8 on
-            scp = scp * np.maximum(1.0, np.array([legendre_conditioning(l) for l in poles]) * 1.2e-3 / 11.0)[None, :]
+            # float32 eps * conditioning of the reference's power-sum evaluation; only matters from l = 8 on
+            scp = scp * np.maximum(1.0, np.array([legendre_conditioning(l) for l in poles]) * 1.2e-3 / 2.0)[None, :]
         assert_close_scaled(gp, wp, scale=scp * 0.1, rtol=rtol, what='poles')

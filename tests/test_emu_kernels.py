@@ -168,3 +168,26 @@ def test_emu_kfield_helpers(emu, name):
              poles.ctypes.data_as(C.POINTER(C.c_int32)), len(poles), P(coef))
     want = g[f'kf/{name}/expand']
     np.testing.assert_allclose(ex, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+
+
+@pytest.mark.parametrize('nranks,n', [(1, 12), (2, 12), (3, 10)])
+def test_emu_transpose_scatter_p2p(emu, nranks, n):
+    """abk_transpose_scatter_p2p (the default FFT transpose at N > 1): every 'rank' is a slab + a pencil buffer on this
+    one device, the peer pointers are plain pointers -- the kernel must leave rank r's pencil = full[:, y-range r, :]."""
+    rng = np.random.default_rng(n + nranks)
+    nzc = n // 2 + 1
+    full = (rng.standard_normal((n, n, nzc)) + 1j * rng.standard_normal((n, n, nzc))).astype(np.complex64)
+    xs = [r * n // nranks for r in range(nranks)] + [n]
+    js = [0] + sorted(rng.choice(np.arange(1, n), size=nranks - 1, replace=False).tolist()) + [n]      # uneven y split
+    nyl_max = max(js[r + 1] - js[r] for r in range(nranks))
+    pencils = [np.full(n * nyl_max * nzc, np.nan + 0j, np.complex64) for _ in range(nranks)]
+    peers = (vp * nranks)(*[p.ctypes.data for p in pencils])
+    jsp = (C.c_int64 * (nranks + 1))(*js)
+    for r in range(nranks):
+        slab = np.ascontiguousarray(full[xs[r]:xs[r + 1]])
+        emu.call('abk_transpose_scatter_p2p', emu.ctx, P(slab), peers, C.c_int64(xs[r + 1] - xs[r]), C.c_int64(n), C.c_int64(nzc),
+                 nranks, jsp, C.c_int64(xs[r]))
+    for r in range(nranks):
+        nyl = js[r + 1] - js[r]
+        got = pencils[r][: n * nyl * nzc].reshape(n, nyl, nzc)
+        np.testing.assert_array_equal(got, full[:, js[r]:js[r + 1], :])

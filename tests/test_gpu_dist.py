@@ -76,3 +76,38 @@ def test_sharded_multi_rank_vs_reference(golden, tmp_path, world, name, reroute)
     pre = f'power/{name}/'
     want = {k[len(pre):]: golden[k] for k in golden.files if k.startswith(pre)}
     compare_power_tables(got, want)
+
+
+@pytest.mark.parametrize('nranks,n', [(1, 24), (2, 24), (3, 20), (8, 64)])
+def test_transpose_scatter_p2p_virtual_ranks(nranks, n):
+    """The fused pack + peer-store transpose kernel (abk_transpose_scatter_p2p, the default at N > 1) on ONE GPU: every
+    virtual rank owns an x-slab and a pencil buffer on this device, so the 'peer' stores are local -- the indexing (uneven
+    y ranges, x offsets, row strides) is exactly what runs over NVLink."""
+    import ctypes as C
+
+    import torch
+
+    from abacusutils_b200._lib import Engine, check
+
+    eng = Engine.get(0)
+    eng.bind_stream()
+    g = torch.Generator(device='cuda')
+    g.manual_seed(n * 10 + nranks)
+    nzc = n // 2 + 1
+    full = torch.view_as_complex(torch.randn((n, n, nzc, 2), device='cuda', generator=g))
+    xs = [r * n // nranks for r in range(nranks)] + [n]
+    rng = np.random.default_rng(nranks)
+    js = [0] + sorted(rng.choice(np.arange(1, n), size=nranks - 1, replace=False).tolist()) + [n]
+    nyl_max = max(js[r + 1] - js[r] for r in range(nranks))
+    pencils = [torch.full((n * nyl_max * nzc,), float('nan'), dtype=torch.complex64, device='cuda') for _ in range(nranks)]
+    peers = (C.c_void_p * nranks)(*[p.data_ptr() for p in pencils])
+    jsp = (C.c_int64 * (nranks + 1))(*js)
+    for r in range(nranks):
+        slab = full[xs[r]:xs[r + 1]].contiguous()
+        check(eng.lib.abk_transpose_scatter_p2p(eng.ctx, C.c_void_p(slab.data_ptr()), peers, xs[r + 1] - xs[r], n, nzc, nranks, jsp,
+                                                xs[r]))
+    torch.cuda.synchronize()
+    for r in range(nranks):
+        nyl = js[r + 1] - js[r]
+        got = pencils[r][: n * nyl * nzc].view(n, nyl, nzc)
+        assert torch.equal(got, full[:, js[r]:js[r + 1], :]), f'rank {r}'

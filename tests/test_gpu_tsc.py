@@ -260,3 +260,20 @@ def test_two_d_grids(tsc, oracle, name):
     assert np.isclose(dens.sum(dtype='f8'), len(pos) if w is None else w.sum(dtype='f8'), rtol=1e-6)
     d2 = tsc.tsc_parallel(pos[:, :2].copy(), c['shape'], c['box'], weights=w, offset=c['offset'])
     assert d2.shape == c['shape'] and np.allclose(d2, dens, rtol=1e-6, atol=1e-7)
+
+
+def test_clustered_grid_large(tsc, oracle):
+    """2e6 clustered particles (dense cells: hundreds of particles per cell, many capacity passes per tile) + weights on a
+    160 x 96 x 200 grid (ragged tiles on every axis) against the oracle, cell by cell."""
+    rng = np.random.default_rng(12)
+    box, shape, N = 300.0, (160, 96, 200), 2_000_000
+    centers = rng.random((40, 3)) * box
+    pos = ((centers[rng.integers(0, 40, N)] + rng.standard_normal((N, 3)) * 2.0) % box).astype(np.float32)
+    pos = np.minimum(pos, np.nextafter(np.float32(box), np.float32(0)))
+    w = rng.random(N, dtype=np.float32)
+    got = np.zeros(shape, np.float32)
+    want = np.zeros(shape, np.float32)
+    tsc.tsc_parallel(pos.copy(), got, box, weights=w)
+    oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
+    assert want.max() > 200 * want.mean()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * max(1.0, float(want.max()) * 1e-2))
