@@ -605,7 +605,57 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
 
 
 # ------------------------------------------------------------------------------------------- bench (N > 1)
-def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
+def parity_at_world(parity_block, world, rank, device):
+    """Parity evidence AT THIS WORLD SIZE for bench.py's multi-GPU line: the sharded pipeline (particle exchange, ghost
+    planes, peer-memory transpose, pencil binning, all-reduce) on (a) three committed outputs of the unmodified reference
+    (tests/golden/reference_runs.npz: weighted auto, cross, default bins) and (b) 1e7 uniform particles on a 256^3 mesh
+    against the single-GPU pipeline on rank 0.  Every rank passes a strided share of the catalogue."""
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    from .analysis import power_spectrum as single
+
+    root = Path(__file__).resolve().parent.parent
+    out = {'world': world, 'cases': {}}
+    gold_dir = root / 'tests' / 'golden'
+    if (gold_dir / 'reference_runs.npz').exists():
+        if str(gold_dir) not in sys.path:
+            sys.path.insert(0, str(gold_dir))
+        import cases
+
+        gold = np.load(gold_dir / 'reference_runs.npz')
+        for name in ('n32_ci', 'n32_cross_ci', 'n40_defaults'):
+            c = cases.POWER_CASES[name]
+            pos, w, pos2, w2 = cases.power_inputs(c)
+            sh = lambda a: None if a is None else np.ascontiguousarray(a[rank::world])      # noqa: E731
+            t = calc_power(sh(pos), c['L'], kbins=c['kbins'], mubins=c['mubins'], k_max=c.get('k_max'), logk=c['logk'], paste='TSC',
+                           nmesh=c['nmesh'], compensated=c['compensated'], interlaced=c['interlaced'], w=sh(w), pos2=sh(pos2),
+                           w2=sh(w2), poles=c['poles'])
+            pre = f'power/{name}/'
+            want = {k[len(pre):]: gold[k] for k in gold.files if k.startswith(pre)}
+            amp = None
+            if pos2 is not None:      # cross-spectrum of independent catalogues: a near-zero residual of the auto-power scale
+                amp = np.full(np.asarray(want['power']).shape[0], float(np.abs(np.asarray(want['power'])).max()))
+            out['cases'][name + ' (vs reference golden)'] = parity_block(t, want, amp=amp)
+    # (b) a larger mesh: every plane / pencil split is ragged for world = 3, 5, 6, 7 and even for 2, 4, 8
+    N, L, n = 10_000_000, 1000.0, 256
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(77)
+    full = torch.rand((N, 3), device=device, dtype=torch.float32, generator=gen) * L      # same catalogue on every rank
+    kw = dict(kbins=100, mubins=10, nmesh=n, compensated=True, interlaced=True, poles=[0, 2, 4])
+    t = calc_power(full[rank::world].contiguous(), L, **kw)
+    if rank == 0:
+        ref = single.calc_power(full, L, **kw)
+        out['cases']['1e7 particles, nmesh 256 (vs single-GPU pipeline on rank 0)'] = parity_block(t, ref)
+    del full
+    oks = [v['n_mode_exact'] and v['max_rel_power'] < 1e-4 and v['max_abs_poles_over_P0'] < 1e-4 for v in out['cases'].values()]
+    out['ok'] = bool(all(oks)) if oks else None
+    return out
+
+
+def bench_main(args, cfg, metric, workload, ClockSampler, peaks, parity_block=None):
     """bench.py's multi-GPU arm: strong scaling of the configs[2] workload over the ranks of one node."""
     import os
 
@@ -677,6 +727,14 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
         d2h = sum(np.asarray(res_h[k]).nbytes for k in ('power', 'N_mode', 'k_avg', 'poles', 'N_mode_poles'))
         e2e = {'value': float(t.item()), 'unit': 'ms', 'h2d_bytes_per_step': int(N * 12), 'd2h_bytes_per_step': int(d2h),
                'host_memory': 'pinned' if pinned else 'pageable', 'steps': e2e_steps}
+    parity = None
+    if parity_block is not None:
+        try:
+            pos = None
+            torch.cuda.empty_cache()
+            parity = parity_at_world(parity_block, world, rank, eng.device)
+        except Exception as e:      # evidence must not be lost silently: the failure goes into the line
+            parity = {'world': world, 'ok': False, 'error': repr(e)}
     if rank == 0:
         peak, peak_src = peaks()
         stages = {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps} for k, v in prof.items()}
@@ -691,7 +749,7 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks):
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * world),
             'roofline': {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
                          'peak_source': peak_src, 'note': 'per-kernel roofline is reported by the N=1 run'},
-            'cpu_baseline': None, 'stages': stages, 'mpart_per_s': N / float(ms.item()) / 1e3,
+            'cpu_baseline': None, 'parity': parity, 'stages': stages, 'mpart_per_s': N / float(ms.item()) / 1e3,
             'N_mode_total': int(np.asarray(res['N_mode']).sum()),
         }
         print(json.dumps(line))
