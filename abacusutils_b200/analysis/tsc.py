@@ -47,6 +47,25 @@ def _validate_npartition(npartition, n1d, nthread):
         raise ValueError(f'npartition {npartition} not divisible by 2')
 
 
+def _wrap_caller_array(pos, box):
+    """One-shot periodic wrap of the caller's array (NumPy or torch, any float dtype), changed entries only:
+    ``>= box -> -= box``, ``< 0 -> += box``, evaluated in float64 and stored in the array's dtype (tsc.py:219-226)."""
+    if is_torch_tensor(pos):
+        import torch
+
+        hi, lo = pos >= box, pos < 0
+        if bool(hi.any()):
+            pos[hi] = (pos[hi].to(torch.float64) - box).to(pos.dtype)
+        if bool(lo.any()):
+            pos[lo] = (pos[lo].to(torch.float64) + box).to(pos.dtype)
+        return
+    hi, lo = pos >= box, pos < 0
+    if hi.any():
+        pos[hi] = (pos[hi].astype(np.float64) - box).astype(pos.dtype)
+    if lo.any():
+        pos[lo] = (pos[lo].astype(np.float64) + box).astype(pos.dtype)
+
+
 def padded_ldz(nz):
     """Row length (floats) of the in-place R2C layout."""
     return 2 * (nz // 2 + 1)
@@ -136,26 +155,18 @@ def tsc_parallel(pos, densgrid, box, weights=None, nthread=-1, wrap=True, nparti
         pos_d[:, :2] = pos_in[:, :2]
 
     if wrap and N > 0:
-        # tsc.py:171-173: the caller's array is wrapped in place
+        # tsc.py:171-173: the caller's array is wrapped in place.  The float32 device copy is wrapped by the kernel (that is
+        # what gets painted); the CALLER's array is then updated entry by entry, in its own dtype and only where a value
+        # lies outside [0, box) -- like _wrap_inplace (tsc.py:219-226), which never touches in-range entries.
         flag = eng.zeros((1,), torch.int64)
         check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(pos_d), N, float(box), ptr(flag)))
         changed = int(flag.item())
-        if two_d and pos.shape[1] == 3 and N > 0:
-            # the reference wraps every column of the caller's array, also an unused third one
-            zcol = pos_in[:, 2].contiguous().view(-1, 1).repeat(1, 3).contiguous()
-            flag2 = eng.zeros((1,), torch.int64)
-            check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(zcol), N, float(box), ptr(flag2)))
-            changed += int(flag2.item())
-            pos_back = torch.cat([pos_d[:, :2], zcol[:, :1]], dim=1)
-        elif two_d:
-            pos_back = pos_d[:, :2]
-        else:
-            pos_back = pos_d
-        if changed and pos_back is not pos:
-            if on_device:
-                pos.copy_(pos_back.to(pos.dtype))
-            else:
-                np.copyto(pos, pos_back.cpu().numpy().astype(pos.dtype, copy=False))
+        if two_d and pos.shape[1] == 3:
+            # the reference wraps every column of the caller's array, also the third one a 2-D grid never reads
+            zc = pos_in[:, 2]
+            changed += int(((zc >= box) | (zc < 0)).sum().item())
+        if changed and pos_d is not pos:
+            _wrap_caller_array(pos, float(box))
 
     # ---- grid on the device -------------------------------------------------------------------------
     grid_is_cuda = user_supplied_grid and is_torch_tensor(densgrid) and densgrid.is_cuda

@@ -56,9 +56,26 @@ struct abk_ctx {
 void abk_prof_begin(abk_ctx *ctx, int id);
 void abk_prof_end(abk_ctx *ctx);
 
-// launch wrapper: optional event pair around the launch, launch counter, error check
+// Makes the context's device current for the lifetime of the guard and restores the caller's device afterwards, so a
+// context of cuda:1 can be used while cuda:0 is current (its streams and buffers belong to device 1).
+struct abk_device_guard {
+    int prev = -1, dev;
+    explicit abk_device_guard(int device) : dev(device)
+    {
+        if (dev < 0) return;  // null context: the entry point reports the error itself
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~abk_device_guard()
+    {
+        if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
+// launch wrapper: device guard, optional event pair around the launch, launch counter, error check
 #define ABK_LAUNCH(ctx, id, ...)                 \
     do {                                         \
+        abk_device_guard _guard((ctx)->device);  \
         if ((ctx)->prof_on) abk_prof_begin((ctx), (id)); \
         __VA_ARGS__;                             \
         if ((ctx)->prof_on) abk_prof_end((ctx)); \

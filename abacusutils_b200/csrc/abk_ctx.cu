@@ -24,7 +24,7 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
     int ndev = 0;
     ABK_CHECK_CUDA(cudaGetDeviceCount(&ndev));
     ABK_REQUIRE(device >= 0 && device < ndev, "abk_ctx_create: device %d out of range (%d visible)", device, ndev);
-    ABK_CHECK_CUDA(cudaSetDevice(device));
+    abk_device_guard guard(device);  // the caller's current device is restored on return
     cudaDeviceProp prop;
     ABK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -56,8 +56,9 @@ extern "C" int abk_ctx_create(int device, abk_ctx **out)
 
 extern "C" int abk_ctx_destroy(abk_ctx *ctx)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     if (!ctx) return ABK_OK;
-    cudaSetDevice(ctx->device);
+    abk_device_guard guard(ctx->device);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     delete ctx;
     return ABK_OK;
@@ -98,6 +99,7 @@ void abk_prof_end(abk_ctx *ctx)
 
 extern "C" int abk_ctx_profile_enable(abk_ctx *ctx, int on)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     ctx->prof_on = on ? 1 : 0;
     return ABK_OK;
@@ -110,6 +112,7 @@ extern "C" const char *abk_kernel_name(int id) { return (id >= 0 && id < ABK_K_C
 // count to n_h[id] (arrays of abk_kernel_count() entries, NOT zeroed here), and clears the records.
 extern "C" int abk_ctx_profile_collect(abk_ctx *ctx, double *ms_h, int64_t *n_h)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && ms_h && n_h, "abk_ctx_profile_collect: null argument");
     ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < ctx->prof_n; i++) {
@@ -133,6 +136,7 @@ extern "C" int abk_ctx_profile_collect(abk_ctx *ctx, double *ms_h, int64_t *n_h)
 
 extern "C" int abk_ctx_set_stream(abk_ctx *ctx, void *stream)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     ctx->stream = (cudaStream_t)stream;
     return ABK_OK;
@@ -140,6 +144,7 @@ extern "C" int abk_ctx_set_stream(abk_ctx *ctx, void *stream)
 
 extern "C" int abk_ctx_sync(abk_ctx *ctx)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     ABK_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
     return ABK_OK;
@@ -149,6 +154,7 @@ extern "C" int64_t abk_ctx_launch_count(abk_ctx *ctx) { return ctx ? ctx->launch
 
 extern "C" int abk_ctx_set_scheme(abk_ctx *ctx, int scheme)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     ABK_REQUIRE(scheme == 0 || scheme == 1, "unknown mass-assignment scheme %d (0 = TSC, 1 = CIC)", scheme);
     ctx->scheme = scheme;
@@ -157,6 +163,7 @@ extern "C" int abk_ctx_set_scheme(abk_ctx *ctx, int scheme)
 
 extern "C" int abk_ctx_set_weight_scale(abk_ctx *ctx, double scale)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     ABK_REQUIRE(scale == scale && scale != 0.0, "weight scale must be a non-zero number");
     ctx->wscale = (float)scale;
@@ -165,6 +172,7 @@ extern "C" int abk_ctx_set_weight_scale(abk_ctx *ctx, double scale)
 
 extern "C" int abk_ctx_set_tile_capacity(abk_ctx *ctx, int capacity)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx != nullptr, "null context");
     const int cap = capacity & 0xffff;
     ABK_REQUIRE(cap == 0 || (cap >= 256 && cap <= 12288), "tile capacity %d out of range", cap);

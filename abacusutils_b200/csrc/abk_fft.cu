@@ -39,6 +39,7 @@ static int make_handle(cufftHandle *h, int rank, long long *n, long long *inembe
 extern "C" int abk_rfft3_plan_create(abk_ctx *ctx, int64_t nx, int64_t ny, int64_t nz, abk_fft_plan **plan,
                                      size_t *work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan && work_bytes && nx > 0 && ny > 0 && nz > 0, "abk_rfft3_plan_create: bad arguments");
     ABK_CHECK_CUDA(cudaSetDevice(ctx->device));
     abk_fft_plan *p = new abk_fft_plan();
@@ -62,6 +63,7 @@ extern "C" int abk_rfft3_plan_create(abk_ctx *ctx, int64_t nx, int64_t ny, int64
 extern "C" int abk_fft_yz_plan_create(abk_ctx *ctx, int64_t nplanes, int64_t ny, int64_t nz, abk_fft_plan **plan,
                                       size_t *work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan && work_bytes && nplanes > 0 && ny > 0 && nz > 0, "abk_fft_yz_plan_create: bad arguments");
     ABK_CHECK_CUDA(cudaSetDevice(ctx->device));
     abk_fft_plan *p = new abk_fft_plan();
@@ -83,6 +85,7 @@ extern "C" int abk_fft_yz_plan_create(abk_ctx *ctx, int64_t nplanes, int64_t ny,
 extern "C" int abk_fft_x_plan_create(abk_ctx *ctx, int64_t nx, int64_t nrows, int64_t nzc, abk_fft_plan **plan,
                                      size_t *work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan && work_bytes && nx > 0 && nrows > 0 && nzc > 0, "abk_fft_x_plan_create: bad arguments");
     ABK_CHECK_CUDA(cudaSetDevice(ctx->device));
     abk_fft_plan *p = new abk_fft_plan();
@@ -115,6 +118,7 @@ static int prep(abk_ctx *ctx, abk_fft_plan *plan, cufftHandle h, void *work, siz
 
 extern "C" int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, void *work, size_t work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan && plan->kind == 0, "abk_rfft3_exec: not a 3-D plan");
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;
@@ -127,6 +131,7 @@ extern "C" int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, voi
 
 extern "C" int abk_irfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, void *work, size_t work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan && plan->kind == 0, "abk_irfft3_exec: not a 3-D plan");
     if (!plan->has_inv) {
         ABK_CHECK_CUDA(cudaSetDevice(ctx->device));
@@ -152,6 +157,7 @@ extern "C" int abk_irfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, vo
 
 extern "C" int abk_fft_exec_generic(abk_ctx *ctx, abk_fft_plan *plan, void *data, void *work, size_t work_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && plan, "abk_fft_exec_generic: null argument");
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;

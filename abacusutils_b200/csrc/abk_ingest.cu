@@ -157,6 +157,7 @@ int64_t p9_blocks(int64_t nrec) { return (nrec + P9_BLOCK - 1) / P9_BLOCK; }
 extern "C" int abk_unpack_rvint(abk_ctx *ctx, const int32_t *intdata, int64_t N, double boxsize, void *posout, void *velout,
                                 int out_f64)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && N >= 0 && (N == 0 || intdata), "abk_unpack_rvint: bad arguments");
     if (N == 0 || (!posout && !velout)) return ABK_OK;
     const int64_t n3 = 3 * N;
@@ -184,6 +185,7 @@ extern "C" int abk_pack9_scratch_bytes(int64_t nrec, size_t *bytes)
 extern "C" int abk_pack9_count(abk_ctx *ctx, const uint8_t *data, int64_t nrec, void *scratch, size_t scratch_bytes,
                                int64_t *nheaders_h)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && nheaders_h && nrec >= 0, "abk_pack9_count: bad arguments");
     *nheaders_h = 0;
     if (nrec == 0) return ABK_OK;
@@ -209,6 +211,7 @@ extern "C" int abk_pack9_count(abk_ctx *ctx, const uint8_t *data, int64_t nrec, 
 extern "C" int abk_pack9_decode(abk_ctx *ctx, const uint8_t *data, int64_t nrec, double boxsize, double velzspace_to_kms,
                                 const void *scratch, void *hdr_tab, int64_t nheaders, void *posout, void *velout, int out_f64)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && nrec >= 0 && nheaders >= 0 && nheaders <= nrec, "abk_pack9_decode: bad arguments");
     if (nrec == 0) return ABK_OK;
     ABK_REQUIRE(data && scratch && (nheaders == 0 || hdr_tab), "abk_pack9_decode: null data/scratch/header table");
@@ -238,6 +241,7 @@ extern "C" int abk_pack9_decode(abk_ctx *ctx, const uint8_t *data, int64_t nrec,
 extern "C" int abk_unpack_pids(abk_ctx *ctx, const uint64_t *packed, int64_t N, double box, int64_t ppd, int64_t *pid,
                                void *lagr_pos, int16_t *lagr_idx, uint8_t *tagged, void *density, int out_f64)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && N >= 0 && (N == 0 || packed) && ppd > 0, "abk_unpack_pids: bad arguments");
     if (N == 0 || (!pid && !lagr_pos && !lagr_idx && !tagged && !density)) return ABK_OK;
     int64_t blocks = (N + 256 * 4 - 1) / (256 * 4);

@@ -211,6 +211,7 @@ int blocks_for(const abk_ctx *ctx, int64_t nrows)
 
 extern "C" int abk_delta_mu2(abk_ctx *ctx, const void *delta, void *out, int n)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && delta && out && n > 0 && n <= 32767, "abk_delta_mu2: bad arguments");
     ABK_LAUNCH(ctx, ABK_K_MISC, delta_mu2_kernel<<<blocks_for(ctx, (int64_t)n * n), 256, 0, ctx->stream>>>(
                                     (const float2 *)delta, (float2 *)out, n, n / 2 + 1));
@@ -219,6 +220,7 @@ extern "C" int abk_delta_mu2(abk_ctx *ctx, const void *delta, void *out, int n)
 
 extern "C" int abk_smoothing(abk_ctx *ctx, float *out, int n, double L, double R)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && out && n > 0 && n <= 32767 && L > 0, "abk_smoothing: bad arguments");
     const float dk = (float)(2.0 * M_PI / L);
     const float dk2 = dk * dk;
@@ -230,6 +232,7 @@ extern "C" int abk_smoothing(abk_ctx *ctx, float *out, int n, double L, double R
 extern "C" int abk_expand_poles_to_3d(abk_ctx *ctx, float *out, int n, double L, const float *k_ell, const float *P_ell,
                                       int Nk, const int32_t *poles_h, int Np, const float *coef)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && out && k_ell && P_ell && coef && poles_h && n > 0 && n <= 32767 && Nk >= 2 && Np >= 1 && Np <= ABK_MAX_POLES,
                 "abk_expand_poles_to_3d: bad arguments");
     ExpandArgs A;
@@ -250,6 +253,7 @@ extern "C" int abk_bin_kppi(abk_ctx *ctx, const void *weights, int weights_f64, 
                             int Nk, const double *piedges2, int Npi, int kperp_f32, unsigned long long *counts,
                             double *sum_w)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && weights && kedges2 && piedges2 && counts && sum_w, "abk_bin_kppi: null argument");
     ABK_REQUIRE(n > 0 && n <= 32767 && ldz >= n / 2 + 1, "abk_bin_kppi: bad mesh (n=%d, ldz=%lld)", n, (long long)ldz);
     ABK_REQUIRE(Nk >= 1 && Npi >= 1 && (int64_t)Nk * Npi < ((int64_t)1 << 28), "abk_bin_kppi: bad bin counts");

@@ -662,6 +662,7 @@ int check_mesh(const abk_kmesh &M)
 extern "C" int abk_normalize_field(abk_ctx *ctx, float *grid, int64_t nx, int64_t ny, int64_t nz, int64_t ldz,
                                    double size_total, double tot_weight)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && grid && nx > 0 && ny > 0 && nz > 0 && ldz >= nz, "abk_normalize_field: bad arguments");
     ABK_REQUIRE(tot_weight != 0.0, "abk_normalize_field: total weight is zero");
     const float norm = (float)(size_total / tot_weight);  // power_spectrum.py:893
@@ -680,6 +681,7 @@ extern "C" int abk_normalize_field(abk_ctx *ctx, float *grid, int64_t nx, int64_
 extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
                                     float scale)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && mesh_h && f, "abk_field_fft_finish: null argument");
     int rc = check_mesh(*mesh_h);
     if (rc) return rc;
@@ -698,6 +700,7 @@ extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void 
 
 extern "C" int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float *out, int64_t size)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && f1 && out && size >= 0, "abk_raw_power: bad arguments");
     if (size == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_RAW_POWER, raw_power_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>((const float2 *)f1, (const float2 *)f2, out, size));
@@ -706,6 +709,7 @@ extern "C" int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float
 
 extern "C" int abk_real_to_complex(abk_ctx *ctx, const float *in, void *out, int64_t size)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && in && out && size >= 0, "abk_real_to_complex: bad arguments");
     if (size == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_MISC, real_to_complex_kernel<<<grid_for(ctx, size, 256, 16), 256, 0, ctx->stream>>>(in, (float2 *)out, size));
@@ -714,6 +718,7 @@ extern "C" int abk_real_to_complex(abk_ctx *ctx, const float *in, void *out, int
 
 extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && R, "abk_power_bin: null argument");
     int rc = check_mesh(R->mesh);
     if (rc) return rc;
@@ -822,6 +827,7 @@ extern "C" int abk_power_bin_scratch_bytes(int Nk, int Nmu, int Np, size_t *byte
 extern "C" int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_t nplanes, int64_t ny, int64_t nz,
                               int64_t ldz)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && dst && src && nplanes >= 0 && ny > 0 && nz > 0 && ldz >= nz, "abk_add_planes: bad arguments");
     if (nplanes == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_ADD_PLANES,
@@ -832,6 +838,7 @@ extern "C" int abk_add_planes(abk_ctx *ctx, float *dst, const float *src, int64_
 extern "C" int abk_transpose_scatter_p2p(abk_ctx *ctx, const void *slab, void *const *peer_pencils_h, int64_t nxl,
                                          int64_t ny, int64_t nzc, int nranks, const int64_t *jsplit_h, int64_t x_lo)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && slab && peer_pencils_h && nxl >= 0 && ny > 0 && nzc > 0 && nranks > 0 && nranks <= MAX_RANKS && jsplit_h,
                 "abk_transpose_scatter_p2p: bad arguments");
     ABK_REQUIRE(jsplit_h[0] == 0 && jsplit_h[nranks] == ny, "abk_transpose_scatter_p2p: jsplit must run from 0 to ny");
@@ -851,6 +858,7 @@ extern "C" int abk_transpose_scatter_p2p(abk_ctx *ctx, const void *slab, void *c
 extern "C" int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf, int64_t nxl, int64_t ny, int64_t nzc,
                                   int nranks, const int64_t *jsplit_h)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && slab && sendbuf && nxl >= 0 && ny > 0 && nzc > 0 && nranks > 0 && nranks <= MAX_RANKS && jsplit_h,
                 "abk_transpose_pack: bad arguments");
     ABK_REQUIRE(jsplit_h[0] == 0 && jsplit_h[nranks] == ny, "abk_transpose_pack: jsplit must run from 0 to ny");

@@ -747,6 +747,7 @@ int grid_for(const abk_ctx *ctx, int64_t work_items, int threads, int per_sm)
 // ==============================================================================================
 extern "C" int abk_wrap_inplace(abk_ctx *ctx, float *pos, int64_t N, double box, int64_t *n_changed_dev)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && (pos || N == 0) && N >= 0, "abk_wrap_inplace: bad arguments");
     if (N == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_WRAP, wrap_inplace_kernel<<<grid_for(ctx, 3 * N, 256, 16), 256, 0, ctx->stream>>>(pos, 3 * N, box,
@@ -765,6 +766,7 @@ extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int
                              int coord, float *out_pos, float *out_w, int64_t *out_starts, void *scratch,
                              size_t scratch_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && out_starts && npart > 0 && N >= 0 && coord >= 0 && coord < 3, "abk_partition: bad arguments");
     ABK_REQUIRE(N < (int64_t)1 << 32, "abk_partition: N=%lld exceeds 2^32-1", (long long)N);
     size_t need;
@@ -792,6 +794,7 @@ extern "C" int abk_route_particles(abk_ctx *ctx, const float *pos, const float *
                                    int wrap, int nranks, const int32_t *xsplit_h, void *records_out,
                                    int64_t *counts_h)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && (pos || N == 0) && N >= 0 && nranks >= 1 && nranks <= 64 && xsplit_h && counts_h,
                 "abk_route_particles: bad arguments");
     ABK_REQUIRE(xsplit_h[0] == 0 && xsplit_h[nranks] == nx, "abk_route_particles: xsplit must run from 0 to nx");
@@ -830,6 +833,7 @@ extern "C" int abk_tsc_num_tiles(int nx, int ny, int nz, int64_t *ntiles)
 
 extern "C" int abk_bench_red_rate(abk_ctx *ctx, float *buf, int64_t nfloats, int mode, double *gadds_per_s)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && buf && gadds_per_s && nfloats >= 1024 && (mode == 0 || mode == 1), "abk_bench_red_rate: bad arguments");
     const int blocks = ctx->num_sms * 8, iters = 256;
     cudaEvent_t a, b;
@@ -895,6 +899,7 @@ extern "C" int abk_tsc_bucket(abk_ctx *ctx, const float *pos, const float *w, in
                               double box, double offset, int wrap, void *records, uint32_t *tile_starts,
                               void *scratch, size_t scratch_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket: null argument");
     TscParams P;
     int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, 0, nx);
@@ -907,6 +912,7 @@ extern "C" int abk_tsc_bucket_slab(abk_ctx *ctx, const float *pos, const float *
                                    void *records, uint32_t *tile_starts, void *scratch, size_t scratch_bytes,
                                    unsigned long long *n_dropped_h)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && records && tile_starts && (pos || N == 0), "abk_tsc_bucket_slab: null argument");
     TscParams P;
     int rc = make_params(ctx, P, nx, ny, nz, box, offset, wrap, x_lo, nxe);
@@ -928,6 +934,7 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
                                      float *grid, int nx, int ny, int nz, int64_t ldz, double box, double offset,
                                      double bucket_offset, int slab, int x_lo, int nxe)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && grid && nseg >= 1 && nseg <= ABK_MAX_SEGMENTS, "abk_tsc_deposit_tiles: bad arguments");
     ABK_REQUIRE(ldz >= nz, "ldz %lld < nz %d", (long long)ldz, nz);
     ABK_REQUIRE(slab || (x_lo == 0 && nxe == nx), "abk_tsc_deposit_tiles: a periodic (non-slab) grid needs x_lo=0, nxe=nx");
@@ -986,6 +993,7 @@ extern "C" int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, i
                                int nz, int64_t ldz, double box, double offset, int wrap, void *scratch,
                                size_t scratch_bytes)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && grid && (pos || N == 0) && N >= 0, "abk_tsc_deposit: bad arguments");
     if (N == 0) return ABK_OK;
     size_t need;
@@ -1025,6 +1033,7 @@ extern "C" int abk_tsc_deposit(abk_ctx *ctx, const float *pos, const float *w, i
 extern "C" int abk_tsc_deposit_naive(abk_ctx *ctx, const float *pos, const float *w, int64_t N, float *grid, int nx,
                                      int ny, int nz, int64_t ldz, double box, double offset, int wrap)
 {
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && grid && (pos || N == 0) && N >= 0, "abk_tsc_deposit_naive: bad arguments");
     if (N == 0) return ABK_OK;
     TscParams P;

@@ -320,6 +320,7 @@ inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp{10, 0, 4, 227 * 1024}; return cudaSuccess; }
 template <class T>
 inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)std::malloc(n); return cudaSuccess; }

@@ -238,3 +238,33 @@ def test_cic_serial(emu):
         assert cic_serial(pos, dens, c['L'], weights=w) is None
         field = dens * np.float32(n**3 / len(pos)) - 1       # get_field normalises by len(pos) (power_spectrum.py:856)
         np.testing.assert_allclose(field, g[f'field/{name}'], rtol=1e-4, atol=1e-5)
+
+
+def test_wrap_writes_back_only_changed_entries_in_callers_dtype(emu):
+    """tsc_parallel(wrap=True) mutates the caller's positions like _wrap_inplace (tsc.py:219-226): only out-of-range
+    entries change, in the array's own dtype -- a float64 catalogue is not rounded through float32 (advisor finding)."""
+    from abacusutils_b200.analysis import tsc
+
+    rng = np.random.default_rng(8)
+    box = 100.0
+    with pytest.warns(UserWarning):
+        pos = rng.random((500, 3)) * box                      # float64, values not representable in float32
+        pos[7, 1] += box
+        pos[11, 2] -= box
+        before = pos.copy()
+        tsc.tsc_parallel(pos, 16, box)
+    changed = pos != before
+    assert changed.sum() == 2 and changed[7, 1] and changed[11, 2]
+    assert pos[7, 1] == before[7, 1] - box and pos[11, 2] == before[11, 2] + box
+    # float32 input: wrapped values are float32(float64(v) -+ box), untouched entries bit-identical
+    p32 = (rng.random((300, 3)) * box).astype(np.float32)
+    p32[3, 0] += np.float32(box)
+    b32 = p32.copy()
+    tsc.tsc_parallel(p32, 16, box)
+    assert (p32 != b32).sum() == 1 and p32[3, 0] == np.float32(np.float64(b32[3, 0]) - box)
+    # 2-D grid with an (N, 3) array: the unused third column is wrapped too, nothing else moves
+    p2 = (rng.random((200, 3)) * box).astype(np.float32)
+    p2[5, 2] = np.float32(-3.0)
+    b2 = p2.copy()
+    tsc.tsc_parallel(p2, (12, 12), box)
+    assert (p2 != b2).sum() == 1 and p2[5, 2] == np.float32(97.0)
