@@ -195,10 +195,11 @@ class _Painter:
 
     def chunk_plan(self, N, host=True):
         """Chunks of the particle set; every chunk becomes one bucket segment.  Host inputs want many chunks (they
-        are the unit of copy/compute overlap).  Device-resident inputs only need them below SEGMENT_MAX particles;
-        ABK_DEVICE_SEGMENTS (experiment knob, default: same plan as host inputs) sets their number."""
+        are the unit of copy/compute overlap).  Device-resident inputs only need them below SEGMENT_MAX particles."""
         max_seg = ABK_MAX_SEGMENTS - 2
         if not host and os.environ.get('ABK_DEVICE_SEGMENTS'):
+            # testing knob.  Default for device-resident input: the host plan -- measured on B200 at config 3, 14 segments
+            # beat one (bucket scatter 30.2 vs 32.4 ms: a segment's open write frontier is smaller), step 86.8 vs 87.7 ms
             max_seg = max(1, min(max_seg, int(os.environ['ABK_DEVICE_SEGMENTS'])))
             chunk = -(-N // max_seg)
         else:

@@ -400,17 +400,23 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
     const uint32_t tile = blockIdx.x;
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (int s = 0; s < segs.nseg; s++) {
-            const uint32_t b = segs.starts[s][tile], e = segs.starts[s][tile + 1];
-            seg_beg[s] = b;
-            seg_off[s] = run;
-            run += e - b;
+    // the tile's record range in every segment: loaded by one lane per segment (the loads overlap), then prefix-summed
+    if (tid < 32) {
+        uint32_t b = 0, cnt = 0;
+        if (tid < segs.nseg) {
+            b = segs.starts[tid][tile];
+            cnt = segs.starts[tid][tile + 1] - b;
         }
-        seg_off[segs.nseg] = run;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < ABK_MAX_SEGMENTS; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (tid < segs.nseg) { seg_beg[tid] = b; seg_off[tid] = inc - cnt; }
+        if (tid == segs.nseg - 1) seg_off[segs.nseg] = inc;
 #if defined(__CUDA_ARCH__)
-        mbar_init(&bar, 1);
+        if (tid == 0) mbar_init(&bar, 1);
 #endif
     }
     __syncthreads();
@@ -438,10 +444,14 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
         if (chunk0) __syncthreads();  // the previous pass' walks are done with the lists and records
         // ---- stage the raw records of this pass: one bulk copy per segment that overlaps [chunk0, chunk0 + m) ----
 #if defined(__CUDA_ARCH__)
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(&bar, (uint32_t)m * 16u);
-            for (int s = 0; s < segs.nseg; s++) {
+        if (tid < 32) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&bar, (uint32_t)m * 16u);
+            }
+            __syncwarp();
+            if (tid < segs.nseg) {
+                const int s = tid;
                 const uint32_t lo = max(seg_off[s], chunk0), hi = min(seg_off[s + 1], chunk0 + (uint32_t)m);
                 if (lo < hi) bulk_g2s(srec + (lo - chunk0), segs.rec[s] + seg_beg[s] + (lo - seg_off[s]), (hi - lo) * 16u, &bar);
             }

@@ -201,6 +201,43 @@ def transpose_slab_to_pencil(packed, plan, rank, group=None):
 # ------------------------------------------------------------------------------------------- peer memory
 _SYMM = {'ok': None, 'bufs': {}}
 
+# optional phase timing (bench.py's multi-GPU arm): CUDA-event pairs on the current stream around the phases of the step
+_PHASES = {'on': False, 'recs': []}
+
+
+class _phase:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _PHASES['on']:
+            import torch
+
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PHASES['on']:
+            self.b.record()
+            _PHASES['recs'].append((self.name, self.a, self.b))
+        return False
+
+
+def phase_times(reset=True):
+    """{phase: total ms} of the recorded phases (synchronises)."""
+    import torch
+
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in _PHASES['recs']:
+        out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    if reset:
+        _PHASES['recs'] = []
+    return out
+
+
 
 def _symm_pencil(group, nelem, slot, device):
     """A symmetric-memory (peer-mapped over NVLink) complex64 buffer of `nelem` elements, cached per slot.
@@ -561,12 +598,15 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
         # one grid at a time (paint -> ghosts -> FFT -> drop the slab): at nmesh 4096 on 8 GPUs a slab is 35 GB
         pencils = []
         if plan.aligned and not force_reroute:
-            segs, _, keep = de.route_bucketed(p, wt, plan, Lbox, paste)
+            with _phase('bucket + particle exchange'):
+                segs, _, keep = de.route_bucketed(p, wt, plan, Lbox, paste)
             for io, off in enumerate(offsets):
-                gb = de.paint_segments(segs, plan, Lbox, [off], paste, bucket_offset=offsets[0])
+                with _phase('deposit + ghost planes'):
+                    gb = de.paint_segments(segs, plan, Lbox, [off], paste, bucket_offset=offsets[0])
                 if io == len(offsets) - 1:
                     del keep, segs  # the routed records are dead once the last grid has been painted
-                pencils.append(de.fft_slab(gb, plan, ntot, slot=slot_base + io))
+                with _phase('fft + transpose'):
+                    pencils.append(de.fft_slab(gb, plan, ntot, slot=slot_base + io))
         else:
             rec = de.route(p, wt, plan, Lbox, paste)
             for io, off in enumerate(offsets):
@@ -587,9 +627,10 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     poles_arr = np.asarray(poles or [], dtype=np.int64)
     kbins, mubins = ps.get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)
     scale = np.float32(0.5 / n**3) if interlaced else np.float32(1 / n**3)
-    binned = de.bin_pencils(plan, float(Lbox), kbins, mubins, poles_arr, g1[0], g1[1] if interlaced else None,
-                            None if g2 is None else g2[0], g2[1] if (g2 is not None and interlaced) else None, W_d,
-                            scale)
+    with _phase('bin + all-reduce'):
+        binned = de.bin_pencils(plan, float(Lbox), kbins, mubins, poles_arr, g1[0], g1[1] if interlaced else None,
+                                None if g2 is None else g2[0], g2[1] if (g2 is not None and interlaced) else None, W_d,
+                                scale)
     P = ps._package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
     kbins, mubins = np.asarray(kbins), np.asarray(mubins)
     res = dict(k_min=kbins[:-1], k_max=kbins[1:], k_mid=(kbins[1:] + kbins[:-1]) * 0.5, k_avg=P['k_avg'],
@@ -686,6 +727,7 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks, parity_block=No
     l0 = eng.launch_count()
     eng.profile(True)
     eng.profile_collect()
+    _PHASES['on'], _PHASES['recs'] = True, []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -699,6 +741,8 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks, parity_block=No
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     prof = eng.profile_collect()
     eng.profile(False)
+    phases = {k: v / args.steps for k, v in phase_times().items()}
+    _PHASES['on'] = False
     launches = eng.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -749,7 +793,7 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks, parity_block=No
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches * world),
             'roofline': {'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
                          'peak_source': peak_src, 'note': 'per-kernel roofline is reported by the N=1 run'},
-            'cpu_baseline': None, 'parity': parity, 'stages': stages, 'mpart_per_s': N / float(ms.item()) / 1e3,
+            'cpu_baseline': None, 'parity': parity, 'stages': stages, 'phases_ms_rank0': phases, 'mpart_per_s': N / float(ms.item()) / 1e3,
             'N_mode_total': int(np.asarray(res['N_mode']).sum()),
         }
         print(json.dumps(line))

@@ -15,7 +15,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-NAMES = {'tsc_tile_walk_kernel': 'tsc_tile_deposit', 'tsc_bucket_kernel<(bool)1': 'tsc_bucket_scatter', 'tsc_bucket_kernel<(bool)0': 'tsc_bucket_hist',
+NAMES = {'tsc_tile_walk_kernel': 'tsc_tile_deposit', 'tsc_bucket_kernel<1': 'tsc_bucket_scatter', 'tsc_bucket_kernel<(bool)1': 'tsc_bucket_scatter', 'tsc_bucket_kernel<0': 'tsc_bucket_hist', 'tsc_bucket_kernel<(bool)0': 'tsc_bucket_hist',
          'power_bin': 'power_bin', 'normalize_kernel': 'normalize_field', 'transpose_scatter_p2p': 'transpose_scatter_p2p'}
 KEYS = {'gpu__time_duration.sum': 'duration_ns', 'dram__bytes_read.sum': 'dram_read', 'dram__bytes_write.sum': 'dram_write',
         'smsp__inst_executed.sum': 'warp_inst_per_launch', 'smsp__issue_active.avg.pct_of_peak_sustained_active': 'issue_active_pct',

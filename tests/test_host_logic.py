@@ -50,6 +50,7 @@ def test_chunk_plan_device_segment_knob(monkeypatch):
     from abacusutils_b200.analysis.power_spectrum import _Painter
 
     P = _Painter.__new__(_Painter)
+    monkeypatch.delenv('ABK_DEVICE_SEGMENTS', raising=False)
     assert P.chunk_plan(10**9, host=False) == P.chunk_plan(10**9, host=True)      # default: same plan
     monkeypatch.setenv('ABK_DEVICE_SEGMENTS', '1')
     assert P.chunk_plan(10**9, host=False) == [(0, 10**9)]
