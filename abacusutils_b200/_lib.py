@@ -182,7 +182,9 @@ class Engine:
     def aux_stream(self):
         """A second CUDA stream of this device (overlap of independent stages)."""
         if getattr(self, '_aux', None) is None:
-            self._aux = _torch().cuda.Stream(device=self.device)
+            # high priority: its kernels (FFT of the previous grid, transposes) must get SMs while a long tile deposit
+            # that fills the whole GPU is running on the main stream
+            self._aux = _torch().cuda.Stream(device=self.device, priority=-1)
         return self._aux
 
     def sync(self):

@@ -29,7 +29,7 @@ import time
 
 import numpy as np
 
-from ._lib import BinRequest, Engine, KMesh, check, ptr
+from ._lib import ABK_MAX_SEGMENTS, BinRequest, Engine, KMesh, check, ptr
 from .analysis import power_spectrum as ps
 from .analysis.tsc import padded_ldz
 
@@ -174,13 +174,15 @@ def exchange_ghost_planes(grid, nxl, add_planes, group=None):
     ops = [dist.P2POp(dist.isend, lo.contiguous(), gl, group=group), dist.P2POp(dist.isend, hi.contiguous(), gr, group=group),
            dist.P2POp(dist.irecv, from_right, gr, group=group), dist.P2POp(dist.irecv, from_left, gl, group=group)]
     if world == 2:
-        # both neighbours are the same peer: order the two messages explicitly with tags via two rounds
-        ops = [dist.P2POp(dist.isend, lo.contiguous(), gl, group=group), dist.P2POp(dist.irecv, from_right, gr, group=group)]
+        # both neighbours are the same peer: one message each way carrying all three planes [lo | hi, hi+1]
+        out = torch.cat([lo, hi])
+        inc = torch.empty_like(out)
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, out, gr, group=group), dist.P2POp(dist.irecv, inc, gr, group=group)]):
+            req.wait()
+        from_right, from_left = inc[0:1], inc[1:3]
+    else:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        ops = [dist.P2POp(dist.isend, hi.contiguous(), gr, group=group), dist.P2POp(dist.irecv, from_left, gl, group=group)]
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
     add_planes(grid[nxl:nxl + 1], from_right)
     add_planes(grid[1:3], from_left)
 
@@ -333,17 +335,22 @@ class DistEngine:
             t = torch.tensor([nchunk_local], dtype=torch.int64, device=self.device)
             _dist().all_reduce(t, op=_dist().ReduceOp.MAX, group=self.group)
             nchunk = int(t.item())
-        if nchunk * self.world > 16:
-            raise NotImplementedError(f'{nchunk} local chunks x {self.world} ranks exceed the 16 bucket segments of the tile kernel')
-        bucket_fn = lib.abk_tsc_bucket
+            # pipelining: more, smaller chunks so that the exchange of chunk c (NCCL, its own stream) runs while chunk c+1
+            # is being bucketed; the tile kernel takes at most 16 segments = chunks x ranks
+            nchunk = max(nchunk, min(ABK_MAX_SEGMENTS // self.world, int(os.environ.get('ABK_DIST_CHUNKS', '4'))))
+        if nchunk * self.world > ABK_MAX_SEGMENTS:
+            raise NotImplementedError(f'{nchunk} local chunks x {self.world} ranks exceed the {ABK_MAX_SEGMENTS} bucket segments of the tile kernel')
+        csize = max(1, -(-N // nchunk))
         nb = C.c_size_t()
-        check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, CH), 1), n, n, n, C.byref(nb)))
+        check(lib.abk_tsc_bucket_scratch_bytes(max(min(N, csize), 1), n, n, n, C.byref(nb)))
         scan_buf = eng.scratch('bucket_scan', nb.value + 256)
         scan_ptr = C.c_void_p((scan_buf.data_ptr() + 255) & ~255)
         wrap = 0 if str(paste).upper() == 'CIC' else 1
         segs, keep, total = [], [], 0
-        for c in range(nchunk):
-            a, bnd = min(c * CH, N), min((c + 1) * CH, N)
+        compute = eng.bind_stream()
+
+        def bucket(c):
+            a, bnd = min(c * csize, N), min((c + 1) * csize, N)
             m = bnd - a
             if self.world == 1:
                 rec = eng.scratch(f'route_out{c}', max(m, 1) * 16)
@@ -351,15 +358,36 @@ class DistEngine:
             else:  # send-side buffers are dead after the exchange: plain tensors, returned to the allocator
                 rec = torch.empty(max(m, 1) * 16, dtype=torch.uint8, device=self.device)
                 starts = torch.empty(ntiles + 1, dtype=torch.int32, device=self.device)
-            check(bucket_fn(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
-                            m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), scan_ptr, nb.value))
-            rows = rec[: m * 16].view(torch.float32).view(m, 4)
-            if self.world == 1:
+            eng.bind_stream()
+            check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
+                                     m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), scan_ptr, nb.value))
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            return rec[: m * 16].view(torch.float32).view(m, 4), starts, m, ev
+
+        if self.world == 1:
+            for c in range(nchunk):
+                rows, starts, m, _ = bucket(c)
                 segs.append((rows.data_ptr(), starts.data_ptr(), m))
                 keep += [rows, starts]
                 total += m
-                continue
-            parts = exchange_bucketed(rows, starts, t0, self.group)
+            return segs, total, keep
+
+        comm = self._comm_stream()
+        nxt = bucket(0)
+        for c in range(nchunk):
+            rows, starts, m, ev = nxt
+            if c + 1 < nchunk:
+                nxt = bucket(c + 1)      # queued before this chunk's exchange blocks the host on its sizes
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                parts = exchange_bucketed(rows, starts, t0, self.group)
+                if rows.is_cuda:      # allocator bookkeeping: tensors cross between the compute and the exchange stream
+                    for recs_q, st_q, _ in parts:
+                        recs_q.record_stream(compute)
+                        st_q.record_stream(compute)
+                    rows.record_stream(comm)
+                    starts.record_stream(comm)
             off = 0
             for recs_q, st_q, base_q in parts:
                 # the slice holds the SENDER's record offsets: bias the record pointer instead of rewriting it
@@ -367,11 +395,20 @@ class DistEngine:
                 off += int(recs_q.shape[0])
             keep.append(parts)
             total += off
-            del rec, rows, starts
+            del rows, starts
+        compute.wait_stream(comm)
         return segs, total, keep
 
-    def paint_segments(self, segs, plan, Lbox, offsets, paste='TSC', bucket_offset=None):
-        """Tile deposit of pre-bucketed segments (route_bucketed) into slab grids, then the ghost exchange."""
+    def _comm_stream(self):
+        import torch
+
+        if getattr(self.eng, '_comm', None) is None:
+            self.eng._comm = torch.cuda.Stream(device=self.device, priority=-1)
+        return self.eng._comm
+
+    def paint_segments(self, segs, plan, Lbox, offsets, paste='TSC', bucket_offset=None, init=0.0, ghosts=True):
+        """Tile deposit of pre-bucketed segments (route_bucketed) into slab grids, then the ghost exchange.  `init`: start
+        value of the OWNED planes (-1 when the field normalisation is folded into the deposit, power_spectrum.py:860-901)."""
         import torch
 
         eng, n = self.eng, plan.n
@@ -384,6 +421,8 @@ class DistEngine:
         grids = []
         for off in offsets:
             grid = eng.zeros((nxl + 3, n, ldz), torch.float32)
+            if init != 0.0:
+                grid[1:nxl + 1].fill_(init)
             if live:
                 m = len(live)
                 recs = (C.c_void_p * m)(*[sg[0] for sg in live])
@@ -393,13 +432,22 @@ class DistEngine:
                 check(lib.abk_tsc_deposit_tiles(eng.ctx, m, recs, sts, cnts, ptr(grid), n, n, n, ldz, float(Lbox), float(off),
                                                 float(offsets[0] if bucket_offset is None else bucket_offset), 1, x_lo, nxl))
 
-            def add_planes(dst, src):
-                eng.bind_stream()
-                check(lib.abk_add_planes(eng.ctx, ptr(dst), ptr(src.contiguous()), dst.shape[0], n, n, ldz))
-
-            exchange_ghost_planes(grid, nxl, add_planes, self.group)
+            if ghosts:
+                self.fold_ghosts(grid, plan)
             grids.append(grid)
         return grids
+
+    def fold_ghosts(self, grid, plan):
+        """Ring exchange of the three ghost planes of a slab grid; the received planes are added to the owned ones."""
+        eng, n = self.eng, plan.n
+        x_lo, x_hi = plan.x_range(self.rank)
+        ldz = padded_ldz(n)
+
+        def add_planes(dst, src):
+            eng.bind_stream()
+            check(eng.lib.abk_add_planes(eng.ctx, ptr(dst), ptr(src.contiguous()), dst.shape[0], n, n, ldz))
+
+        exchange_ghost_planes(grid, x_hi - x_lo, add_planes, self.group)
 
     # -- 2. deposit + ghosts ----------------------------------------------------------------------------
     def paint_slab(self, records, plan, Lbox, offsets, paste='TSC', bucket_offset=None):
@@ -483,7 +531,8 @@ class DistEngine:
         ldz = padded_ldz(n)
         owned = grid[1:nxl + 1]
         eng.bind_stream()
-        check(eng.lib.abk_normalize_field(eng.ctx, ptr(owned), nxl, n, n, ldz, float(n) ** 3, float(n_total)))
+        if n_total is not None:      # None: the deposit already produced rho * n^3/N - 1
+            check(eng.lib.abk_normalize_field(eng.ctx, ptr(owned), nxl, n, n, ldz, float(n) ** 3, float(n_total)))
         h, wb = self._plan('yz', nxl, n, n)
         self._exec(h, wb, owned.data_ptr())
         js = (C.c_int64 * (self.world + 1))(*plan.jsplit)
@@ -598,15 +647,46 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
         # one grid at a time (paint -> ghosts -> FFT -> drop the slab): at nmesh 4096 on 8 GPUs a slab is 35 GB
         pencils = []
         if plan.aligned and not force_reroute:
+            # normalize_field folded into the deposit: weights scaled by n^3/N as the records are written, owned planes
+            # start at -1 (ABK_FUSED_NORMALIZE=0 restores the separate pass)
+            fused = os.environ.get('ABK_FUSED_NORMALIZE', '1') != '0' and ntot > 0
             with _phase('bucket + particle exchange'):
-                segs, _, keep = de.route_bucketed(p, wt, plan, Lbox, paste)
+                if fused:
+                    eng.set_weight_scale(float(np.float32(float(n) ** 3 / float(ntot))))
+                try:
+                    segs, _, keep = de.route_bucketed(p, wt, plan, Lbox, paste)
+                finally:
+                    eng.set_weight_scale(1.0)
+            # the FFT + transpose of grid i runs on an auxiliary stream while grid i+1 is being painted; two slabs are
+            # alive at once then, so only where they fit comfortably (a slab is 35 GB at nmesh 4096 on 8 GPUs)
+            overlap = de.world > 1 and len(offsets) > 1 and plan.n <= 2048 and os.environ.get('ABK_DIST_OVERLAP', '1') != '0'
+            compute = eng.bind_stream()
+            aux = eng.aux_stream()
+            done = None
             for io, off in enumerate(offsets):
-                with _phase('deposit + ghost planes'):
-                    gb = de.paint_segments(segs, plan, Lbox, [off], paste, bucket_offset=offsets[0])
+                with _phase('deposit' if overlap else 'deposit + ghost planes'):
+                    gb = de.paint_segments(segs, plan, Lbox, [off], paste, bucket_offset=offsets[0], init=-1.0 if fused else 0.0,
+                                           ghosts=not overlap)
                 if io == len(offsets) - 1:
                     del keep, segs  # the routed records are dead once the last grid has been painted
-                with _phase('fft + transpose'):
-                    pencils.append(de.fft_slab(gb, plan, ntot, slot=slot_base + io))
+                if overlap:
+                    # ghost planes, FFT and transpose of this grid all go to the auxiliary stream: the compute stream
+                    # paints the grids back to back (all ranks issue their collectives in the same order: only `aux` does)
+                    if gb[0].is_cuda:
+                        gb[0].record_stream(aux)
+                    aux.wait_stream(compute)
+                    with torch.cuda.stream(aux):
+                        de.fold_ghosts(gb[0], plan)
+                        pencils.append(de.fft_slab(gb, plan, None if fused else ntot, slot=slot_base + io))
+                        done = torch.cuda.Event()
+                        done.record(aux)
+                    eng.bind_stream()
+                else:
+                    with _phase('fft + transpose'):
+                        pencils.append(de.fft_slab(gb, plan, None if fused else ntot, slot=slot_base + io))
+            if done is not None:
+                with _phase('ghost planes + fft + transpose (exposed tail)'):
+                    compute.wait_event(done)
         else:
             rec = de.route(p, wt, plan, Lbox, paste)
             for io, off in enumerate(offsets):
@@ -705,7 +785,12 @@ def bench_main(args, cfg, metric, workload, ClockSampler, peaks, parity_block=No
     dist = _dist()
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    # NCCL on a high-priority stream: the particle exchange of chunk c must get SMs while chunk c+1 is being bucketed
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank), pg_options=opts)
+    except Exception:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     world, rank = dist.get_world_size(), dist.get_rank()
     eng = Engine.get(local_rank)
     N, L, n = cfg['N'], cfg['L'], cfg['nmesh']
