@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libabk.so'
-SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu', 'abk_kfields.cu', 'abk_ingest.cu']
+SOURCES = ['abk_ctx.cu', 'abk_tsc.cu', 'abk_fft.cu', 'abk_kspace.cu', 'abk_kfields.cu', 'abk_ingest.cu', 'abk_f64.cu']
 CUDA_HOME = os.environ.get('CUDA_HOME', '/usr/local/cuda')
 
 NVCC_FLAGS = [

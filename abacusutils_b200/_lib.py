@@ -63,7 +63,7 @@ SIGNATURES = {
     'abk_kernel_name': (C.c_char_p, [_i32]),
     'abk_wrap_inplace': (_i32, [_vp, _vp, _i64, _dbl, _vp]),
     'abk_partition_scratch_bytes': (_i32, [_i64, _i32, _psz]),
-    'abk_partition': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _sz]),
+    'abk_partition': (_i32, [_vp, _vp, _vp, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _sz]),
     'abk_tsc_num_tiles': (_i32, [_i32, _i32, _i32, C.POINTER(_i64)]),
     'abk_bench_red_rate': (_i32, [_vp, _vp, _i64, _i32, C.POINTER(C.c_double)]),
     'abk_tsc_tile_shape': (_i32, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -78,6 +78,10 @@ SIGNATURES = {
     'abk_tsc_deposit_scratch_bytes': (_i32, [_i64, _i32, _i32, _i32, _psz]),
     'abk_tsc_deposit': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _dbl, _dbl, _i32, _vp, _sz]),
     'abk_tsc_deposit_naive': (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i64, _dbl, _dbl, _i32]),
+    'abk_tsc_deposit_typed': (_i32, [_vp, _vp, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _i32, _i64, _dbl, _dbl, _i32]),
+    'abk_normalize_field_f64': (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl]),
+    'abk_rfft3_f64': (_i32, [_vp, _vp, _i64, _i64, _i64]),
+    'abk_power_from_f64': (_i32, [_vp, _vp, _vp, _vp, _i32, _dbl, _vp]),
     'abk_normalize_field': (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _dbl, _dbl]),
     'abk_rfft3_plan_create': (_i32, [_vp, _i64, _i64, _i64, C.POINTER(_vp), _psz]),
     'abk_rfft3_exec': (_i32, [_vp, _vp, _vp, _vp, _sz]),
@@ -87,6 +91,7 @@ SIGNATURES = {
     'abk_fft_x_plan_create': (_i32, [_vp, _i64, _i64, _i64, C.POINTER(_vp), _psz]),
     'abk_fft_exec_generic': (_i32, [_vp, _vp, _vp, _vp, _sz]),
     'abk_field_fft_finish': (_i32, [_vp, C.POINTER(KMesh), _vp, _vp, _vp, _flt]),
+    'abk_shift_field_fft': (_i32, [_vp, C.POINTER(KMesh), _vp, _vp, _dbl, _flt]),
     'abk_raw_power': (_i32, [_vp, _vp, _vp, _vp, _i64]),
     'abk_real_to_complex': (_i32, [_vp, _vp, _vp, _i64]),
     'abk_delta_mu2': (_i32, [_vp, _vp, _vp, _i32]),

@@ -510,12 +510,10 @@ def get_field(pos, Lbox, nmesh, paste, w=None, d=0.0, nthread=MAX_THREADS, dtype
 # ---------------------------------------------------------------------------------------------
 # Fourier-space fields
 def shift_field_fft(field_fft, field_shift_fft, n1d, L, d, dtype=np.float32):
-    """In place ``f <- (f + fs * exp(i*0.5*d*(kx+ky+kz))) * 0.5/n^3`` (power_spectrum.py:904-948).
-    Only the reference's own call pattern ``d == L/n1d`` (half-cell interlacing) is supported."""
+    """In place ``f <- (f + fs * exp(i*0.5*d*(kx+ky+kz))) * 0.5/n^3`` for any shift ``d`` (power_spectrum.py:904-948;
+    the reference's own callers pass ``d = L/n1d``, the half-cell interlacing shift)."""
     import torch
 
-    if not math.isclose(float(d), float(L) / int(n1d), rel_tol=1e-6):
-        raise NotImplementedError('shift_field_fft: only d == L/n1d (the interlacing shift) is implemented')
     on_device = is_torch_tensor(field_fft) and field_fft.is_cuda
     eng = Engine.get(field_fft.device if on_device else None)
     eng.bind_stream()
@@ -523,7 +521,7 @@ def shift_field_fft(field_fft, field_shift_fft, n1d, L, d, dtype=np.float32):
     f = field_fft if on_device else eng.to_device(field_fft, torch.complex64)
     fs = eng.to_device(field_shift_fft, torch.complex64)
     mesh = _kmesh(n)
-    check(eng.lib.abk_field_fft_finish(eng.ctx, C.byref(mesh), ptr(f), ptr(fs), None, np.float32(0.5 / n**3)))
+    check(eng.lib.abk_shift_field_fft(eng.ctx, C.byref(mesh), ptr(f), ptr(fs), float(d) / float(L), np.float32(0.5 / n**3)))
     if not on_device:
         np.copyto(field_fft, f.cpu().numpy())
 
@@ -534,6 +532,38 @@ def _field_fft_device(eng, pos, Lbox, nmesh, w, interlaced, tag='', paste='TSC')
     P = _Painter(eng, n, Lbox, paste)
     offsets = [0.0, 0.5 * (float(Lbox) / n)] if interlaced else [0.0]
     return P.paint(pos, w, offsets, tag=tag, fft_weight=len(pos))
+
+
+def _is_f64(dtype):
+    return np.dtype(dtype) == np.float64
+
+
+def _field_fft_f64(eng, pos, Lbox, nmesh, w, paste='TSC'):
+    """The non-interlaced branch of get_field_fft in float64 (power_spectrum.py:1053-1060 with dtype=float64): paint onto
+    a float64 grid (arithmetic in the dtype of ``pos``, tsc.py:400), normalise by len(pos), D2Z transform.  Returns the
+    UNSCALED spectrum as a device tensor complex128 (n, n, n//2+1) (a view of the padded in-place buffer)."""
+    import torch
+
+    from .tsc import _float_kind
+
+    n = int(nmesh)
+    ldz = padded_ldz(n)
+    N = len(pos)
+    if N == 0:
+        raise ValueError('cannot normalise an empty particle set')
+    pos_dt = _float_kind(pos)
+    pos_d = eng.to_device(pos, torch.float64 if pos_dt == 'f8' else torch.float32)
+    w_dt = None if w is None else _float_kind(w)
+    w_d = None if w is None else eng.to_device(w, torch.float64 if w_dt == 'f8' else torch.float32)
+    grid = eng.zeros((n, n, ldz), torch.float64)
+    eng.bind_stream()
+    eng.set_scheme(paste)
+    # TSC wraps the positions once (tsc.py:171-173); cic_serial does not (power_spectrum.py:846-853)
+    check(eng.lib.abk_tsc_deposit_typed(eng.ctx, ptr(pos_d), int(pos_dt == 'f8'), ptr(w_d), int(w_dt == 'f8'), N, ptr(grid), 1,
+                                        n, n, n, ldz, float(Lbox), 0.0, int(paste == 'TSC')))
+    check(eng.lib.abk_normalize_field_f64(eng.ctx, ptr(grid), n, n, n, ldz, float(n) ** 3, float(N)))
+    check(eng.lib.abk_rfft3_f64(eng.ctx, ptr(grid), n, n, n))
+    return torch.view_as_complex(grid.view(n, n, n // 2 + 1, 2))
 
 
 def get_interlaced_field_fft(pos, Lbox, nmesh, paste, w, nthread=MAX_THREADS, verbose=False):
@@ -556,6 +586,15 @@ def get_field_fft(pos, Lbox, nmesh, paste, w, W, compensated, interlaced, nthrea
     on_device = is_torch_tensor(pos) and pos.is_cuda
     eng = Engine.get(pos.device if on_device else None)
     n = int(nmesh)
+    if _is_f64(dtype) and not interlaced:
+        # the reference honours dtype on the non-interlaced branch only (power_spectrum.py:1053-1069; the interlaced
+        # paints are always float32, :979,985): float64 field, float64 transform, complex128 result
+        f = _field_fft_f64(eng, pos, Lbox, n, w, paste)
+        f *= 1.0 / float(n) ** 3
+        if compensated:
+            Wt = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32)
+            f /= ((Wt[:, None, None] * Wt[None, :, None]) * Wt[None, None, : n // 2 + 1])
+        return f if on_device else f.cpu().numpy()
     grids = _field_fft_device(eng, pos, Lbox, n, w, interlaced, paste=paste)
     W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
     mesh = _kmesh(n)
@@ -767,9 +806,31 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     on_device = is_torch_tensor(pos) and pos.is_cuda
     eng = Engine.get(pos.device if on_device else None)
     n = int(nmesh)
+    # ABK_META_TIMINGS=1: per-kernel CUDA-event times of THIS call in meta['kernel_ms'] (the reference prints stage times
+    # when verbose, tsc.py:175-201; here they travel with the result)
+    timings = os.environ.get('ABK_META_TIMINGS') == '1'
+    if timings:
+        eng.profile_collect()
+        eng.profile(True)
+    try:
+        return _calc_power_impl(eng, on_device, pos, Lbox, kbins, mubins, k_max, logk, paste, paste_u, n, compensated, interlaced, w, pos2,
+                                w2, poles, squeeze_mu_axis, dtype, return_mubins, meta)
+    finally:
+        if timings:
+            meta['kernel_ms'] = {k: {'ms': v[0], 'launches': v[1]} for k, v in eng.profile_collect().items()}
+            eng.profile(False)
+
+
+def _calc_power_impl(eng, on_device, pos, Lbox, kbins, mubins, k_max, logk, paste, paste_u, n, compensated, interlaced, w, pos2, w2,
+                     poles, squeeze_mu_axis, dtype, return_mubins, meta):
+    import torch
+
     W = get_W_compensated(Lbox, n, paste, interlaced) if compensated else None
     W_d = eng.to_device(np.asarray(W, dtype=np.float32), torch.float32) if compensated else None
 
+    if _is_f64(dtype) and not interlaced and not isinstance(pos, PackedParticles):
+        return _calc_power_f64(eng, pos, Lbox, kbins, mubins, k_max, logk, paste_u, n, W, w, pos2, w2, poles, squeeze_mu_axis,
+                               return_mubins, meta)
     g1 = _field_fft_device(eng, pos, Lbox, n, w, interlaced, tag='a', paste=paste_u)
     g2 = _field_fft_device(eng, pos2, Lbox, n, w2, interlaced, tag='a', paste=paste_u) if pos2 is not None else None
     if isinstance(pos, PackedParticles):      # pack9: the particle count is known once the records are decoded
@@ -795,6 +856,37 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     if len(poles_arr) > 0:
         res.update(poles=P['binned_poles'].T, N_mode_poles=P['N_mode_poles'])
     if return_mubins:
+        res.update(mu_min=np.broadcast_to(mubins[:-1], res['power'].shape),
+                   mu_max=np.broadcast_to(mubins[1:], res['power'].shape),
+                   mu_mid=np.broadcast_to(mu_binc, res['power'].shape))
+    return _make_table(res, meta)
+
+
+def _calc_power_f64(eng, pos, Lbox, kbins, mubins, k_max, logk, paste, n, W, w, pos2, w2, poles, squeeze_mu_axis, return_mubins, meta):
+    """calc_power(dtype=float64, interlaced=False): float64 field and transform (power_spectrum.py:1053-1069), raw power
+    |f|^2 in float64 (:707-727), handed to the binning kernel as the float32 mesh whose sums the reference also keeps in
+    float32 (bin_kmu is always called with dtype=float32, :781-783)."""
+    import torch
+
+    f1 = _field_fft_f64(eng, pos, Lbox, n, w, paste)
+    f2 = _field_fft_f64(eng, pos2, Lbox, n, w2, paste) if pos2 is not None else None
+    W_d = None if W is None else eng.to_device(np.asarray(W, dtype=np.float32), torch.float32)
+    nzc = n // 2 + 1
+    power = eng.empty((n, n, nzc), torch.float32)
+    eng.bind_stream()
+    check(eng.lib.abk_power_from_f64(eng.ctx, ptr(f1), ptr(f2), ptr(W_d), n, 1.0 / float(n) ** 3, ptr(power)))
+    del f1, f2
+    poles_arr = np.asarray(poles or [], dtype=np.int64)
+    kbins, mubins = get_k_mu_edges(Lbox, k_max, kbins, mubins, logk)
+    binned = _bin_device(eng, n, float(Lbox), kbins, mubins, poles_arr, True, real_in=power, row_len=nzc)
+    P = _package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
+    kbins, mubins = np.asarray(kbins), np.asarray(mubins)
+    res = dict(k_min=kbins[:-1], k_max=kbins[1:], k_mid=(kbins[1:] + kbins[:-1]) * 0.5, k_avg=P['k_avg'], power=P['power'],
+               N_mode=P['N_mode'])
+    if len(poles_arr) > 0:
+        res.update(poles=P['binned_poles'].T, N_mode_poles=P['N_mode_poles'])
+    if return_mubins:
+        mu_binc = (mubins[1:] + mubins[:-1]) * 0.5
         res.update(mu_min=np.broadcast_to(mubins[:-1], res['power'].shape),
                    mu_max=np.broadcast_to(mubins[1:], res['power'].shape),
                    mu_mid=np.broadcast_to(mu_binc, res['power'].shape))

@@ -11,8 +11,10 @@ Differences from the reference, all deliberate:
   * ``nthread``, ``npartition``, ``sort`` (for ``tsc_parallel``) are accepted and validated like the
     reference but do not influence the result: the GPU schedule (tile bucketing) replaces the
     x-stripe schedule they tune.
-  * float64 positions/grids are accepted with the reference's warning (tsc.py:155-165) but the
-    deposit runs in float32.
+  * float64 positions / grids / weights are honoured like the reference does (same warning, tsc.py:155-165):
+    arithmetic in the dtype of the positions (tsc.py:400), accumulation in the dtype of the grid.  Only
+    float32 positions on a float32 grid take the tuned path (tile bucketing + walk kernel); every other
+    combination runs the typed one-thread-per-particle kernel of csrc/abk_f64.cu.
   * the sum order differs (per-cell register sums, float reductions into the grid), so grids agree
     with the reference to float32 round-off, not bit for bit -- as between two thread counts of the
     reference itself (its kernels are ``fastmath=True``).
@@ -45,6 +47,15 @@ def _validate_npartition(npartition, n1d, nthread):
                          f'ngrid//2 = {n1d // 2}')
     if npartition > 1 and npartition % 2 != 0 and nthread > 1:
         raise ValueError(f'npartition {npartition} not divisible by 2')
+
+
+def _float_kind(a):
+    """'f8' for float64 arrays / tensors, 'f4' otherwise (other dtypes are converted to float32, as before)."""
+    if is_torch_tensor(a):
+        import torch
+
+        return 'f8' if a.dtype == torch.float64 else 'f4'
+    return 'f8' if np.asarray(a).dtype == np.float64 else 'f4'
 
 
 def _wrap_caller_array(pos, box):
@@ -142,39 +153,56 @@ def tsc_parallel(pos, densgrid, box, weights=None, nthread=-1, wrap=True, nparti
 
     N = len(pos)
     stream = eng.bind_stream()
+    pos_dt = _float_kind(pos)
+    grid_dt = _float_kind(densgrid) if user_supplied_grid else 'f4'      # a new grid is float32 (tsc.py:118-120)
+    w_dt = None if weights is None else _float_kind(weights)
+    typed = not (pos_dt == 'f4' and grid_dt == 'f4' and w_dt in (None, 'f4'))
+    tpos = torch.float64 if pos_dt == 'f8' else torch.float32
     # ---- particles on the device ------------------------------------------------------------------
     if on_device:
-        pos_d = pos if (pos.dtype == torch.float32 and pos.is_contiguous()) else pos.to(torch.float32).contiguous()
+        pos_d = pos if (pos.dtype == tpos and pos.is_contiguous()) else pos.to(tpos).contiguous()
     else:
-        pos_d = eng.to_device(pos, torch.float32)
-    w_d = None if weights is None else eng.to_device(weights, torch.float32)
+        pos_d = eng.to_device(pos, tpos)
+    w_d = None if weights is None else eng.to_device(weights, torch.float64 if w_dt == 'f8' else torch.float32)
     pos_in = pos_d
     if two_d:
         # (x, y, 0) copy for the 3-D kernels; the in-place wrap below is applied to the caller's columns
-        pos_d = torch.zeros((N, 3), dtype=torch.float32, device=eng.device)
+        pos_d = torch.zeros((N, 3), dtype=tpos, device=eng.device)
         pos_d[:, :2] = pos_in[:, :2]
 
     if wrap and N > 0:
-        # tsc.py:171-173: the caller's array is wrapped in place.  The float32 device copy is wrapped by the kernel (that is
-        # what gets painted); the CALLER's array is then updated entry by entry, in its own dtype and only where a value
-        # lies outside [0, box) -- like _wrap_inplace (tsc.py:219-226), which never touches in-range entries.
-        flag = eng.zeros((1,), torch.int64)
-        check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(pos_d), N, float(box), ptr(flag)))
-        changed = int(flag.item())
-        if two_d and pos.shape[1] == 3:
-            # the reference wraps every column of the caller's array, also the third one a 2-D grid never reads
-            zc = pos_in[:, 2]
-            changed += int(((zc >= box) | (zc < 0)).sum().item())
-        if changed and pos_d is not pos:
+        # tsc.py:171-173: the caller's array is wrapped in place.  The device copy is wrapped by the kernel (that is what
+        # gets painted); the CALLER's array is then updated entry by entry, in its own dtype and only where a value lies
+        # outside [0, box) -- like _wrap_inplace (tsc.py:219-226), which never touches in-range entries.
+        if typed:
+            changed = int(((pos_in >= box) | (pos_in < 0)).sum().item())
+        else:
+            flag = eng.zeros((1,), torch.int64)
+            check(eng.lib.abk_wrap_inplace(eng.ctx, ptr(pos_d), N, float(box), ptr(flag)))
+            changed = int(flag.item())
+            if two_d and pos.shape[1] == 3:
+                # the reference wraps every column of the caller's array, also the third one a 2-D grid never reads
+                zc = pos_in[:, 2]
+                changed += int(((zc >= box) | (zc < 0)).sum().item())
+        if changed and (typed or pos_d is not pos):
             _wrap_caller_array(pos, float(box))
 
     # ---- grid on the device -------------------------------------------------------------------------
+    tgrid = torch.float64 if grid_dt == 'f8' else torch.float32
     grid_is_cuda = user_supplied_grid and is_torch_tensor(densgrid) and densgrid.is_cuda
-    if grid_is_cuda and densgrid.dtype == torch.float32 and densgrid.is_contiguous():
+    if grid_is_cuda and densgrid.dtype == tgrid and densgrid.is_contiguous():
         grid_d = densgrid
     else:
-        grid_d = eng.zeros(shape, torch.float32)
-    deposit_device(eng, pos_d, w_d, grid_d, shape3, shape3[2], box, offset, wrap=False)
+        grid_d = eng.zeros(shape, tgrid)
+    if typed:
+        if N > 0:
+            eng.bind_stream()
+            eng.set_scheme('TSC')
+            check(eng.lib.abk_tsc_deposit_typed(eng.ctx, ptr(pos_d), int(pos_dt == 'f8'), ptr(w_d), int(w_dt == 'f8'), N, ptr(grid_d),
+                                                int(grid_dt == 'f8'), shape3[0], shape3[1], shape3[2], shape3[2], float(box),
+                                                float(offset), int(bool(wrap))))
+    else:
+        deposit_device(eng, pos_d, w_d, grid_d, shape3, shape3[2], box, offset, wrap=False)
 
     if user_supplied_grid:
         if grid_d is not densgrid:
@@ -194,8 +222,9 @@ def partition_parallel(pos, npartition, boxsize, weights=None, coord=0, nthread=
     """
     Partition particles into ``npartition`` stripes along ``coord`` (reference: tsc.py:259-384).
 
-    Returns ``(partitioned, part_starts int64[npartition+1], wpart or None)``.  The order of
-    particles inside a stripe is unspecified unless ``sort=True`` (then sorted on ``coord``).
+    Returns ``(partitioned, part_starts int64[npartition+1], wpart or None)``.  Inside a stripe the
+    particles keep their input order (the reference's stable partition); with ``sort=True`` every stripe
+    is sorted on ``coord``.
     """
     import torch
 
@@ -215,8 +244,18 @@ def partition_parallel(pos, npartition, boxsize, weights=None, coord=0, nthread=
     nb = C.c_size_t()
     check(eng.lib.abk_partition_scratch_bytes(N, int(npartition), C.byref(nb)))
     scratch = eng.scratch('partition', nb.value)
+    src = eng.empty((N,), torch.int32)
     check(eng.lib.abk_partition(eng.ctx, ptr(pos_d), ptr(w_d), N, int(npartition), float(boxsize), int(coord),
-                                ptr(out_pos), ptr(out_w), ptr(starts), ptr(scratch), scratch.numel()))
+                                ptr(out_pos), ptr(out_w), ptr(starts), ptr(src), ptr(scratch), scratch.numel()))
+    if N > 1 and not sort:
+        # The reference's output is the STABLE partition (input order kept inside a stripe, tsc.py:338-376); the kernel's
+        # atomic scatter is not.  Stripes are contiguous row ranges, so ordering the rows of every stripe by their source
+        # index restores it: one sort of (stripe, source index) keys.
+        stripe = torch.searchsorted(starts[1:].contiguous(), torch.arange(N, device=starts.device), right=True)
+        order = torch.argsort((stripe << 32) | (src.to(torch.int64) & 0xffffffff))
+        out_pos = out_pos[order].contiguous()
+        if out_w is not None:
+            out_w = out_w[order].contiguous()
     if sort and N > 0:
         # tsc.py:361-367, :378-382 sort each stripe on the coordinate.  The stripe key is monotone in
         # pos[:, coord], so one global stable sort on the coordinate leaves the stripes where they are

@@ -177,3 +177,32 @@ extern "C" int abk_fft_plan_destroy(abk_fft_plan *plan)
     delete plan;
     return ABK_OK;
 }
+
+// In-place D2Z transform of a padded float64 grid [nx][ny][2 (nz/2+1)] -> complex128 [nx][ny][nz/2+1] (numpy rfftn
+// conventions, unnormalised).  The plan is created and destroyed per call (this is not the fast path); cuFFT allocates its
+// own work area here.
+extern "C" int abk_rfft3_f64(abk_ctx *ctx, double *grid_inplace, int64_t nx, int64_t ny, int64_t nz)
+{
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
+    ABK_REQUIRE(ctx && grid_inplace && nx > 0 && ny > 0 && nz > 0, "abk_rfft3_f64: bad arguments");
+    cufftHandle h;
+    long long n[3] = {nx, ny, nz};
+    const long long nzc = nz / 2 + 1;
+    long long rembed[3] = {nx, ny, 2 * nzc}, cembed[3] = {nx, ny, nzc};
+    size_t work = 0;
+    cufftResult r = cufftCreate(&h);
+    if (r == CUFFT_SUCCESS) r = cufftMakePlanMany64(h, 3, n, rembed, 1, nx * ny * 2 * nzc, cembed, 1, nx * ny * nzc, CUFFT_D2Z, 1, &work);
+    if (r == CUFFT_SUCCESS) r = cufftSetStream(h, ctx->stream);
+    if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
+    if (r == CUFFT_SUCCESS) r = cufftExecD2Z(h, grid_inplace, (cufftDoubleComplex *)grid_inplace);
+    if (ctx->prof_on) abk_prof_end(ctx);
+    ctx->launches++;
+    cudaStreamSynchronize(ctx->stream);  // the plan (and its work area) is destroyed below
+    cufftDestroy(h);
+    if (r != CUFFT_SUCCESS) {
+        abk_set_error("abk_rfft3_f64: cufft error %d", (int)r);
+        return ABK_ERR_CUFFT;
+    }
+    return ABK_OK;
+}
+

@@ -678,11 +678,8 @@ extern "C" int abk_normalize_field(abk_ctx *ctx, float *grid, int64_t nx, int64_
     return ABK_OK;
 }
 
-extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
-                                    float scale)
+static int finish_impl(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W, float scale, float phase_step)
 {
-    abk_device_guard entry_guard(ctx ? ctx->device : -1);
-    ABK_REQUIRE(ctx && mesh_h && f, "abk_field_fft_finish: null argument");
     int rc = check_mesh(*mesh_h);
     if (rc) return rc;
     FinishArgs F;
@@ -690,12 +687,27 @@ extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void 
     F.W = W;
     F.scale = scale;
     F.n = mesh_h->n;
-    F.inv_n = 1.0f / (float)mesh_h->n;
+    F.inv_n = phase_step;  // phase of mode (i', j', k) = pi * (i' + j' + k) * phase_step
     const int64_t nrows = (int64_t)(mesh_h->i1 - mesh_h->i0) * (mesh_h->j1 - mesh_h->j0);
     if (nrows == 0) return ABK_OK;
     ABK_LAUNCH(ctx, ABK_K_FINISH,
                finish_kernel<<<grid_for(ctx, nrows * 32, 256, 8), 256, 0, ctx->stream>>>((float2 *)f, F, *mesh_h));
     return ABK_OK;
+}
+
+extern "C" int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
+                                    float scale)
+{
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
+    ABK_REQUIRE(ctx && mesh_h && f, "abk_field_fft_finish: null argument");
+    return finish_impl(ctx, mesh_h, f, fs, W, scale, 1.0f / (float)mesh_h->n);
+}
+
+extern "C" int abk_shift_field_fft(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, double d_over_L, float scale)
+{
+    abk_device_guard entry_guard(ctx ? ctx->device : -1);
+    ABK_REQUIRE(ctx && mesh_h && f && fs, "abk_shift_field_fft: null argument");
+    return finish_impl(ctx, mesh_h, f, fs, nullptr, scale, (float)d_over_L);
 }
 
 extern "C" int abk_raw_power(abk_ctx *ctx, const void *f1, const void *f2, float *out, int64_t size)

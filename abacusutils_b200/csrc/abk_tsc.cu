@@ -696,7 +696,7 @@ template <bool SCATTER>
 __global__ void __launch_bounds__(256) partition_kernel(const float *__restrict__ pos, const float *__restrict__ w,
                                                         int64_t N, int npart, float inv_pwidth, int coord,
                                                         uint32_t *__restrict__ counts, float *__restrict__ out_pos,
-                                                        float *__restrict__ out_w)
+                                                        float *__restrict__ out_w, uint32_t *__restrict__ out_index)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
         const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
@@ -711,6 +711,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const float *__restrict_
             out_pos[3 * (int64_t)s + 1] = y;
             out_pos[3 * (int64_t)s + 2] = z;
             if (w) out_w[s] = w[i];
+            if (out_index) out_index[s] = (uint32_t)i;
         }
     }
 }
@@ -773,7 +774,7 @@ extern "C" int abk_partition_scratch_bytes(int64_t N, int npart, size_t *bytes)
 }
 
 extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int npart, double box,
-                             int coord, float *out_pos, float *out_w, int64_t *out_starts, void *scratch,
+                             int coord, float *out_pos, float *out_w, int64_t *out_starts, uint32_t *out_index, void *scratch,
                              size_t scratch_bytes)
 {
     abk_device_guard entry_guard(ctx ? ctx->device : -1);
@@ -791,10 +792,10 @@ extern "C" int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int
     const float inv_pwidth = (float)((double)npart / box);
     if (N > 0) {
         const int blocks = grid_for(ctx, N, 256, 16);
-        ABK_LAUNCH(ctx, ABK_K_PART_HIST, partition_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, nullptr, nullptr));
+        ABK_LAUNCH(ctx, ABK_K_PART_HIST, partition_kernel<false><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, nullptr, nullptr, nullptr));
         int rc = abk_inclusive_scan_u32(ctx, counts, npart, tmp);
         if (rc) return rc;
-        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, partition_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, out_pos, out_w));
+        ABK_LAUNCH(ctx, ABK_K_PART_SCATTER, partition_kernel<true><<<blocks, 256, 0, ctx->stream>>>(pos, w, N, npart, inv_pwidth, coord, counts, out_pos, out_w, out_index));
     }
     ABK_LAUNCH(ctx, ABK_K_MISC, starts_to_i64_kernel<<<(npart + 256) / 256, 256, 0, ctx->stream>>>(counts, npart, N, out_starts));
     return ABK_OK;

@@ -85,11 +85,13 @@ int abk_wrap_inplace(abk_ctx *ctx, float *pos, int64_t N, double box, int64_t *n
 
 /* tsc.py:259-384 `partition_parallel`: counting sort of particles into `npart` stripes along
  * `coord`; key = min(int32(pos[coord] * f32(npart/box)), npart-1).  out_starts is int64[npart+1].
- * The order of particles inside a stripe is unspecified (atomic scatter), which the reference's
- * own test allows (tests/test_tsc.py:194-208).  scratch: abk_partition_scratch_bytes(). */
+ * The order of particles inside a stripe as written by the kernel is unspecified (atomic scatter), which the
+ * reference's own test allows (tests/test_tsc.py:194-208); out_index (uint32[N], may be NULL) receives the source
+ * index of every output row, from which the host layer restores the reference's stable order (threads own contiguous
+ * input ranges there, tsc.py:338-376).  scratch: abk_partition_scratch_bytes(). */
 int abk_partition_scratch_bytes(int64_t N, int npart, size_t *bytes);
 int abk_partition(abk_ctx *ctx, const float *pos, const float *w, int64_t N, int npart, double box,
-                  int coord, float *out_pos, float *out_w, int64_t *out_starts, void *scratch,
+                  int coord, float *out_pos, float *out_w, int64_t *out_starts, uint32_t *out_index, void *scratch,
                   size_t scratch_bytes);
 
 /* Particle bucketing for the deposit (replaces the x-stripe partition of tsc.py:178-188 and the
@@ -219,6 +221,10 @@ typedef struct abk_kmesh {
  * i' = i (i < n/2) else i-n, likewise j'. */
 int abk_field_fft_finish(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, const float *W,
                          float scale);
+/* power_spectrum.py:904-948 `shift_field_fft` for an arbitrary shift d of the second field:
+ *     f <- (f + fs * exp(i * 0.5 d (kx+ky+kz))) * scale = (f + fs * exp(i*pi*(i'+j'+k) * d/L)) * scale
+ * (abk_field_fft_finish is the d = L/n case fused with the window division). */
+int abk_shift_field_fft(abk_ctx *ctx, const abk_kmesh *mesh_h, void *f, const void *fs, double d_over_L, float scale);
 
 /* power_spectrum.py:707-727 `get_raw_power`: out[t] = |f1[t]|^2, or Re(conj(f1[t]) f2[t]) when f2 != NULL,
  * over `size` complex64 elements (materialised; calc_power itself uses the fused abk_power_bin). */
@@ -348,6 +354,24 @@ int abk_transpose_pack(abk_ctx *ctx, const void *slab, void *sendbuf, int64_t nx
  * torch symmetric memory).  The caller synchronises the ranks before (buffer free) and after (writes landed). */
 int abk_transpose_scatter_p2p(abk_ctx *ctx, const void *slab, void *const *peer_pencils_h, int64_t nxl, int64_t ny,
                               int64_t nzc, int nranks, const int64_t *jsplit_h, int64_t x_lo);
+
+/* ---- float64 --------------------------------------------------------------------
+ * The reference's TSC computes in the dtype of the positions and accumulates in the dtype of the grid (tsc.py:400,
+ * :471-507); calc_power(dtype=float64) honours the dtype on its non-interlaced branch (power_spectrum.py:1053-1069).
+ * float32 / float32 is the fast path (abk_tsc_deposit); every other combination takes these entry points:
+ * one thread per particle, 27 global reductions in the grid's dtype, arithmetic in the positions' dtype.
+ *   pos  : float32 or float64 [N][3] (pos_f64), w: NULL or float32 / float64 [N] (w_f64), grid: float32 / float64 [nx][ny][ldz] */
+int abk_tsc_deposit_typed(abk_ctx *ctx, const void *pos, int pos_f64, const void *w, int w_f64, int64_t N, void *grid,
+                          int grid_f64, int nx, int ny, int nz, int64_t ldz, double box, double offset, int wrap);
+/* normalize_field in float64: grid = grid * (size_total / tot_weight) - 1 (power_spectrum.py:860-901) */
+int abk_normalize_field_f64(abk_ctx *ctx, double *grid, int64_t nx, int64_t ny, int64_t nz, int64_t ldz, double size_total,
+                            double tot_weight);
+/* in-place D2Z transform of a padded float64 grid [nx][ny][2(nz/2+1)] -> complex128 [nx][ny][nz/2+1] (scipy.fft.rfftn
+ * of a float64 field, power_spectrum.py:1059); synchronises the stream */
+int abk_rfft3_f64(abk_ctx *ctx, double *grid_inplace, int64_t nx, int64_t ny, int64_t nz);
+/* power_spectrum.py:1058-1069 + :707-727 on complex128 spectra: f *= inv_size, f /= (W_i W_j) W_k (W may be NULL),
+ * out = |f1|^2 or Re(conj(f1) f2) as the float32 mesh [n][n][n/2+1] that abk_power_bin reads (real_in) */
+int abk_power_from_f64(abk_ctx *ctx, const void *f1, const void *f2, const float *W, int n, double inv_size, float *out);
 
 #ifdef __cplusplus
 }

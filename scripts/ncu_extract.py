@@ -37,8 +37,8 @@ def num(v):
 
 def main(reps):
     h = hashlib.sha256()
-    for src in sorted((ROOT / 'abacusutils_b200' / 'csrc').glob('abk_*.cu*')):
-        h.update(src.read_bytes())
+    for name in ('abk_common.cuh', 'abk_kspace.cu', 'abk_tsc.cu'):      # the sources of the profiled kernels
+        h.update((ROOT / 'abacusutils_b200' / 'csrc' / name).read_bytes())
     out = {'csrc_sha256': h.hexdigest(), 'captures': [Path(r).name for r in reps], 'kernels': {}}
     for rep in reps:
         txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout

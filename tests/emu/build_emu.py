@@ -16,7 +16,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / 'abacusutils_b200' / 'csrc'
-SOURCES = ['abk_ctx.cu', 'abk_ingest.cu', 'abk_kfields.cu', 'abk_kspace.cu', 'abk_tsc.cu']
+SOURCES = ['abk_ctx.cu', 'abk_ingest.cu', 'abk_kfields.cu', 'abk_kspace.cu', 'abk_tsc.cu', 'abk_f64.cu']
 
 LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(', re.S)
 PTX_HINT = re.compile(r'asm\s+volatile\s*\(\s*"prefetch[^;]*;[^;]*;')   # the PTX string itself ends in ';'

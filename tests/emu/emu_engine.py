@@ -65,6 +65,15 @@ class EmuLib:
         _view(grid, np.complex64, nx * ny * (nz // 2 + 1)).reshape(nx, ny, nz // 2 + 1)[...] = spec
         return 0
 
+    def abk_rfft3_f64(self, ctx, grid, nx, ny, nz):
+        from scipy.fft import rfftn
+
+        ldz = 2 * (nz // 2 + 1)
+        real = _view(grid, np.float64, nx * ny * ldz).reshape(nx, ny, ldz)
+        spec = rfftn(real[:, :, :nz].copy())
+        _view(grid, np.complex128, nx * ny * (nz // 2 + 1)).reshape(nx, ny, nz // 2 + 1)[...] = spec
+        return 0
+
     def abk_irfft3_exec(self, ctx, plan, grid, work, work_bytes):
         from scipy.fft import irfftn
 

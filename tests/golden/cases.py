@@ -271,3 +271,17 @@ def pack9_inputs(seed, nrec, hdr_frac=0.05, cpd=875, first_header=True):
         setfield(f, rng.integers(-2000, cpd - 2000, nh))
     d[idx, 0] = 0xFF
     return d
+
+
+# ---------------------------------------------------------------- float64 (tests/golden/make_golden_f64.py)
+def f64_inputs(seed=71, N=6000, box=77.0):
+    """float64 positions whose low bits matter (not representable in float32), some outside [0, box); float64 weights."""
+    rng = np.random.default_rng(seed)
+    pos = rng.random((N, 3)) * box
+    pos[:40] += box * rng.integers(-1, 2, size=(40, 3))
+    pos = np.clip(pos, -0.999 * box, 1.999 * box)
+    w = rng.random(N) + 0.5
+    return pos, w
+
+
+F64_POWER = dict(seed=72, N=30000, L=600.0, nmesh=36, kbins=14, mubins=3, poles=[0, 2, 4])

@@ -122,9 +122,13 @@ def test_partition_parallel(emu, golden):
     ppart, starts, wpart = tsc.partition_parallel(pos, c['npartition'], c['box'], weights=w)
     np.testing.assert_array_equal(starts, golden[f'partition/{name}/starts'])
     ref = golden[f'partition/{name}/ppart']
-    for i in range(c['npartition']):                       # same multiset per stripe (the scatter order is free)
+    for i in range(c['npartition']):                       # same multiset per stripe
         a, b = starts[i], starts[i + 1]
         np.testing.assert_array_equal(np.sort(ppart[a:b].view('f4,f4,f4'), axis=0), np.sort(ref[a:b].view('f4,f4,f4'), axis=0))
+    # and the same ORDER as the unmodified reference: its output is the stable partition, restored from the source indices
+    np.testing.assert_array_equal(ppart, ref)
+    if f'partition/{name}/wpart' in golden.files:
+        np.testing.assert_array_equal(wpart, golden[f'partition/{name}/wpart'])
 
 
 def test_ingest_through_the_product_wrappers(emu, oracle):
@@ -268,3 +272,37 @@ def test_wrap_writes_back_only_changed_entries_in_callers_dtype(emu):
     b2 = p2.copy()
     tsc.tsc_parallel(p2, (12, 12), box)
     assert (p2 != b2).sum() == 1 and p2[5, 2] == np.float32(97.0)
+
+
+@pytest.mark.parametrize('pd,gd,wd', [('f8', 'f8', 'f8'), ('f4', 'f8', None), ('f8', 'f4', 'f4'), ('f4', 'f8', 'f8')])
+def test_tsc_parallel_float64(emu, pd, gd, wd):
+    import f64_checks
+
+    f64_checks.check_tsc_parallel(pd, gd, wd)
+
+
+@pytest.mark.parametrize('name', ['auto_w', 'cross'])
+def test_calc_power_float64(emu, name):
+    import f64_checks
+
+    f64_checks.check_calc_power(name)
+
+
+def test_shift_field_fft_any_shift(emu, oracle):
+    """shift_field_fft (power_spectrum.py:904-948) for the interlacing shift and for arbitrary d, against the oracle and --
+    where the live reference is importable -- against the reference itself."""
+    from abacusutils_b200.analysis import power_spectrum as ps
+    from oracle import ref_shim
+
+    c = cases.DELTAK_CASES['d32']
+    f1, f2, _ = cases.deltak_inputs(c)
+    ref = ref_shim.load(2)[1] if ref_shim.available() else None
+    for d in (c['L'] / c['n'], 0.37 * c['L'] / c['n'], 2.5 * c['L'] / c['n'], -0.8):
+        a, b = f1.copy(), f1.copy()
+        ps.shift_field_fft(a, f2, c['n'], c['L'], d)
+        oracle.shift_field_fft(b, f2, c['n'], c['L'], d, nthread=2)
+        assert np.abs(a - b).max() < 2e-6 * np.abs(b).max(), d
+        if ref is not None:
+            r = f1.copy()
+            ref.shift_field_fft(r, f2, c['n'], c['L'], d)
+            assert np.abs(a - r).max() < 2e-6 * np.abs(r).max(), d

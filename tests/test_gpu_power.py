@@ -132,6 +132,11 @@ def test_shift_field_fft(ps, oracle):
     ps.shift_field_fft(a, f2, c['n'], c['L'], c['L'] / c['n'])
     oracle.shift_field_fft(b, f2, c['n'], c['L'], c['L'] / c['n'], nthread=2)
     assert np.abs(a - b).max() < 1e-6 * np.abs(b).max()
+    for d in (0.37 * c['L'] / c['n'], 2.5 * c['L'] / c['n'], -0.8):      # any shift, not only the interlacing one
+        a, b = f1.copy(), f1.copy()
+        ps.shift_field_fft(a, f2, c['n'], c['L'], d)
+        oracle.shift_field_fft(b, f2, c['n'], c['L'], d, nthread=2)
+        assert np.abs(a - b).max() < 2e-6 * np.abs(b).max(), d
 
 
 @pytest.mark.parametrize('name', list(cases.POWER_CASES))
@@ -344,3 +349,16 @@ def test_clustered_anisotropic_vs_oracle(ps, oracle, weighted):
     big[0] = False
     rel = np.abs(np.asarray(got['poles'], 'f8') - want['poles'])[big] / np.abs(want['poles'])[big]
     assert rel.max() < 1e-4, rel.max()
+
+
+def test_meta_carries_kernel_timings(ps, monkeypatch):
+    """ABK_META_TIMINGS=1: per-kernel CUDA-event times of the call in meta['kernel_ms']."""
+    c = cases.POWER_CASES['n32_ci']
+    pos, w, _, _ = cases.power_inputs(c)
+    monkeypatch.setenv('ABK_META_TIMINGS', '1')
+    t = ps.calc_power(pos, c['L'], kbins=16, mubins=4, nmesh=32, w=w, poles=[0, 2, 4])
+    km = t.meta['kernel_ms']
+    assert {'tsc_bucket_scatter', 'tsc_tile_deposit', 'cufft', 'power_bin'} <= set(km)
+    assert all(v['ms'] > 0 and v['launches'] >= 1 for v in km.values())
+    monkeypatch.delenv('ABK_META_TIMINGS')
+    assert 'kernel_ms' not in ps.calc_power(pos, c['L'], kbins=16, mubins=4, nmesh=32, w=w).meta

@@ -205,6 +205,9 @@ def test_partition(tsc, seed, npartition, sort):
         assert np.array_equal(got, want)
         if sort:
             assert np.all(np.diff(ppart[a:b, coord]) >= 0)
+    if not sort:
+        # the reference's output is exactly the stable partition: same here, row for row
+        assert np.array_equal(ppart, spos) and np.array_equal(wpart, sw)
 
 
 def test_deposit_with_foreign_bucket_offset(oracle):
