@@ -321,6 +321,8 @@ class _Painter:
         if host and nseg >= 6:
             groups = max(1, int(os.environ.get('ABK_EARLY_GROUPS', '1')))
             tail = max(3, -(-3 * nseg // 10)) if groups == 1 else max(2, -(-(2 if groups == 2 else 1.5) * nseg // 10))
+            if os.environ.get('ABK_TAIL_SEGMENTS'):      # experiment knob: segments left for the un-overlapped tail
+                tail = max(1, min(nseg - 1, int(os.environ['ABK_TAIL_SEGMENTS'])))
             split = nseg - int(tail)
             cuts = sorted({max(1, round(split * (j + 1) / groups)) for j in range(groups)})
         early_done = None

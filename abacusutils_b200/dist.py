@@ -29,7 +29,7 @@ import time
 
 import numpy as np
 
-from ._lib import ABK_MAX_SEGMENTS, BinRequest, Engine, KMesh, check, ptr
+from ._lib import ABK_MAX_SEGMENTS, BinRequest, Engine, KMesh, check, is_torch_tensor, ptr
 from .analysis import power_spectrum as ps
 from .analysis.tsc import padded_ldz
 
@@ -320,8 +320,21 @@ class DistEngine:
         lib = eng.lib
         eng.bind_stream()
         eng.set_scheme(paste)
-        pos_d = eng.to_device(pos, torch.float32)
-        w_d = None if w is None else eng.to_device(w, torch.float32)
+        # host inputs (CPU torch tensors / NumPy arrays of float32): copied chunk by chunk on a copy stream further down, so
+        # that the bucketing of chunk c overlaps the host->device copy of chunk c+1; anything else is moved up front
+        host_src = None
+        if not (is_torch_tensor(pos) and pos.is_cuda):
+            src = pos if is_torch_tensor(pos) else torch.from_numpy(np.ascontiguousarray(pos))
+            wsrc = None if w is None else (w if is_torch_tensor(w) else torch.from_numpy(np.ascontiguousarray(w)))
+            if src.dtype == torch.float32 and src.is_contiguous() and src.device.type == 'cpu' and \
+                    (wsrc is None or (wsrc.dtype == torch.float32 and wsrc.is_contiguous() and wsrc.device.type == 'cpu')):
+                host_src = (src, wsrc)
+        if host_src is not None:
+            pos_d = eng.empty(tuple(host_src[0].shape), torch.float32)
+            w_d = None if w is None else eng.empty((int(host_src[0].shape[0]),), torch.float32)
+        else:
+            pos_d = eng.to_device(pos, torch.float32)
+            w_d = None if w is None else eng.to_device(w, torch.float32)
         N = int(pos_d.shape[0])
         nty, ntz = -(-n // TILE_Y), -(-n // TILE_Z)
         per_col = nty * ntz
@@ -349,9 +362,25 @@ class DistEngine:
         segs, keep, total = [], [], 0
         compute = eng.bind_stream()
 
+        copied = {}
+        if host_src is not None and N > 0:
+            copy_stream = self._copy_stream()
+            copy_stream.wait_stream(compute)
+            with torch.cuda.stream(copy_stream):
+                for c in range(nchunk):
+                    a, bnd = min(c * csize, N), min((c + 1) * csize, N)
+                    if bnd > a:
+                        pos_d[a:bnd].copy_(host_src[0][a:bnd], non_blocking=True)
+                        if w_d is not None:
+                            w_d[a:bnd].copy_(host_src[1][a:bnd], non_blocking=True)
+                    copied[c] = torch.cuda.Event()
+                    copied[c].record(copy_stream)
+
         def bucket(c):
             a, bnd = min(c * csize, N), min((c + 1) * csize, N)
             m = bnd - a
+            if c in copied:
+                compute.wait_event(copied[c])
             if self.world == 1:
                 rec = eng.scratch(f'route_out{c}', max(m, 1) * 16)
                 starts = eng.scratch(f'route_starts{c}', (ntiles + 1) * 4).view(torch.int32)[: ntiles + 1]
@@ -398,6 +427,13 @@ class DistEngine:
             del rows, starts
         compute.wait_stream(comm)
         return segs, total, keep
+
+    def _copy_stream(self):
+        import torch
+
+        if getattr(self.eng, '_copy', None) is None:
+            self.eng._copy = torch.cuda.Stream(device=self.device)
+        return self.eng._copy
 
     def _comm_stream(self):
         import torch

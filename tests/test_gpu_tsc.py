@@ -280,3 +280,33 @@ def test_clustered_grid_large(tsc, oracle):
     oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
     assert want.max() > 200 * want.mean()
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * max(1.0, float(want.max()) * 1e-2))
+
+
+def test_64bit_indexing_2048_cubed(tsc, oracle):
+    """Values (not just sums) on a mesh whose flat indices exceed 2^32 bytes and 2^31 elements: 3e5 weighted particles in the
+    LAST x-planes of a 2048^3 float32 grid (34 GB; element offsets up to 8.6e9), wrapping around to plane 0, against the
+    oracle.  The oracle's grid is calloc'ed and only touched near the particles, so the host cost is ~1 GB."""
+    import torch
+
+    n, box = 2048, 2048.0
+    free, _ = torch.cuda.mem_get_info()
+    if free < 45 * 2**30:
+        pytest.skip('needs 45 GB of free device memory')
+    rng = np.random.default_rng(64)
+    N = 300_000
+    pos = np.empty((N, 3), np.float32)
+    pos[:, 0] = (2000.0 + rng.random(N) * 48.0).astype(np.float32)      # cells 2000 .. 2048 -> planes 1999 .. 2047 and 0
+    pos[:, 1:] = (rng.random((N, 2)) * box).astype(np.float32)
+    pos = np.minimum(pos, np.nextafter(np.float32(box), np.float32(0)))
+    w = rng.random(N, dtype=np.float32)
+    grid = torch.zeros((n, n, n), dtype=torch.float32, device='cuda')
+    assert tsc.tsc_parallel(torch.from_numpy(pos).cuda(), grid, box, weights=torch.from_numpy(w).cuda()) is None
+    want = np.zeros((n, n, n), np.float32)
+    oracle.tsc_parallel(pos.copy(), want, box, weights=w, nthread=1)
+    total = float(grid.sum(dtype=torch.float64).item())
+    assert abs(total - float(w.sum(dtype=np.float64))) < 1e-6 * total
+    for sl in (slice(1996, 2048), slice(0, 3)):
+        got = grid[sl].cpu().numpy()
+        assert np.abs(want[sl]).sum() > 0
+        np.testing.assert_allclose(got, want[sl], rtol=1e-4, atol=1e-5)
+    assert float(grid[3:1996].abs().max().item()) == 0.0
