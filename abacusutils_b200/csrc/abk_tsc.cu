@@ -310,20 +310,45 @@ __device__ __forceinline__ void mas_pair(float d, float W, float2 &wmp, float &w
 template <bool CIC>
 __device__ __forceinline__ void accumulate_particle(const float4 r, Plane &A, Plane &B, Plane &C)
 {
-    float2 X2, Y2, Z2;
-    float x0, y0, z0;
-    mas_pair<CIC>(r.x, 1.0f, X2, x0);
-    mas_pair<CIC>(r.y, r.w, Y2, y0);
-    mas_pair<CIC>(r.z, 1.0f, Z2, z0);
+    if (CIC) {
+        float2 X2, Y2, Z2;
+        float x0, y0, z0;
+        mas_pair<true>(r.x, 1.0f, X2, x0);
+        mas_pair<true>(r.y, r.w, Y2, y0);
+        mas_pair<true>(r.z, 1.0f, Z2, z0);
+        float2 T[3];
+        T[0] = __fmul2_rn(Z2, make_float2(Y2.x, Y2.x));
+        T[1] = __fmul2_rn(Z2, make_float2(y0, y0));
+        T[2] = __fmul2_rn(Z2, make_float2(Y2.y, Y2.y));
+        const float2 U = __fmul2_rn(Y2, make_float2(z0, z0));
+        const float u0 = y0 * z0;
+        plane_fma(A, X2.x, T, U, u0);
+        plane_fma(B, x0, T, U, u0);
+        plane_fma(C, X2.y, T, U, u0);
+        return;
+    }
+    // TSC (tsc.py:442-451): w-+ = 0.5 (0.5 +- d)^2 = (c +- d/sqrt2)^2 with c = 0.5/sqrt2 -- one packed FMA and one packed
+    // square per pair, no separate halving; x and y share the packed operations ((dx, dy) is a register pair of the
+    // record as loaded), the particle weight rides on the z factors.
+    constexpr float K = 0.70710678118654752f, CC = 0.35355339059327376f;
+    const float2 dxy = make_float2(r.x, r.y);
+    const float2 am = __ffma2_rn(dxy, make_float2(K, K), make_float2(CC, CC));
+    const float2 ap = __ffma2_rn(dxy, make_float2(-K, -K), make_float2(CC, CC));
+    const float2 Sm = __fmul2_rn(am, am);                                              // (x-, y-)
+    const float2 Sp = __fmul2_rn(ap, ap);                                              // (x+, y+)
+    const float2 S0 = __ffma2_rn(make_float2(-r.x, -r.y), dxy, make_float2(0.75f, 0.75f));  // (x0, y0)
+    const float zm = fmaf(r.z, K, CC), zp = fmaf(r.z, -K, CC);
+    const float2 Z2 = __fmul2_rn(__fmul2_rn(make_float2(zm, zp), make_float2(zm, zp)), make_float2(r.w, r.w));  // (z-, z+) W
+    const float z0 = fmaf(-r.z, r.z, 0.75f) * r.w;
     float2 T[3];
-    T[0] = __fmul2_rn(Z2, make_float2(Y2.x, Y2.x));
-    T[1] = __fmul2_rn(Z2, make_float2(y0, y0));
-    T[2] = __fmul2_rn(Z2, make_float2(Y2.y, Y2.y));
-    const float2 U = __fmul2_rn(Y2, make_float2(z0, z0));
-    const float u0 = y0 * z0;
-    plane_fma(A, X2.x, T, U, u0);
-    plane_fma(B, x0, T, U, u0);
-    plane_fma(C, X2.y, T, U, u0);
+    T[0] = __fmul2_rn(Z2, make_float2(Sm.y, Sm.y));
+    T[1] = __fmul2_rn(Z2, make_float2(S0.y, S0.y));
+    T[2] = __fmul2_rn(Z2, make_float2(Sp.y, Sp.y));
+    const float2 U = make_float2(Sm.y * z0, Sp.y * z0);
+    const float u0 = S0.y * z0;
+    plane_fma(A, Sm.x, T, U, u0);
+    plane_fma(B, S0.x, T, U, u0);
+    plane_fma(C, Sp.x, T, U, u0);
 }
 
 template <int EXT>
