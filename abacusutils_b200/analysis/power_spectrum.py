@@ -362,6 +362,16 @@ class _Painter:
                 ready[sl].record(copy_stream)
             staged[si] = (pd_, wd_)
 
+        nbs = min(nseg, max(1, int(os.environ.get('ABK_BUCKET_STREAMS', '2')))) if not host else 1
+        bstreams, scan_ptrs = [], []
+        if nbs > 1:
+            if len(getattr(eng, '_bstreams', [])) < nbs - 1:
+                eng._bstreams = [torch.cuda.Stream(device=eng.device) for _ in range(nbs - 1)]
+            bstreams = eng._bstreams[: nbs - 1]
+            for i, bs in enumerate(bstreams):
+                sb = eng.scratch(f'bucket_scan_side{i}', nb.value + 256)
+                scan_ptrs.append(C.c_void_p((sb.data_ptr() + 255) & ~255))
+                bs.wait_stream(compute)
         issued = 0
         for s, (a, b) in enumerate(chunks):
             m = b - a
@@ -385,11 +395,24 @@ class _Painter:
                 wd = None if wsrc is None else wsrc[a:b]
                 if not pd.is_contiguous():
                     pd = pd.contiguous()
-            for o in range(nbuck):
-                rec_ptr = records[o].data_ptr() + a * 16
-                st_ptr = starts[o].data_ptr() + s * starts_stride * 4
-                check(bucket_fn(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]), int(bool(wrap)),
-                                C.c_void_p(rec_ptr), C.c_void_p(st_ptr), scan_ptr, nb.value))
+            # Device-resident input: the segments are independent, so odd segments are bucketed on a second stream -- the
+            # histogram pass of one segment (bound by the L2 reduction rate) then shares the GPU with the scatter pass of
+            # another (bound by store / translation latency at 12 % issue utilisation) instead of running after it.
+            side = (s % nbs) if nbs > 1 else 0
+            if side:
+                with torch.cuda.stream(bstreams[side - 1]):
+                    eng.bind_stream()
+                    for o in range(nbuck):
+                        check(bucket_fn(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]), int(bool(wrap)),
+                                        C.c_void_p(records[o].data_ptr() + a * 16), C.c_void_p(starts[o].data_ptr() + s * starts_stride * 4),
+                                        scan_ptrs[side - 1], nb.value))
+                eng.bind_stream()
+            else:
+                for o in range(nbuck):
+                    rec_ptr = records[o].data_ptr() + a * 16
+                    st_ptr = starts[o].data_ptr() + s * starts_stride * 4
+                    check(bucket_fn(eng.ctx, ptr(pd), ptr(wd), m, n, n, n, self.L, float(offsets[o]), int(bool(wrap)),
+                                    C.c_void_p(rec_ptr), C.c_void_p(st_ptr), scan_ptr, nb.value))
             if host:
                 done[slot].record(compute)
             if (s + 1) in cuts:
@@ -402,6 +425,8 @@ class _Painter:
                 early_done = torch.cuda.Event()
                 early_done.record(aux)
 
+        for bs in bstreams:
+            compute.wait_stream(bs)
         if packed is not None:
             packed.n_particles = int(sum(counts))
             if fft_weight is not None:
