@@ -144,7 +144,8 @@ def _torch():
 
 
 class Engine:
-    """Per-device state: library context, cached FFT plans and reusable scratch buffers."""
+    """Per-device state: library context, cached FFT plans and reusable scratch buffers.  Not thread-safe: the context
+    carries ONE current stream (``bind_stream``); use one Engine per host thread or serialise the calls."""
 
     _instances: dict = {}
     _lock = threading.Lock()
@@ -241,6 +242,10 @@ class Engine:
         torch = _torch()
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and buf.is_cuda:
+                # scratch is shared between the compute, copy and auxiliary streams without allocator bookkeeping: before
+                # a buffer is handed back (regrowth, rare) nothing may still be using it on any stream
+                torch.cuda.synchronize(self.device)
             self._bufs.pop(key, None)
             buf = None
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
@@ -248,6 +253,8 @@ class Engine:
         return buf
 
     def release_scratch(self):
+        if self._bufs and next(iter(self._bufs.values())).is_cuda:
+            _torch().cuda.synchronize(self.device)
         self._bufs.clear()
 
     def to_device(self, arr, dtype=None):

@@ -201,7 +201,7 @@ def transpose_slab_to_pencil(packed, plan, rank, group=None):
 
 
 # ------------------------------------------------------------------------------------------- peer memory
-_SYMM = {'ok': None, 'bufs': {}}
+_SYMM = {'ok': {}, 'bufs': {}}      # per process group: symmetric memory usable?, cached buffers
 
 # optional phase timing (bench.py's multi-GPU arm): CUDA-event pairs on the current stream around the phases of the step
 _PHASES = {'on': False, 'recs': []}
@@ -248,28 +248,36 @@ def _symm_pencil(group, nelem, slot, device):
 
     import torch
 
-    if os.environ.get('ABK_NO_P2P') == '1' or _SYMM['ok'] is False:
-        return None
     key = (id(group), slot)
+    if os.environ.get('ABK_NO_P2P') == '1' or _SYMM['ok'].get(id(group)) is False:
+        return None
     ent = _SYMM['bufs'].get(key)
     if ent is not None and ent[0].numel() >= nelem:
         return ent
+    dist = _dist()
+    g = group if group is not None else dist.group.WORLD
+    got, err = None, None
     try:
         import torch.distributed._symmetric_memory as symm_mem
 
-        dist = _dist()
-        g = group if group is not None else dist.group.WORLD
         t = symm_mem.empty(int(nelem), dtype=torch.complex64, device=device)
         hdl = symm_mem.rendezvous(t, g)
-        _SYMM['ok'] = True
-        _SYMM['bufs'][key] = (t, hdl)
-        return t, hdl
+        got = (t, hdl)
     except Exception as e:  # pragma: no cover - depends on the platform
+        err = e
+    # every rank must take the same path (peer stores + device barriers vs NCCL all-to-all): agree on the outcome
+    flag = torch.tensor([1 if got is not None else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
         import warnings
 
-        warnings.warn(f'symmetric memory unavailable ({type(e).__name__}: {e}); the FFT transpose uses NCCL all-to-all')
-        _SYMM['ok'] = False
+        why = f'{type(err).__name__}: {err}' if err is not None else 'failed on another rank'
+        warnings.warn(f'symmetric memory unavailable ({why}); the FFT transpose uses NCCL all-to-all')
+        _SYMM['ok'][id(group)] = False
         return None
+    _SYMM['ok'][id(group)] = True
+    _SYMM['bufs'][key] = got
+    return got
 
 
 # ------------------------------------------------------------------------------------------- pipeline
