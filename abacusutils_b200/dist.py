@@ -384,22 +384,38 @@ class DistEngine:
                     copied[c] = torch.cuda.Event()
                     copied[c].record(copy_stream)
 
+        # odd chunks are bucketed on a second stream: the histogram pass of chunk c+1 (L2-reduction-bound) shares the GPU with
+        # the scatter pass of chunk c (latency-bound), as in the single-GPU painter
+        side = None
+        if nchunk > 1 and os.environ.get('ABK_BUCKET_STREAMS', '2') != '1':
+            side = self._side_stream()
+            side.wait_stream(compute)
+            scan_side = eng.scratch('bucket_scan_side0', nb.value + 256)
+            scan_ptr_side = C.c_void_p((scan_side.data_ptr() + 255) & ~255)
+
         def bucket(c):
             a, bnd = min(c * csize, N), min((c + 1) * csize, N)
             m = bnd - a
+            st = side if (side is not None and (c & 1)) else compute
             if c in copied:
-                compute.wait_event(copied[c])
+                st.wait_event(copied[c])
             if self.world == 1:
                 rec = eng.scratch(f'route_out{c}', max(m, 1) * 16)
                 starts = eng.scratch(f'route_starts{c}', (ntiles + 1) * 4).view(torch.int32)[: ntiles + 1]
             else:  # send-side buffers are dead after the exchange: plain tensors, returned to the allocator
                 rec = torch.empty(max(m, 1) * 16, dtype=torch.uint8, device=self.device)
                 starts = torch.empty(ntiles + 1, dtype=torch.int32, device=self.device)
+                if rec.is_cuda and st is not compute:
+                    rec.record_stream(st)
+                    starts.record_stream(st)
+            with torch.cuda.stream(st):
+                eng.bind_stream()
+                check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
+                                         m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts),
+                                         scan_ptr_side if st is not compute else scan_ptr, nb.value))
+                ev = torch.cuda.Event()
+                ev.record(st)
             eng.bind_stream()
-            check(lib.abk_tsc_bucket(eng.ctx, ptr(pos_d[a:bnd]) if m else None, ptr(w_d[a:bnd]) if (w_d is not None and m) else None,
-                                     m, n, n, n, float(Lbox), 0.0, wrap, ptr(rec), ptr(starts), scan_ptr, nb.value))
-            ev = torch.cuda.Event()
-            ev.record(compute)
             return rec[: m * 16].view(torch.float32).view(m, 4), starts, m, ev
 
         if self.world == 1:
@@ -408,6 +424,8 @@ class DistEngine:
                 segs.append((rows.data_ptr(), starts.data_ptr(), m))
                 keep += [rows, starts]
                 total += m
+            if side is not None:
+                compute.wait_stream(side)
             return segs, total, keep
 
         comm = self._comm_stream()
@@ -434,7 +452,16 @@ class DistEngine:
             total += off
             del rows, starts
         compute.wait_stream(comm)
+        if side is not None:
+            compute.wait_stream(side)
         return segs, total, keep
+
+    def _side_stream(self):
+        import torch
+
+        if getattr(self.eng, '_side', None) is None:
+            self.eng._side = torch.cuda.Stream(device=self.device)
+        return self.eng._side
 
     def _copy_stream(self):
         import torch
