@@ -611,7 +611,17 @@ __global__ void __launch_bounds__(256) transpose_scatter_p2p_kernel(const float2
         const int64_t nyl = s_js[r + 1] - s_js[r];
         const float2 *src = slab + row * nzc;
         float2 *dst = s_peer[r] + ((x_lo + x) * nyl + (j - s_js[r])) * nzc;
-        for (int64_t k = lane; k < nzc; k += 32) dst[k] = src[k];
+        // 16-byte peer stores (two modes per lane and instruction): rows are nzc * 8 bytes long, so every other row starts
+        // 8 bytes off a 16-byte boundary -- one leading mode goes alone there, and one trailing mode where the rest is odd
+        const int64_t k0 = (reinterpret_cast<uintptr_t>(dst) & 8) ? 1 : 0;
+        if (k0 && lane == 0) dst[0] = src[0];
+        const int64_t npair = (nzc - k0) >> 1;
+        for (int64_t p = lane; p < npair; p += 32) {
+            const int64_t k = k0 + 2 * p;
+            const float2 a = src[k], b = src[k + 1];
+            *reinterpret_cast<float4 *>(dst + k) = make_float4(a.x, a.y, b.x, b.y);
+        }
+        if (((nzc - k0) & 1) && lane == 31) dst[nzc - 1] = src[nzc - 1];
     }
 }
 

@@ -678,10 +678,12 @@ class DistEngine:
         eng.bind_stream()
         check(eng.lib.abk_power_bin(eng.ctx, C.byref(req)))
         if self.world > 1:
-            # counts are exact integers: reduce them as int64, the float sums as float64
+            # ONE all-reduce for counts and sums: the integer mode counts travel as float64, which is exact (every count
+            # and every partial sum of counts is far below 2^53), and are turned back into int64 bit patterns afterwards
             cnt = sums[:Nb].view(torch.int64)
-            dist.all_reduce(cnt, group=self.group)
-            dist.all_reduce(sums[Nb:], group=self.group)
+            sums[:Nb] = cnt.to(torch.float64)
+            dist.all_reduce(sums, group=self.group)
+            cnt.copy_(sums[:Nb].round().to(torch.int64))
         return ps._finalize_bins(sums, Nk, Nmu, poles, dk)
 
 
