@@ -362,7 +362,8 @@ class _Painter:
                 ready[sl].record(copy_stream)
             staged[si] = (pd_, wd_)
 
-        nbs = min(nseg, max(1, int(os.environ.get('ABK_BUCKET_STREAMS', '2')))) if not host else 1
+        serial = os.environ.get('ABK_NO_OVERLAP') == '1'      # measurement knob: every kernel alone on one stream
+        nbs = min(nseg, max(1, int(os.environ.get('ABK_BUCKET_STREAMS', '2')))) if not (host or serial) else 1
         bstreams, scan_ptrs = [], []
         if nbs > 1:
             if len(getattr(eng, '_bstreams', [])) < nbs - 1:
@@ -440,7 +441,7 @@ class _Painter:
             if fft_weight is None:
                 continue
             last = o == len(offsets) - 1
-            if not last:
+            if not last and not serial:
                 ev = torch.cuda.Event()
                 ev.record(compute)
                 aux.wait_event(ev)  # aux already holds the early deposits of this grid, in order

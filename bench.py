@@ -411,10 +411,29 @@ def run_gpu_arm(args):
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
-    prof = eng.profile_collect()
-    eng.profile(False)
+    prof_conc = eng.profile_collect()
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
+    # Per-kernel durations for the roofline: inside the timed region the bucket kernels of different segments and the FFT
+    # of the first grid run concurrently with other kernels (two bucket streams, auxiliary FFT stream), so their event
+    # pairs include the time they share the GPU.  One extra step with every overlap switched off (ABK_NO_OVERLAP=1) gives
+    # each kernel's duration alone, still from CUDA events on its launch stream.
+    os.environ['ABK_NO_OVERLAP'] = '1'
+    try:
+        step(pos)
+        torch.cuda.synchronize()
+        eng.profile_collect()
+        ser0, ser1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ser0.record()
+        for _ in range(2):
+            step(pos)
+        ser1.record()
+        torch.cuda.synchronize()
+        prof = {k: (v[0] * args.steps / 2.0, v[1] * args.steps // 2) for k, v in eng.profile_collect().items()}
+        ms_serial = ser0.elapsed_time(ser1) / 2.0
+    finally:
+        os.environ.pop('ABK_NO_OVERLAP', None)
+    eng.profile(False)
 
     # ---- end to end: host (pinned) particles, copies inside the timed region --------------------------
     e2e = None
@@ -444,7 +463,8 @@ def run_gpu_arm(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------
     peak, peak_src = peaks()
-    nseg = max(1, prof.get('tsc_bucket_hist', (0, 2 * args.steps))[1] // (2 * args.steps))
+    # bucket launches per step = number of segments (device-resident input is bucketed once, for the first offset)
+    nseg = max(1, round(prof.get('tsc_bucket_hist', (0, args.steps))[1] / args.steps))
     n_used = used_entries(n, L, np.pi * n / L)
     default_workload = not (args.nparticles or args.nmesh or args.clustered)
     ncu = ncu_metrics() if default_workload else {}
@@ -548,10 +568,14 @@ def run_gpu_arm(args):
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'parity': parity,
         'stages': stages,
-        'stages_note': ('per-kernel CUDA-event times; the cufft of the first grid runs on an auxiliary stream '
-                        'concurrently with the tile deposit of the second grid, so their event times include the time '
-                        'they share the SMs and the stage times add up to more than the step; normalize_field is '
-                        'folded into the deposit (grid starts at -1, weights scaled by n^3/N)'),
+        'stages_in_timed_region': {k: {'ms_per_step': v[0] / args.steps, 'launches_per_step': v[1] / args.steps}
+                                   for k, v in prof_conc.items()},
+        'ms_per_step_without_overlap': ms_serial,
+        'stages_note': ('`stages` (and the roofline) use per-kernel CUDA-event durations from extra steps with all stream '
+                        'overlap switched off (ABK_NO_OVERLAP=1): inside the timed region odd bucket segments run on a '
+                        'second stream and the cufft of the first grid on an auxiliary stream, so those event pairs '
+                        '(`stages_in_timed_region`) include the time kernels share the GPU and add up to more than the '
+                        'step; normalize_field is folded into the deposit (grid starts at -1, weights scaled by n^3/N)'),
         'config2_tsc': cfg2, 'mpart_per_s': N / ms / 1e3, 'e2e_packed': packed_e2e,
         'tsc_gpart_per_s': (2 * N / (dep_ms * 1e-3) / 1e9) if dep_ms else None,
         'N_mode_total': int(np.asarray(res['N_mode']).sum()),
