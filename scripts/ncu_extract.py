@@ -2,7 +2,7 @@
 
     python scripts/ncu_extract.py gpurun_out/prof_r2_*.ncu-rep
 
-For every kernel the LAST profiled launch is kept: duration, dram__bytes_read/write.sum, smsp__inst_executed.sum, issue
+For every kernel the profiled launches are averaged (per-launch values kept alongside): duration, dram__bytes_read/write.sum, smsp__inst_executed.sum, issue
 active, achieved occupancy, registers, FMA / LSU pipe utilisation, top stall reasons.  The JSON carries the SHA-256 of the
 kernel sources (abacusutils_b200/csrc/abk_*.cu*) it was captured from; bench.py only reports these numbers while the
 sources still hash to the same value.  Run it right after the capture, before touching the kernels."""
@@ -59,7 +59,21 @@ def main(reps):
             stalls = sorted(((num(d[k]), k.split('issue_stalled_')[1].replace('_per_issue_active.ratio', '')) for k in hdr
                              if 'issue_stalled' in k and k.endswith('_per_issue_active.ratio') and num(d[k]) is not None), reverse=True)
             rec['top_stalls_per_issue'] = {k: round(v, 2) for v, k in stalls[:5]}
-            out['kernels'][name] = rec
+            out['kernels'].setdefault(name, []).append(rec)
+    # one entry per kernel: the mean over the profiled launches (the two tile deposits of a step are different template
+    # instances -- plain and widened cell domain -- with different costs; the bench reports their average launch too)
+    for name, recs in list(out['kernels'].items()):
+        mean = dict(recs[-1])
+        for k, v in recs[-1].items():
+            if isinstance(v, float):
+                mean[k] = sum(r.get(k, v) for r in recs) / len(recs)
+        mean['launches_profiled'] = len(recs)
+        mean['per_launch'] = [{'kernel': r['kernel'][:70], 'duration_ns': r.get('duration_ns'), 'warp_inst_per_launch': r.get('warp_inst_per_launch'),
+                               'dram_bytes_per_launch': r.get('dram_bytes_per_launch'), 'issue_active_pct': r.get('issue_active_pct'),
+                               'fma_pipe_pct': r.get('fma_pipe_pct')} for r in recs]
+        mean.pop('top_stalls_per_issue', None)
+        mean['top_stalls_per_issue'] = recs[-1]['top_stalls_per_issue']
+        out['kernels'][name] = mean
     (ROOT / 'profiles' / 'r2_ncu_metrics.json').write_text(json.dumps(out, indent=1))
     for k, v in out['kernels'].items():
         print(k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items() if a not in ('kernel',)})
