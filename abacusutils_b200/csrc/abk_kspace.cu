@@ -150,7 +150,7 @@ __device__ __forceinline__ void lane_flush(const BinArgs &A, const LaneAcc<NPN> 
 }
 
 template <int NPN>
-__global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__restrict__ task_counter, int nrep)
+__global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__restrict__ task_counter, int nrep, int use_tab)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_ke = reinterpret_cast<float *>(smem_raw);
@@ -158,9 +158,24 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
     float *s_coef = s_me + (A.Nmu + 1);
     int *s_pidx = reinterpret_cast<int *>(s_coef + A.Npn * ABK_POLE_NCOEF);
     const int lane = threadIdx.x & 31;
+    const abk_kmesh M = A.M;
+    const int nj = M.j1 - M.j0, ni = M.i1 - M.i0;
+    // per-row tables of the fused finish step (use_tab): phasor e^{i pi j' / n} of the interlacing phase and window W[j] for
+    // the local j range -- the phase of a mode is the product of a per-lane phasor (i', k) and this one: no sincos per mode
+    const int hdr = (A.Nk + 1) + (A.Nmu + 1) + A.Npn * ABK_POLE_NCOEF + A.Npn;
+    float2 *s_phj = reinterpret_cast<float2 *>(smem_raw + (size_t)((hdr + 3) & ~3) * 4);
+    float *s_Wj = reinterpret_cast<float *>(s_phj + (use_tab ? nj : 0));
 
     for (int t = threadIdx.x; t <= A.Nk; t += blockDim.x) s_ke[t] = A.kedges2[t];
     for (int t = threadIdx.x; t <= A.Nmu; t += blockDim.x) s_me[t] = A.muedges2[t];
+    if (use_tab) {
+        for (int t = threadIdx.x; t < nj; t += blockDim.x) {
+            float sn, cs;
+            sincospif((float)fold(M.j0 + t, M.n) * A.F1.inv_n, &sn, &cs);
+            s_phj[t] = make_float2(cs, sn);
+            s_Wj[t] = A.F1.W ? A.F1.W[M.j0 + t] : 1.0f;
+        }
+    }
     if (threadIdx.x == 0) {
         int q = 0;
         for (int p = 0; p < A.Np; p++)
@@ -172,9 +187,7 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
     }
     __syncthreads();
 
-    const abk_kmesh M = A.M;
     const int Nk = A.Nk, Nmu = A.Nmu;
-    const int nj = M.j1 - M.j0, ni = M.i1 - M.i0;
     const int nchunks = (M.nzc + 31) / 32;
     const unsigned ntasks = (unsigned)ni * nchunks;
     const float e_lo = s_ke[0], e_hi = s_ke[Nk];
@@ -198,6 +211,11 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
         const float Wk = (A.finish && A.F1.W && k_ok) ? A.F1.W[k] : 1.0f;
         const float mult = (k == 0) ? 1.0f : 2.0f;
         const unsigned cmult = (k == 0) ? 1u : 2u;
+        float2 e_ik = make_float2(1.0f, 0.0f);  // e^{i pi (i' + k) / n}
+        if (use_tab && A.F1.fs) sincospif((float)(ii + k) * A.F1.inv_n, &e_ik.y, &e_ik.x);
+        // scale and window are applied to the POWER of the mode (one division), not to the field components
+        const float pscale = A.f2 ? A.F1.scale * A.F2.scale : A.F1.scale * A.F1.scale;
+        const int wpow = (A.F1.W ? 1 : 0) + ((A.f2 ? A.F2.W : A.F1.W) ? 1 : 0);
 
         LaneAcc<NPN> acc;
         acc.key = -1; acc.bk = 0; acc.cnt = 0; acc.p = 0.0f; acc.k = 0.0f;
@@ -242,7 +260,25 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
                     val = va[u].x;
                 } else {
                     float2 a = va[u], b = vb[u];
-                    if (A.finish) {
+                    if (A.finish && use_tab) {
+                        const float2 ej = s_phj[jl];
+                        const float cs = e_ik.x * ej.x - e_ik.y * ej.y, sn = e_ik.x * ej.y + e_ik.y * ej.x;
+                        if (A.F1.fs) {
+                            a.x += vas[u].x * cs - vas[u].y * sn;
+                            a.y += vas[u].x * sn + vas[u].y * cs;
+                        }
+                        if (A.f2 && A.F2.fs) {
+                            b.x += vbs[u].x * cs - vbs[u].y * sn;
+                            b.y += vbs[u].x * sn + vbs[u].y * cs;
+                        }
+                        float pw = (A.f2 ? (a.x * b.x + a.y * b.y) : (a.x * a.x + a.y * a.y)) * pscale;
+                        if (wpow) {
+                            const float ww = (Wi * s_Wj[jl]) * Wk;
+                            pw = __fdiv_rn(pw, wpow == 2 ? ww * ww : ww);
+                        }
+                        a = make_float2(pw, 0.0f);
+                        b = make_float2(1.0f, 0.0f);
+                    } else if (A.finish) {
                         float sn = 0.0f, cs = 1.0f;
                         if (A.F1.fs) {
                             sincospif((float)(ii + jj + k) * A.F1.inv_n, &sn, &cs);
@@ -270,7 +306,7 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
                             }
                         }
                     }
-                    val = A.f2 ? (a.x * b.x + a.y * b.y) : (a.x * a.x + a.y * a.y);
+                    val = (A.finish && use_tab) ? a.x : (A.f2 ? (a.x * b.x + a.y * b.y) : (a.x * a.x + a.y * a.y));
                 }
                 const float km2 = kmag2[u];
                 const float mu2 = km2 > 0.0f ? __fdiv_rn(k2f, km2) : 0.0f;
@@ -805,6 +841,8 @@ extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
     ABK_CHECK_CUDA(cudaMemsetAsync(task_counter, 0, sizeof(unsigned), ctx->stream));
     const int blocks = ctx->num_sms * 4;
     void (*kern)(BinArgs, unsigned *, int) = nullptr;
+    void (*kern2)(BinArgs, unsigned *, int, int) = nullptr;
+    int use_tab = 0;
     // mirror-symmetric kernel: needs the full mesh on this GPU, the finish step fused (so the scale and
     // window can be applied to the group sum) or no finish at all, and a symmetric window table
     const int n = A.M.n, amax = n - n / 2;
@@ -823,13 +861,24 @@ extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
         else kern = power_bin_sym_kernel<ABK_MAX_POLES>;
     } else {
         smem = hdr_bytes;
-        if (A.Npn == 0) kern = power_bin2_kernel<0>;
-        else if (A.Npn <= 2) kern = power_bin2_kernel<2>;
-        else if (A.Npn <= 4) kern = power_bin2_kernel<4>;
-        else kern = power_bin2_kernel<ABK_MAX_POLES>;
+        // fused finish step: per-row phasor and window tables in shared memory if they fit (else sincos per mode)
+        const size_t tab = (size_t)(A.M.j1 - A.M.j0) * 12 + 16;
+        if (A.finish && hdr_bytes + tab + 1024 <= (size_t)ctx->smem_optin) {
+            use_tab = 1;
+            smem = hdr_bytes + tab;
+        }
+        if (A.Npn == 0) kern2 = power_bin2_kernel<0>;
+        else if (A.Npn <= 2) kern2 = power_bin2_kernel<2>;
+        else if (A.Npn <= 4) kern2 = power_bin2_kernel<4>;
+        else kern2 = power_bin2_kernel<ABK_MAX_POLES>;
     }
-    ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_LAUNCH(ctx, ABK_K_POWER_BIN, kern<<<blocks, 256, smem, ctx->stream>>>(A, task_counter, nrep));
+    if (kern2) {
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, kern2<<<blocks, 256, smem, ctx->stream>>>(A, task_counter, nrep, use_tab));
+    } else {
+        ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ABK_LAUNCH(ctx, ABK_K_POWER_BIN, kern<<<blocks, 256, smem, ctx->stream>>>(A, task_counter, nrep));
+    }
     if (nrep > 1) {
         const int64_t m = Nb > Npl ? Nb : Npl;
         ABK_LAUNCH(ctx, ABK_K_MISC,
