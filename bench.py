@@ -52,7 +52,7 @@ def ncu_metrics():
     try:
         d = json.loads(f.read_text())
         h = hashlib.sha256()
-        for name in ('abk_common.cuh', 'abk_kspace.cu', 'abk_tsc.cu'):      # the sources of the profiled kernels
+        for name in ('abk_common.cuh', 'abk_tsc.cu'):      # the sources of the profiled kernels (deposit, bucketing)
             h.update((ROOT / 'abacusutils_b200' / 'csrc' / name).read_bytes())
         return d['kernels'] if d.get('csrc_sha256') == h.hexdigest() else {}
     except Exception:

@@ -16,15 +16,14 @@ ap.add_argument('--n', type=int, default=512)
 ap.add_argument('--N', type=int, default=100_000_000)
 ap.add_argument('--cap', type=int, default=0)
 ap.add_argument('--reps', type=int, default=3)
-ap.add_argument('--variant', type=int, default=0, help='1..4: (PRE,PRIV) = (0,0),(1,0),(0,1),(1,1)')
 args = ap.parse_args()
 
 eng = Engine.get()
 L = 1000.0
 g = torch.Generator(device='cuda'); g.manual_seed(1)
 pos = torch.rand((args.N, 3), device='cuda', generator=g) * L
-if args.cap or args.variant:
-    check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, args.cap | (args.variant << 16)))
+if args.cap:
+    check(eng.lib.abk_ctx_set_tile_capacity(eng.ctx, args.cap))
 P = _Painter(eng, args.n, L)
 d = 0.5 * L / args.n
 for offs in ([0.0], [d], [0.0, d]):

@@ -37,7 +37,7 @@ def num(v):
 
 def main(reps):
     h = hashlib.sha256()
-    for name in ('abk_common.cuh', 'abk_kspace.cu', 'abk_tsc.cu'):      # the sources of the profiled kernels
+    for name in ('abk_common.cuh', 'abk_tsc.cu'):      # the sources of the profiled kernels (deposit, bucketing)
         h.update((ROOT / 'abacusutils_b200' / 'csrc' / name).read_bytes())
     out = {'csrc_sha256': h.hexdigest(), 'captures': [Path(r).name for r in reps], 'kernels': {}}
     for rep in reps:
