@@ -253,11 +253,18 @@ class _Painter:
                 fft_weight = packed.n_particles
                 if fft_weight == 0:
                     raise ValueError('cannot normalise an empty particle set')
+        # the grids are initialised on the auxiliary stream: 4.3 GB each at nmesh 1024, 0.7 ms that would otherwise sit
+        # in front of the (latency-bound) bucketing; every deposit waits for `self._grids_ready`
+        grids = [eng.empty((n, n, ldz), torch.float32) for _ in offsets]
+        aux = eng.aux_stream()
+        aux.wait_stream(compute)      # the allocator handed the blocks out in the order of the compute stream
+        with torch.cuda.stream(aux):
+            for g in grids:
+                g.fill_(-1.0 if fused_norm else 0.0)
+            self._grids_ready = torch.cuda.Event()
+            self._grids_ready.record(aux)
         if fused_norm:
-            grids = [eng.empty((n, n, ldz), torch.float32).fill_(-1.0) for _ in offsets]
             eng.set_weight_scale(float(np.float32(float(n) ** 3 / float(fft_weight))))
-        else:
-            grids = [eng.zeros((n, n, ldz), torch.float32) for _ in offsets]
         try:
             return self._paint(psrc, wsrc, kind, N, offsets, wrap, tag, fft_weight, fused_norm, grids, compute, packed)
         finally:
@@ -307,6 +314,7 @@ class _Painter:
             recs = (C.c_void_p * m)(*[records[ob].data_ptr() + chunks[s][0] * 16 for s in range(lo, hi)])
             sts = (C.c_void_p * m)(*[starts[ob].data_ptr() + s * starts_stride * 4 for s in range(lo, hi)])
             cnts = (C.c_int64 * m)(*[counts[s] for s in range(lo, hi)])
+            stream.wait_event(self._grids_ready)
             with torch.cuda.stream(stream):
                 eng.bind_stream()
                 check(lib.abk_tsc_deposit_tiles(eng.ctx, m, recs, sts, cnts, ptr(grids[o]), n, n, n, ldz, self.L,

@@ -225,6 +225,30 @@ __global__ void __launch_bounds__(256) onepass_kernel(const float *__restrict__ 
     }
 }
 
+// occupancy variants of the one-pass scatter: PER particles per thread, MINB resident CTAs of 256 threads asked for
+template <int PER, int MINB>
+__global__ void __launch_bounds__(256, MINB) onepass_occ_kernel(const float *__restrict__ pos, int64_t N, Geo g, uint32_t *__restrict__ cur, float4 *__restrict__ out)
+{
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * PER < N; q += (int64_t)gridDim.x * blockDim.x) {
+        float c[3 * PER];
+        if (PER == 4) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(pos + 12 * q);
+            const float4 a = __ldcs(p4), b = __ldcs(p4 + 1), d = __ldcs(p4 + 2);
+            const float t[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 3 * PER; k++) c[k] = t[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3 * PER; k++) c[k] = __ldcs(pos + 3 * PER * q + k);
+        }
+        uint32_t slot[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) slot[k] = atomicAdd(&cur[tile_of(g, c[3 * k], c[3 * k + 1], c[3 * k + 2])], 1u);
+#pragma unroll
+        for (int k = 0; k < PER; k++) out[slot[k]] = make_float4(c[3 * k], c[3 * k + 1], c[3 * k + 2], 1.0f);
+    }
+}
+
 __global__ void verify_kernel(const float4 *__restrict__ out, const uint32_t *__restrict__ starts, Geo g, unsigned long long *__restrict__ res)
 {
     unsigned long long bad = 0, sum = 0;
@@ -330,6 +354,30 @@ int main(int argc, char **argv)
         unsigned long long h[3];
         CK(cudaMemcpy(h, res, 24, cudaMemcpyDeviceToHost));
         printf("%-34s %6.2f ms/1e9  bad %llu checksum %s\n", "one pass, 16-B stores", t1 * sc, h[0], h[1] == h[2] ? "ok" : "MISMATCH");
+    }
+    {
+        auto run1 = [&](const char *name, auto kern, int per_sm) -> int {
+            float t1 = 0;
+            for (int rep = 0; rep < 2; rep++) {
+                CK(cudaMemcpy(cur_fine, starts, (g.ntiles + 1) * 4, cudaMemcpyDeviceToDevice));
+                cudaEventRecord(a);
+                kern<<<num_sms * per_sm, 256>>>(pos, N, g, cur_fine, out);
+                cudaEventRecord(b);
+                CK(cudaDeviceSynchronize());
+                cudaEventElapsedTime(&t1, a, b);
+            }
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 256, 0);
+            printf("%-34s %6.2f ms/1e9  (%d CTAs of 256 resident per SM)\n", name, t1 * sc, nb);
+            return 0;
+        };
+        if (run1("one pass, 4/thread, minb 4", onepass_occ_kernel<4, 4>, 16)) return 1;
+        if (run1("one pass, 4/thread, minb 6", onepass_occ_kernel<4, 6>, 24)) return 1;
+        if (run1("one pass, 4/thread, minb 8", onepass_occ_kernel<4, 8>, 32)) return 1;
+        if (run1("one pass, 2/thread, minb 8", onepass_occ_kernel<2, 8>, 32)) return 1;
+        if (run1("one pass, 1/thread, minb 8", onepass_occ_kernel<1, 8>, 32)) return 1;
+        if (run1("one pass, 2/thread, minb 4", onepass_occ_kernel<2, 4>, 16)) return 1;
+        if (argc > 1 && argv[1][0] == 'o') return 0;
     }
     const int D = (int)ceil(sqrt((double)g.ntiles));
     const int ncoarse = (g.ntiles + D - 1) / D;
