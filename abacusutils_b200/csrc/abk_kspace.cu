@@ -125,7 +125,8 @@ struct BinArgs {
 // the loop.  Loads stay fully coalesced: lanes hold consecutive k of the same (i,j) row.
 constexpr int BIN_NREP = 16;
 constexpr int BIN_UNROLL = 4;
-constexpr int BIN_PF_DIST = 1;  // prefetch distance (steps) of the symmetric kernel
+constexpr int BIN_PF_DIST = 2;  // prefetch distance (steps) of the symmetric kernel
+constexpr int BIN_AJ_SEG = 64;  // symmetric kernel: a task walks this many |j'| (a full column would be up to n/2 + 1 steps)
 
 template <int NPN>
 struct LaneAcc {
@@ -398,7 +399,11 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
 
     const int Nk = A.Nk, Nmu = A.Nmu;
     const int nchunks = (M.nzc + 31) / 32;
-    const unsigned ntasks = (unsigned)(amax + 1) * nchunks;
+    // A task is (|i'|, 32 k, a segment of BIN_AJ_SEG |j'|): a whole column would be up to n/2 + 1 dependent steps, and with
+    // fewer columns than resident warps the kernel lasted as long as its longest column (513 steps of one memory latency
+    // each at nmesh 1024).  Segments give every warp the same short walk; those beyond the last edge exit at once.
+    const int nseg = amax / BIN_AJ_SEG + 1;
+    const unsigned ntasks = (unsigned)(amax + 1) * nchunks * nseg;
     const float e_lo = s_ke[0], e_hi = s_ke[Nk];
     const int rep = (nrep > 1) ? (int)(blockIdx.x % nrep) : 0;
     const size_t rep_off_bins = (size_t)rep * Nk * Nmu, rep_off_poles = (size_t)rep * A.Np * Nk;
@@ -413,11 +418,13 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= ntasks) break;
         // heavy columns (small |i'|) first: tasks are handed out in order of increasing |i'|
-        const int ai = task / nchunks, k0 = (task % nchunks) * 32;
+        const int seg = task % nseg, col = task / nseg;
+        const int ai = col / nchunks, k0 = (col % nchunks) * 32;
+        const int aj_lo = seg * BIN_AJ_SEG, aj_hi = min(amax, aj_lo + BIN_AJ_SEG - 1);
         const int k = k0 + lane;
         const bool k_ok = k < M.nzc;
         const int ik2 = ai * ai + k * k;
-        if ((float)(ai * ai + k0 * k0) >= e_hi) continue;
+        if ((float)(ai * ai + k0 * k0 + aj_lo * aj_lo) >= e_hi) continue;
         const float k2f = (float)(k * k);
         const float mult = (k == 0) ? 1.0f : 2.0f;
         const unsigned cmult = (k == 0) ? 1u : 2u;
@@ -441,7 +448,37 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
         for (int q = 0; q < (NPN > 0 ? NPN : 1); q++) acc.pl[q] = 0.0f;
         int bk = 0, bmu = 0;
 
-        for (int aj = 0; aj <= amax; aj++) {
+        // software prefetch of a later step's rows into the L1: the loop is otherwise latency-bound (one dependent batch of
+        // loads per step)
+        auto prefetch_step = [&](int an) {
+            if (!k_ok || an > aj_hi) return;
+            const int njn = (an < n / 2 ? 1 : 0) + ((an >= 1 && an <= amax) ? 1 : 0);
+            const int jn1 = (an < n / 2) ? an : n - an, jn2 = n - an;
+#pragma unroll
+            for (int mi = 0; mi < 2; mi++) {
+                if (mi >= ni_mem) break;
+                const int i = mi == 0 ? i_first : i_second;
+#pragma unroll
+                for (int mj = 0; mj < 2; mj++) {
+                    if (mj >= njn) break;
+                    const int64_t idx = (int64_t)i * M.stride_i + (int64_t)(mj == 0 ? jn1 : jn2) * M.stride_j + k;
+                    if (A.real_in) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.real_in + idx));
+                    } else {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f1 + idx));
+                        if (inter1) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F1.fs + idx));
+                        if (cross) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f2 + idx));
+                            if (inter2) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F2.fs + idx));
+                        }
+                    }
+                }
+            }
+        };
+#pragma unroll
+        for (int d = 0; d < BIN_PF_DIST; d++) prefetch_step(aj_lo + d);
+
+        for (int aj = aj_lo; aj <= aj_hi; aj++) {
             const float km2 = (float)(ik2 + aj * aj);
             if ((float)(ai * ai + k0 * k0 + aj * aj) >= e_hi) break;  // |k| only grows with aj: warp-uniform exit
             const bool use = k_ok && km2 >= e_lo && km2 < e_hi;
@@ -452,33 +489,7 @@ __global__ void __launch_bounds__(256) power_bin_sym_kernel(BinArgs A, unsigned 
             const float2 ej = s_ph[aj];
             float sum = 0.0f;
             int members = 0;
-            // software prefetch of the next step's rows into L2->L1: the loop is otherwise latency-bound
-            // (one dependent batch of loads per step)
-            if (k_ok && aj + BIN_PF_DIST <= amax) {
-                const int an = aj + BIN_PF_DIST;
-                const int njn = (an < n / 2 ? 1 : 0) + ((an >= 1 && an <= amax) ? 1 : 0);
-                const int jn1 = (an < n / 2) ? an : n - an, jn2 = n - an;
-#pragma unroll
-                for (int mi = 0; mi < 2; mi++) {
-                    if (mi >= ni_mem) break;
-                    const int i = mi == 0 ? i_first : i_second;
-#pragma unroll
-                    for (int mj = 0; mj < 2; mj++) {
-                        if (mj >= njn) break;
-                        const int64_t idx = (int64_t)i * M.stride_i + (int64_t)(mj == 0 ? jn1 : jn2) * M.stride_j + k;
-                        if (A.real_in) {
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.real_in + idx));
-                        } else {
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f1 + idx));
-                            if (inter1) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F1.fs + idx));
-                            if (cross) {
-                                asm volatile("prefetch.global.L1 [%0];" ::"l"(A.f2 + idx));
-                                if (inter2) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.F2.fs + idx));
-                            }
-                        }
-                    }
-                }
-            }
+            prefetch_step(aj + BIN_PF_DIST);
             if (use) {
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) {
