@@ -37,6 +37,7 @@ struct TscParams {
     double gx_d, gy_d, gz_d;       // CIC works in double: p = (x / box) * g
     float wscale;                  // multiplies every weight as the bucket records are written (1 unless the caller
                                    // folds the field normalisation into the deposit, abk_ctx_set_weight_scale)
+    int64_t plane_bytes, wrap_bytes;  // tile deposit: bytes of one x-plane of the grid (ny * ldz * 4) and of nx of them
 };
 
 // tsc.py:219-226: one-shot wrap; compare against the double box, store float32
@@ -222,7 +223,10 @@ __device__ __forceinline__ void mas_w(float d, float &wm, float &w0, float &wp)
 
 // 27 global reductions for a particle whose centre cell lies outside the cell domain of the tile it
 // was bucketed in (only possible when the deposit offset differs from the bucketing offset).
-__device__ __noinline__ void deposit_direct(float *__restrict__ grid, const TscParams &P, int64_t ldz, int slab,
+// (the mesh shape comes by value: a reference to the kernel's parameter struct would force a copy of it into local memory,
+// and every later use of a field -- also in the hot loops -- would become a local load)
+struct MeshShape { int nx, ny, nz, x_lo, cic; };
+__device__ __noinline__ void deposit_direct(float *__restrict__ grid, const MeshShape P, int64_t ldz, int slab,
                                             int cx, int cy, int cz, float dx, float dy, float dz, float W)
 {
     const int64_t sx = (int64_t)P.ny * ldz;
@@ -424,7 +428,9 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
     __shared__ unsigned ovf_cnt;
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
-    const uint32_t tile = blockIdx.x;
+    // 3-D grid (tz, ty, tx): the tile's coordinates come from the block index, not from three integer divisions per thread
+    const uint32_t tz = blockIdx.x, ty = blockIdx.y, tx = blockIdx.z;
+    const uint32_t tile = (tx * gridDim.y + ty) * gridDim.x + tz;
     // the tile's record range in every segment: loaded by one lane per segment (the loads overlap), then prefix-summed
     if (tid < 32) {
         uint32_t b = 0, cnt = 0;
@@ -448,19 +454,18 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
     const uint32_t total = seg_off[segs.nseg];
     if (total == 0) return;
 
-    const uint32_t tz = tile % P.ntz, ty = (tile / P.ntz) % P.nty, tx = tile / (P.ntz * P.nty);
     const int x0 = tx * ABK_TX, y0 = ty * ABK_TY, z0 = tz * ABK_TZ;  // x0 relative to x_lo
     const int64_t sx = (int64_t)P.ny * ldz;
 
     // plane-independent pieces of this warp's output addresses: rows y0+wy-1 .. y0+wy+1, column z0-1+lane.  Rows or
     // columns beyond the mesh (ragged last tile, meshes smaller than a tile) only ever carry zeros, which are not written.
-    const int sx32 = (int)sx;  // ny * ldz < 2^31 for every mesh the reference's int16 cell indices allow
+
     const int ldz32 = (int)ldz;
     const int gy0 = abk_wrap_cell(y0 + wy - 1, P.ny), gy1 = wrap_near(gy0 + 1, P.ny), gy2 = wrap_near(gy1 + 1, P.ny);
     const int rowo0 = gy0 * ldz32 + abk_wrap_cell(z0 - 1 + lane, P.nz);
     const int d01 = (gy1 - gy0) * ldz32, d12 = (gy2 - gy1) * ldz32;  // warp-uniform row steps (ldz, or back to row 0)
     const int gx_first = slab ? x0 : wrap_near(x0 - 1, P.nx);        // global x of plane 0 (local x = -1)
-    const int lane_up = (lane + 31) & 31, lane_dn = (lane + 1) & 31;
+    const int d01b = d01 * 4, d12b = d12 * 4;                         // the same row steps in bytes
     float *stash = stash_all + wy * D::STASH;
     uint32_t parity = 0;
 
@@ -515,7 +520,7 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
                     ovf_xyz[slot] = (uint16_t)((lx << 10) | (ly << 6) | lz);
                 } else {
                     // far outside the tile (arbitrary offset difference): global cell = origin + local
-                    deposit_direct(grid, P, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
+                    deposit_direct(grid, MeshShape{P.nx, P.ny, P.nz, P.x_lo, P.cic}, ldz, slab, abk_wrap_cell(P.x_lo + x0 + lx, P.nx), abk_wrap_cell(y0 + ly, P.ny),
                                    abk_wrap_cell(z0 + lz, P.nz), dx, dy, dz, r.w);
                 }
             }
@@ -548,6 +553,9 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
         Plane S0, S1, S2;
         plane_zero(S0); plane_zero(S1); plane_zero(S2);
         int gx = gx_first;
+        // row y-1 of the plane being emitted; advanced by one plane per step (a running pointer: recomputing the 64-bit
+        // address for each of the three reductions of a step cost more instructions than the reductions themselves)
+        char *rowp = reinterpret_cast<char *>(grid) + ((int64_t)gx_first * sx + rowo0) * 4;
         const uint32_t *hp = head + wy * 32 + lane;
         // sum the lists of cell column cx into (A, B, C) = planes cx-1, cx, cx+1 (plane index cx, cx+1, cx+2); then
         // plane index cx is complete: combine across lanes, add to the grid, hand the registers back zeroed
@@ -561,22 +569,35 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
                     accumulate_particle<CIC>(r, A, B, C);
                 }
             }
-            float *row = grid + (int64_t)gx * sx32 + rowo0;
             const float ctr[3] = {A.q.x, A.s, A.q.y};
+            float v[3];
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                // rotating shuffles: the halo lanes hold no particles, so what wraps around is zero -- except, EXT, the
-                // upper term of lane 31 (local z = 31), which lands on lane 0 and is stashed
-                const float up = __shfl_sync(0xffffffffu, A.p[b].y, lane_up);  // lane z-1's contribution to z
-                const float dn = __shfl_sync(0xffffffffu, A.p[b].x, lane_dn);  // lane z+1's contribution to z
-                const float v = ctr[b] + ((EXT && lane == 0) ? 0.0f : up) + dn;
-                if (__any_sync(0xffffffffu, v != 0.0f)) atomicAdd(row, v);
-                if (EXT && lane == 0) stash[cx * 3 + b] = up;
-                row += (b == 0 ? d01 : d12);
+                // neighbour shuffles by one lane: lane 0 (a halo lane, no particles) receives its own zero from below; lane 31
+                // receives its own value from above -- zero as well, except EXT, where it owns the cell local z = 30: its
+                // upper term belongs to local z = 31 and goes to the stash
+                const float up = __shfl_up_sync(0xffffffffu, A.p[b].y, 1);    // lane z-1's contribution to z
+                float dn = __shfl_down_sync(0xffffffffu, A.p[b].x, 1);        // lane z+1's contribution to z
+                if (EXT && lane == 31) {
+                    stash[cx * 3 + b] = A.p[b].y;
+                    dn = 0.0f;
+                }
+                v[b] = ctr[b] + up + dn;
+            }
+            // one vote per step: rows of zeros (empty tiles of a sparse catalogue) are skipped three at a time; a zero row
+            // next to a non-zero one is added as it is (x + 0 = x; the addresses are wrapped into the mesh)
+            if (__any_sync(0xffffffffu, (v[0] != 0.0f) | (v[1] != 0.0f) | (v[2] != 0.0f))) {
+                atomicAdd(reinterpret_cast<float *>(rowp), v[0]);
+                atomicAdd(reinterpret_cast<float *>(rowp + d01b), v[1]);
+                atomicAdd(reinterpret_cast<float *>(rowp + d01b + d12b), v[2]);
             }
             plane_zero(A);
+            rowp += P.plane_bytes;
             gx++;
-            if (!slab && gx >= P.nx) gx -= P.nx;
+            if (!slab && gx >= P.nx) {
+                gx -= P.nx;
+                rowp -= P.wrap_bytes;
+            }
         };
         {
             int cx = 0;
@@ -766,6 +787,7 @@ int make_params(const abk_ctx *ctx, TscParams &P, int nx, int ny, int nz, double
     P.cic = ctx->scheme == 1;
     P.gx_d = nx; P.gy_d = ny; P.gz_d = nz;
     P.wscale = ctx->wscale;
+    P.plane_bytes = P.wrap_bytes = 0;
     return ABK_OK;
 }
 
@@ -977,7 +999,10 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     TscParams P;
     int rc = make_params(ctx, P, nx, ny, nz, box, offset, 0, x_lo, nxe);
     if (rc) return rc;
+    P.plane_bytes = (int64_t)ny * ldz * 4;
+    P.wrap_bytes = (int64_t)nx * P.plane_bytes;
     const abk_tile_geom g = abk_make_geom(nxe, ny, nz);
+    ABK_REQUIRE(g.ntx <= 65535 && g.nty <= 65535, "mesh too large for the tile grid (%d x %d tile columns)", g.ntx, g.nty);
     SegList segs;
     segs.nseg = nseg;
     int64_t n_total = 0;
@@ -1009,7 +1034,7 @@ extern "C" int abk_tsc_deposit_tiles(abk_ctx *ctx, int nseg, const void *const *
     ABK_REQUIRE(smem + fa.sharedSizeBytes <= (size_t)ctx->smem_optin, "tile capacity %d needs %zu B shared memory (> %d)", cap,
                 smem + fa.sharedSizeBytes, ctx->smem_optin);
     ABK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<(unsigned)g.ntiles, ext ? WalkDom<1>::NT : WalkDom<0>::NT, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
+    ABK_LAUNCH(ctx, ABK_K_TILE_DEPOSIT, kern<<<dim3((unsigned)g.ntz, (unsigned)g.nty, (unsigned)g.ntx), ext ? WalkDom<1>::NT : WalkDom<0>::NT, smem, ctx->stream>>>(segs, grid, P, ldz, cap, slab));
     return ABK_OK;
 }
 
