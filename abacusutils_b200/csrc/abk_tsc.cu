@@ -552,7 +552,7 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
         // ---- phase 2, lane <-> cell (row wy, lane = local z + 1): rolling 3-plane register window along x --------
         Plane S0, S1, S2;
         plane_zero(S0); plane_zero(S1); plane_zero(S2);
-        int gx = gx_first;
+        int to_wrap = slab ? 0x7fffffff : P.nx - gx_first;      // planes left before the periodic wrap (slab grids: none)
         // row y-1 of the plane being emitted; advanced by one plane per step (a running pointer: recomputing the 64-bit
         // address for each of the three reductions of a step cost more instructions than the reductions themselves)
         char *rowp = reinterpret_cast<char *>(grid) + ((int64_t)gx_first * sx + rowo0) * 4;
@@ -593,9 +593,8 @@ tsc_tile_walk_kernel(SegList segs, float *__restrict__ grid, TscParams P, int64_
             }
             plane_zero(A);
             rowp += P.plane_bytes;
-            gx++;
-            if (!slab && gx >= P.nx) {
-                gx -= P.nx;
+            if (--to_wrap == 0) {      // periodic grid: the plane after nx - 1 is plane 0
+                to_wrap = P.nx;
                 rowp -= P.wrap_bytes;
             }
         };
