@@ -249,6 +249,29 @@ __global__ void __launch_bounds__(256, MINB) onepass_occ_kernel(const float *__r
     }
 }
 
+// one-pass scatter whose record stores carry an L2 evict_last policy (keep the open write frontier resident) while the
+// position loads stay evict_first
+template <int PRIO>
+__global__ void __launch_bounds__(256) onepass_policy_kernel(const float *__restrict__ pos, int64_t N, Geo g, uint32_t *__restrict__ cur, float4 *__restrict__ out)
+{
+    uint64_t pol;
+    if (PRIO == 0) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.5;" : "=l"(pol));
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < N; q += (int64_t)gridDim.x * blockDim.x) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(pos + 12 * q);
+        const float4 a = __ldcs(p4), b = __ldcs(p4 + 1), d = __ldcs(p4 + 2);
+        const float c[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};
+        uint32_t slot[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) slot[k] = atomicAdd(&cur[tile_of(g, c[3 * k], c[3 * k + 1], c[3 * k + 2])], 1u);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(out + slot[k]), "f"(c[3 * k]), "f"(c[3 * k + 1]), "f"(c[3 * k + 2]),
+                         "f"(1.0f), "l"(pol)
+                         : "memory");
+    }
+}
+
 __global__ void verify_kernel(const float4 *__restrict__ out, const uint32_t *__restrict__ starts, Geo g, unsigned long long *__restrict__ res)
 {
     unsigned long long bad = 0, sum = 0;
@@ -377,6 +400,8 @@ int main(int argc, char **argv)
         if (run1("one pass, 2/thread, minb 8", onepass_occ_kernel<2, 8>, 32)) return 1;
         if (run1("one pass, 1/thread, minb 8", onepass_occ_kernel<1, 8>, 32)) return 1;
         if (run1("one pass, 2/thread, minb 4", onepass_occ_kernel<2, 4>, 16)) return 1;
+        if (run1("one pass, stores L2 evict_last", onepass_policy_kernel<0>, 16)) return 1;
+        if (run1("one pass, stores evict_last 50 %", onepass_policy_kernel<1>, 16)) return 1;
         if (argc > 1 && argv[1][0] == 'o') return 0;
     }
     const int D = (int)ceil(sqrt((double)g.ntiles));
