@@ -4,7 +4,7 @@ set -u
 G=$1
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $G --steps 3 --warmup 2 > gpurun_out/r2_bench_n$G.json 2> gpurun_out/r2_bench_n$G.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $G --steps 5 --warmup 3 > gpurun_out/r2_bench_n$G.json 2> gpurun_out/r2_bench_n$G.err
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/r2_bench_n$G.json').read().strip().splitlines()[-1])
