@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc, *NVCC_FLAGS, '-ccbin', '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++',
            '-I', str(ROOT / 'include'), '-I', str(CSRC),
            *[str(CSRC / s) for s in SOURCES], '-o', str(LIB),
-           '-L', os.path.join(CUDA_HOME, 'lib64'), '-lcufft', '-Xlinker', f'-rpath={CUDA_HOME}/lib64']
+           '-L', os.path.join(CUDA_HOME, 'lib64'), '-ldl']      # cuFFT is opened at run time (csrc/abk_fft.cu), not linked
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

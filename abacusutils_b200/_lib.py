@@ -87,6 +87,7 @@ SIGNATURES = {
     'abk_rfft3_exec': (_i32, [_vp, _vp, _vp, _vp, _sz]),
     'abk_irfft3_exec': (_i32, [_vp, _vp, _vp, _vp, _sz]),
     'abk_fft_plan_destroy': (_i32, [_vp]),
+    'abk_fft_backend': (_i32, [C.c_char_p, _i32, C.POINTER(C.c_int)]),
     'abk_fft_yz_plan_create': (_i32, [_vp, _i64, _i64, _i64, C.POINTER(_vp), _psz]),
     'abk_fft_x_plan_create': (_i32, [_vp, _i64, _i64, _i64, C.POINTER(_vp), _psz]),
     'abk_fft_exec_generic': (_i32, [_vp, _vp, _vp, _vp, _sz]),

@@ -4,8 +4,96 @@
 // (cufftMakePlanMany64) so nmesh >= 2048 (> 2^31 elements) works, and a caller-provided work
 // area so all large device memory stays owned by the host framework's allocator.
 #include <cufft.h>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
 
 #include "abk_common.cuh"
+
+// ---- which cuFFT ---------------------------------------------------------------------------------
+// libabk does not link against libcufft: in a process that has imported torch, the soname libcufft.so.11 is already bound to
+// the copy bundled with torch (CUDA 12.8), and that is what a linked libabk would silently get.  The toolkit's cuFFT 11.4
+// (CUDA 12.9) transforms the 1024^3 grid in place in 5.9 ms with no work area, the bundled 11.3 in 6.6 ms with a 4.3 GB work
+// area (scripts/micro/fft_pad_micro.cu, profiles/r2_micro8.log).  So the library is opened by PATH at first use -- a path with
+// a slash is matched by file identity, not by soname, and loads next to torch's copy: $ABK_CUFFT, then $CUDA_HOME/lib64 and
+// /usr/local/cuda/lib64, then whatever "libcufft.so.11" resolves to (abk_fft_backend reports the choice).
+namespace {
+struct CufftApi {
+    void *handle = nullptr;
+    std::string path;
+    int version = 0;
+    cufftResult (*Create)(cufftHandle *) = nullptr;
+    cufftResult (*Destroy)(cufftHandle) = nullptr;
+    cufftResult (*SetAutoAllocation)(cufftHandle, int) = nullptr;
+    cufftResult (*MakePlanMany64)(cufftHandle, int, long long *, long long *, long long, long long, long long *, long long, long long,
+                                  cufftType, long long, size_t *) = nullptr;
+    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
+    cufftResult (*SetWorkArea)(cufftHandle, void *) = nullptr;
+    cufftResult (*ExecR2C)(cufftHandle, cufftReal *, cufftComplex *) = nullptr;
+    cufftResult (*ExecC2R)(cufftHandle, cufftComplex *, cufftReal *) = nullptr;
+    cufftResult (*ExecC2C)(cufftHandle, cufftComplex *, cufftComplex *, int) = nullptr;
+    cufftResult (*ExecD2Z)(cufftHandle, cufftDoubleReal *, cufftDoubleComplex *) = nullptr;
+    cufftResult (*GetVersion)(int *) = nullptr;
+};
+CufftApi g_fft;
+std::once_flag g_fft_once;
+
+bool cufft_try(const std::string &path)
+{
+    void *h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) return false;
+    CufftApi a;
+    a.handle = h;
+    a.path = path;
+#define ABK_SYM(field, name) a.field = reinterpret_cast<decltype(a.field)>(dlsym(h, name))
+    ABK_SYM(Create, "cufftCreate"); ABK_SYM(Destroy, "cufftDestroy"); ABK_SYM(SetAutoAllocation, "cufftSetAutoAllocation");
+    ABK_SYM(MakePlanMany64, "cufftMakePlanMany64"); ABK_SYM(SetStream, "cufftSetStream"); ABK_SYM(SetWorkArea, "cufftSetWorkArea");
+    ABK_SYM(ExecR2C, "cufftExecR2C"); ABK_SYM(ExecC2R, "cufftExecC2R"); ABK_SYM(ExecC2C, "cufftExecC2C");
+    ABK_SYM(ExecD2Z, "cufftExecD2Z"); ABK_SYM(GetVersion, "cufftGetVersion");
+#undef ABK_SYM
+    if (!a.Create || !a.Destroy || !a.SetAutoAllocation || !a.MakePlanMany64 || !a.SetStream || !a.SetWorkArea || !a.ExecR2C ||
+        !a.ExecC2R || !a.ExecC2C || !a.ExecD2Z || !a.GetVersion) {
+        dlclose(h);
+        return false;
+    }
+    a.GetVersion(&a.version);
+    g_fft = a;
+    return true;
+}
+
+void cufft_load()
+{
+    const char *env = getenv("ABK_CUFFT");
+    if (env && *env && cufft_try(env)) return;
+    const char *home = getenv("CUDA_HOME");
+    if (home && *home && cufft_try(std::string(home) + "/lib64/libcufft.so.11")) return;
+    if (cufft_try("/usr/local/cuda/lib64/libcufft.so.11")) return;
+    cufft_try("libcufft.so.11");
+}
+
+// nullptr (and the error string set) if no cuFFT can be loaded
+const CufftApi *cufft_api()
+{
+    std::call_once(g_fft_once, cufft_load);
+    if (!g_fft.handle) {
+        abk_set_error("cuFFT not found: tried $ABK_CUFFT, $CUDA_HOME/lib64/libcufft.so.11, /usr/local/cuda/lib64/libcufft.so.11, libcufft.so.11");
+        return nullptr;
+    }
+    return &g_fft;
+}
+}  // namespace
+
+#define ABK_FFT_API(var)                 \
+    const CufftApi *var = cufft_api();   \
+    if (!var) return ABK_ERR_CUFFT
+
+extern "C" int abk_fft_backend(char *path, int path_len, int *version)
+{
+    ABK_FFT_API(F);
+    if (path && path_len > 0) snprintf(path, (size_t)path_len, "%s", F->path.c_str());
+    if (version) *version = F->version;
+    return ABK_OK;
+}
 
 struct abk_fft_plan {
     cufftHandle fwd;
@@ -30,9 +118,10 @@ static int make_handle(cufftHandle *h, int rank, long long *n, long long *inembe
                        long long *onembed, long long ostride, long long odist, cufftType type, long long batch,
                        size_t *work)
 {
-    ABK_CHECK_CUFFT(cufftCreate(h));
-    ABK_CHECK_CUFFT(cufftSetAutoAllocation(*h, 0));
-    ABK_CHECK_CUFFT(cufftMakePlanMany64(*h, rank, n, inembed, istride, idist, onembed, ostride, odist, type, batch, work));
+    ABK_FFT_API(F);
+    ABK_CHECK_CUFFT(F->Create(h));
+    ABK_CHECK_CUFFT(F->SetAutoAllocation(*h, 0));
+    ABK_CHECK_CUFFT(F->MakePlanMany64(*h, rank, n, inembed, istride, idist, onembed, ostride, odist, type, batch, work));
     return ABK_OK;
 }
 
@@ -111,8 +200,9 @@ static int prep(abk_ctx *ctx, abk_fft_plan *plan, cufftHandle h, void *work, siz
         abk_set_error("fft exec: work area %zu < %zu", work_bytes, plan->work_bytes);
         return ABK_ERR_SCRATCH;
     }
-    ABK_CHECK_CUFFT(cufftSetStream(h, ctx->stream));
-    if (plan->work_bytes) ABK_CHECK_CUFFT(cufftSetWorkArea(h, work));
+    ABK_FFT_API(F);
+    ABK_CHECK_CUFFT(F->SetStream(h, ctx->stream));
+    if (plan->work_bytes) ABK_CHECK_CUFFT(F->SetWorkArea(h, work));
     return ABK_OK;
 }
 
@@ -123,7 +213,7 @@ extern "C" int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, voi
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;
     if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
-    ABK_CHECK_CUFFT(cufftExecR2C(plan->fwd, (cufftReal *)grid, (cufftComplex *)grid));
+    ABK_CHECK_CUFFT(g_fft.ExecR2C(plan->fwd, (cufftReal *)grid, (cufftComplex *)grid));
     if (ctx->prof_on) abk_prof_end(ctx);
     ctx->launches += 1;  // cuFFT launches several kernels; counted as one library call
     return ABK_OK;
@@ -148,9 +238,9 @@ extern "C" int abk_irfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid, vo
         abk_set_error("abk_irfft3_exec: work area %zu < %zu", work_bytes, plan->inv_work_bytes);
         return ABK_ERR_SCRATCH;
     }
-    ABK_CHECK_CUFFT(cufftSetStream(plan->inv, ctx->stream));
-    if (plan->inv_work_bytes) ABK_CHECK_CUFFT(cufftSetWorkArea(plan->inv, work));
-    ABK_CHECK_CUFFT(cufftExecC2R(plan->inv, (cufftComplex *)grid, (cufftReal *)grid));
+    ABK_CHECK_CUFFT(g_fft.SetStream(plan->inv, ctx->stream));
+    if (plan->inv_work_bytes) ABK_CHECK_CUFFT(g_fft.SetWorkArea(plan->inv, work));
+    ABK_CHECK_CUFFT(g_fft.ExecC2R(plan->inv, (cufftComplex *)grid, (cufftReal *)grid));
     ctx->launches += 1;
     return ABK_OK;
 }
@@ -162,8 +252,8 @@ extern "C" int abk_fft_exec_generic(abk_ctx *ctx, abk_fft_plan *plan, void *data
     int rc = prep(ctx, plan, plan->fwd, work, work_bytes);
     if (rc) return rc;
     if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
-    if (plan->kind == 2) ABK_CHECK_CUFFT(cufftExecC2C(plan->fwd, (cufftComplex *)data, (cufftComplex *)data, CUFFT_FORWARD));
-    else ABK_CHECK_CUFFT(cufftExecR2C(plan->fwd, (cufftReal *)data, (cufftComplex *)data));
+    if (plan->kind == 2) ABK_CHECK_CUFFT(g_fft.ExecC2C(plan->fwd, (cufftComplex *)data, (cufftComplex *)data, CUFFT_FORWARD));
+    else ABK_CHECK_CUFFT(g_fft.ExecR2C(plan->fwd, (cufftReal *)data, (cufftComplex *)data));
     if (ctx->prof_on) abk_prof_end(ctx);
     ctx->launches += 1;
     return ABK_OK;
@@ -172,8 +262,10 @@ extern "C" int abk_fft_exec_generic(abk_ctx *ctx, abk_fft_plan *plan, void *data
 extern "C" int abk_fft_plan_destroy(abk_fft_plan *plan)
 {
     if (!plan) return ABK_OK;
-    cufftDestroy(plan->fwd);
-    if (plan->has_inv) cufftDestroy(plan->inv);
+    if (g_fft.handle) {      // a plan can only exist if the library was loaded
+        g_fft.Destroy(plan->fwd);
+        if (plan->has_inv) g_fft.Destroy(plan->inv);
+    }
     delete plan;
     return ABK_OK;
 }
@@ -185,20 +277,21 @@ extern "C" int abk_rfft3_f64(abk_ctx *ctx, double *grid_inplace, int64_t nx, int
 {
     abk_device_guard entry_guard(ctx ? ctx->device : -1);
     ABK_REQUIRE(ctx && grid_inplace && nx > 0 && ny > 0 && nz > 0, "abk_rfft3_f64: bad arguments");
+    ABK_FFT_API(F);
     cufftHandle h;
     long long n[3] = {nx, ny, nz};
     const long long nzc = nz / 2 + 1;
     long long rembed[3] = {nx, ny, 2 * nzc}, cembed[3] = {nx, ny, nzc};
     size_t work = 0;
-    cufftResult r = cufftCreate(&h);
-    if (r == CUFFT_SUCCESS) r = cufftMakePlanMany64(h, 3, n, rembed, 1, nx * ny * 2 * nzc, cembed, 1, nx * ny * nzc, CUFFT_D2Z, 1, &work);
-    if (r == CUFFT_SUCCESS) r = cufftSetStream(h, ctx->stream);
+    cufftResult r = F->Create(&h);
+    if (r == CUFFT_SUCCESS) r = F->MakePlanMany64(h, 3, n, rembed, 1, nx * ny * 2 * nzc, cembed, 1, nx * ny * nzc, CUFFT_D2Z, 1, &work);
+    if (r == CUFFT_SUCCESS) r = F->SetStream(h, ctx->stream);
     if (ctx->prof_on) abk_prof_begin(ctx, ABK_K_FFT);
-    if (r == CUFFT_SUCCESS) r = cufftExecD2Z(h, grid_inplace, (cufftDoubleComplex *)grid_inplace);
+    if (r == CUFFT_SUCCESS) r = F->ExecD2Z(h, grid_inplace, (cufftDoubleComplex *)grid_inplace);
     if (ctx->prof_on) abk_prof_end(ctx);
     ctx->launches++;
     cudaStreamSynchronize(ctx->stream);  // the plan (and its work area) is destroyed below
-    cufftDestroy(h);
+    F->Destroy(h);
     if (r != CUFFT_SUCCESS) {
         abk_set_error("abk_rfft3_f64: cufft error %d", (int)r);
         return ABK_ERR_CUFFT;

@@ -187,6 +187,10 @@ int abk_rfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid_inplace, void *
 /* inverse (C2R, unnormalised) of the same layout: power_spectrum.py:645 `irfftn` (xi(r) path) */
 int abk_irfft3_exec(abk_ctx *ctx, abk_fft_plan *plan, float *grid_inplace, void *work, size_t work_bytes);
 int abk_fft_plan_destroy(abk_fft_plan *plan);
+/* Which cuFFT the plans run on: libabk opens the library by path at first use (the CUDA toolkit's copy in preference to
+ * one another package has already loaded under the same soname, see csrc/abk_fft.cu); `path` receives the name it was
+ * opened by, `version` cufftGetVersion(). */
+int abk_fft_backend(char *path, int path_len, int *version);
 
 /* Slab-decomposed pieces for a mesh sharded over GPUs by x-planes:
  *   2-D R2C over (y,z) on `nplanes` local planes (in place, ldz = 2*(nz/2+1)), and

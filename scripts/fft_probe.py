@@ -35,3 +35,4 @@ print('torch 2-D rfft2 over (y,z) + 1-D fft over x:          %.2f ms' % timeit(l
 y = torch.fft.rfft2(x)
 print('   of which the 1-D pass over x (strided):            %.2f ms' % timeit(lambda: torch.fft.fft(y, dim=0)))
 print('   of which the 2-D pass:                             %.2f ms' % timeit(lambda: torch.fft.rfft2(x)))
+print('libabk 3-D plan work area: %d bytes' % eng.rfft3_plan(n, n, n)[1])
