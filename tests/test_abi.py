@@ -41,6 +41,23 @@ def test_version_and_error_string(lib):
     assert isinstance(lib.abk_last_error(), bytes)
 
 
+def test_fft_backend_is_opened_by_path(lib):
+    """libabk does not link cuFFT (a process that imported torch would hand it torch's bundled copy): it opens the toolkit's
+    library by path; no compute call is made here."""
+    import ctypes as C
+    import subprocess
+
+    from abacusutils_b200 import _lib
+
+    needed = subprocess.run(['ldd', str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    assert 'cufft' not in needed
+    buf, ver = C.create_string_buffer(512), C.c_int()
+    rc = lib.abk_fft_backend(buf, 512, C.byref(ver))
+    if rc != 0:
+        pytest.skip('no cuFFT on this machine: ' + lib.abk_last_error().decode())
+    assert b'libcufft' in buf.value and ver.value >= 11000
+
+
 def test_struct_layouts_match_header():
     """sizeof of the ctypes mirrors == what the C compiler lays out (checked with a tiny C program)."""
     import ctypes
