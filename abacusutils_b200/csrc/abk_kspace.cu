@@ -353,6 +353,185 @@ __global__ void __launch_bounds__(256) power_bin2_kernel(BinArgs A, unsigned *__
 }
 
 // ------------------------------------------------------------------------------------------
+// (k,mu) binning of a PENCIL (all x, a range of y, all k_z: what a rank of the sharded path holds after the transpose), fused
+// finish step.  The two modes (+-i', j, k) share |k|^2, mu^2, the bin, the Legendre weights and -- for a symmetric window
+// table -- the window product, and both live on this rank: a warp owns (|i'|, 32 k), walks the local j two rows at a time,
+// loads both mirror entries of every mesh, applies the interlacing phase as a product of unit phasors (per-lane e^{i pi (+-i' + k)/n},
+// per-row table e^{i pi j'/n}) and does the bin arithmetic ONCE per pair: half the divisions, square roots, bin searches,
+// Legendre sums and reductions of power_bin2_kernel.  (The full-mesh kernel below shares four modes; +-j' sit on different
+// ranks here.)
+template <int NPN>
+__global__ void __launch_bounds__(256) power_bin_pair_kernel(BinArgs A, unsigned *__restrict__ task_counter, int nrep)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_ke = reinterpret_cast<float *>(smem_raw);
+    float *s_me = s_ke + (A.Nk + 1);
+    float *s_coef = s_me + (A.Nmu + 1);
+    int *s_pidx = reinterpret_cast<int *>(s_coef + A.Npn * ABK_POLE_NCOEF);
+    const int lane = threadIdx.x & 31;
+    const abk_kmesh M = A.M;
+    const int n = M.n, nj = M.j1 - M.j0, amax = n - n / 2;
+    const int hdr = (A.Nk + 1) + (A.Nmu + 1) + A.Npn * ABK_POLE_NCOEF + A.Npn;
+    float2 *s_phj = reinterpret_cast<float2 *>(smem_raw + (size_t)((hdr + 3) & ~3) * 4);
+    float *s_Wj = reinterpret_cast<float *>(s_phj + nj);
+
+    for (int t = threadIdx.x; t <= A.Nk; t += blockDim.x) s_ke[t] = A.kedges2[t];
+    for (int t = threadIdx.x; t <= A.Nmu; t += blockDim.x) s_me[t] = A.muedges2[t];
+    for (int t = threadIdx.x; t < nj; t += blockDim.x) {
+        float sn, cs;
+        sincospif((float)fold(M.j0 + t, n) * A.F1.inv_n, &sn, &cs);
+        s_phj[t] = make_float2(cs, sn);
+        s_Wj[t] = A.F1.W ? A.F1.W[M.j0 + t] : 1.0f;
+    }
+    if (threadIdx.x == 0) {
+        int q = 0;
+        for (int p = 0; p < A.Np; p++)
+            if (A.pole_ell[p] != 0) {
+                for (int c = 0; c < ABK_POLE_NCOEF; c++) s_coef[q * ABK_POLE_NCOEF + c] = A.pole_coef[p * ABK_POLE_NCOEF + c];
+                s_pidx[q] = p;
+                q++;
+            }
+    }
+    __syncthreads();
+
+    const int Nk = A.Nk, Nmu = A.Nmu;
+    const int nchunks = (M.nzc + 31) / 32;
+    const unsigned ntasks = (unsigned)(amax + 1) * nchunks;
+    const float e_lo = s_ke[0], e_hi = s_ke[Nk];
+    const int rep = (nrep > 1) ? (int)(blockIdx.x % nrep) : 0;
+    const size_t rep_off_bins = (size_t)rep * Nk * Nmu, rep_off_poles = (size_t)rep * A.Np * Nk;
+    const bool inter1 = A.F1.fs != nullptr, cross = A.f2 != nullptr, inter2 = cross && A.F2.fs != nullptr;
+    const float pscale = cross ? A.F1.scale * A.F2.scale : A.F1.scale * A.F1.scale;
+    const int wpow = (A.F1.W ? 1 : 0) + ((cross ? A.F2.W : A.F1.W) ? 1 : 0);
+
+    for (;;) {
+        unsigned task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= ntasks) break;
+        const int ai = task / nchunks, k0 = (task % nchunks) * 32;
+        const int k = k0 + lane;
+        const bool k_ok = k < M.nzc;
+        const int ik2 = ai * ai + k * k;
+        if ((float)(ai * ai + k0 * k0) >= e_hi) continue;  // the whole column pair lies beyond the last edge
+        // members of |i'| = ai: i = ai (i' = +ai, if ai < n/2) and i = n - ai (i' = -ai, if ai >= 1); i' = -n/2 has no mirror
+        const int nmem = (ai < n / 2 ? 1 : 0) + (ai >= 1 ? 1 : 0);
+        const int i_a = (ai < n / 2) ? ai : n - ai, i_b = n - ai;
+        const int64_t off_a = (int64_t)(i_a - M.i0) * M.stride_i + k, off_b = (int64_t)(i_b - M.i0) * M.stride_i + k;
+        float2 e_a = make_float2(1.0f, 0.0f), e_b = make_float2(1.0f, 0.0f);  // e^{i pi (i' + k) / n} of the two members
+        if (inter1 || inter2) {
+            sincospif((float)(fold(i_a, n) + k) * A.F1.inv_n, &e_a.y, &e_a.x);
+            sincospif((float)(fold(i_b, n) + k) * A.F1.inv_n, &e_b.y, &e_b.x);
+        }
+        const float k2f = (float)(k * k);
+        const float Wi = A.F1.W ? A.F1.W[i_a] : 1.0f;      // == W[i_b]: the window table is symmetric
+        const float Wk = (A.F1.W && k_ok) ? A.F1.W[k] : 1.0f;
+        const float mult = (k == 0) ? 1.0f : 2.0f;
+        const unsigned cmult = ((k == 0) ? 1u : 2u) * (unsigned)nmem;
+
+        LaneAcc<NPN> acc;
+        acc.key = -1; acc.bk = 0; acc.cnt = 0; acc.p = 0.0f; acc.k = 0.0f;
+#pragma unroll
+        for (int q = 0; q < (NPN > 0 ? NPN : 1); q++) acc.pl[q] = 0.0f;
+        int bk = 0, bmu = 0;
+
+        constexpr int ROWS = 2;
+        for (int jl0 = 0; jl0 < nj; jl0 += ROWS) {
+            // ---- issue the loads of ROWS rows x 2 members first -------------------------------------------
+            float2 va[ROWS][2], vas[ROWS][2], vb[ROWS][2], vbs[ROWS][2];
+            float kmag2[ROWS];
+            bool use[ROWS];
+#pragma unroll
+            for (int u = 0; u < ROWS; u++) {
+                const int jl = jl0 + u;
+                const int jj = fold(M.j0 + jl, n);
+                kmag2[u] = (float)(ik2 + jj * jj);
+                use[u] = k_ok && jl < nj && kmag2[u] >= e_lo && kmag2[u] < e_hi;
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    va[u][mi] = vas[u][mi] = vb[u][mi] = vbs[u][mi] = make_float2(0.0f, 0.0f);
+                    if (use[u] && mi < nmem) {
+                        const int64_t idx = (mi == 0 ? off_a : off_b) + (int64_t)jl * M.stride_j;
+                        va[u][mi] = __ldcs(A.f1 + idx);
+                        if (inter1) vas[u][mi] = __ldcs(A.F1.fs + idx);
+                        if (cross) {
+                            vb[u][mi] = __ldcs(A.f2 + idx);
+                            if (inter2) vbs[u][mi] = __ldcs(A.F2.fs + idx);
+                        }
+                    }
+                }
+            }
+            // ---- per-row arithmetic, once for the pair ----------------------------------------------------------
+#pragma unroll
+            for (int u = 0; u < ROWS; u++) {
+                if (!use[u]) continue;
+                const int jl = jl0 + u;
+                const float2 ej = s_phj[jl];
+                float sum = 0.0f;
+#pragma unroll
+                for (int mi = 0; mi < 2; mi++) {
+                    if (mi >= nmem) break;
+                    const float2 e = mi == 0 ? e_a : e_b;
+                    const float cs = e.x * ej.x - e.y * ej.y, sn = e.x * ej.y + e.y * ej.x;
+                    float2 a = va[u][mi], b = vb[u][mi];
+                    if (inter1) {
+                        a.x += vas[u][mi].x * cs - vas[u][mi].y * sn;
+                        a.y += vas[u][mi].x * sn + vas[u][mi].y * cs;
+                    }
+                    if (inter2) {
+                        b.x += vbs[u][mi].x * cs - vbs[u][mi].y * sn;
+                        b.y += vbs[u][mi].x * sn + vbs[u][mi].y * cs;
+                    }
+                    sum += cross ? (a.x * b.x + a.y * b.y) : (a.x * a.x + a.y * a.y);
+                }
+                float val = sum * pscale;
+                if (wpow) {
+                    const float ww = (Wi * s_Wj[jl]) * Wk;
+                    val = __fdiv_rn(val, wpow == 2 ? ww * ww : ww);
+                }
+                const float km2 = kmag2[u];
+                const float mu2 = km2 > 0.0f ? __fdiv_rn(k2f, km2) : 0.0f;
+                while (bk < Nk - 1 && km2 > s_ke[bk + 1]) bk++;
+                while (bk > 0 && !(km2 > s_ke[bk])) bk--;
+                while (bmu < Nmu - 1 && mu2 > s_me[bmu + 1]) bmu++;
+                while (bmu > 0 && !(mu2 > s_me[bmu])) bmu--;
+                const int key = bk * Nmu + bmu;
+                if (key != acc.key) {
+                    lane_flush<NPN>(A, acc, rep_off_bins, rep_off_poles, s_pidx);
+                    acc.key = key; acc.bk = bk; acc.cnt = 0; acc.p = 0.0f; acc.k = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < (NPN > 0 ? NPN : 1); q++) acc.pl[q] = 0.0f;
+                }
+                const float pv = mult * val;
+                acc.cnt += cmult;
+                acc.p += pv;
+                acc.k = fmaf(mult * (float)nmem, sqrtf(km2), acc.k);
+                if (NPN > 0) {
+                    const float sarg = A.even_only ? mu2 : sqrtf(mu2);
+#pragma unroll
+                    for (int q = 0; q < NPN; q++) {
+                        if (q >= A.Npn) break;
+                        const float *c = s_coef + q * ABK_POLE_NCOEF;
+                        float pw;
+                        if (A.even_only) {
+                            pw = c[10];
+                            pw = fmaf(pw, sarg, c[8]); pw = fmaf(pw, sarg, c[6]); pw = fmaf(pw, sarg, c[4]);
+                            pw = fmaf(pw, sarg, c[2]); pw = fmaf(pw, sarg, c[0]);
+                        } else {
+                            pw = c[10];
+#pragma unroll
+                            for (int m = 9; m >= 0; m--) pw = fmaf(pw, sarg, c[m]);
+                        }
+                        acc.pl[q] = fmaf(pv, pw, acc.pl[q]);
+                    }
+                }
+            }
+        }
+        lane_flush<NPN>(A, acc, rep_off_bins, rep_off_poles, s_pidx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // (k,mu) binning, symmetric formulation (single GPU, full mesh).
 //
 // The modes (+-i', +-j', k) share |k|^2, mu^2, hence the bin, the Legendre weights and the window
@@ -878,7 +1057,14 @@ extern "C" int abk_power_bin(abk_ctx *ctx, const abk_bin_request *R)
             use_tab = 1;
             smem = hdr_bytes + tab;
         }
-        if (A.Npn == 0) kern2 = power_bin2_kernel<0>;
+        // pencil of a sharded mesh (all x-planes here): the +-i' mirror pair shares the bin arithmetic
+        const bool all_x = A.M.i0 == 0 && A.M.i1 == n;
+        if (use_tab && all_x && same_scale && R->w_symmetric && n >= 4 && !ctx->bin_no_sym) {
+            if (A.Npn == 0) kern = power_bin_pair_kernel<0>;
+            else if (A.Npn <= 2) kern = power_bin_pair_kernel<2>;
+            else if (A.Npn <= 4) kern = power_bin_pair_kernel<4>;
+            else kern = power_bin_pair_kernel<ABK_MAX_POLES>;
+        } else if (A.Npn == 0) kern2 = power_bin2_kernel<0>;
         else if (A.Npn <= 2) kern2 = power_bin2_kernel<2>;
         else if (A.Npn <= 4) kern2 = power_bin2_kernel<4>;
         else kern2 = power_bin2_kernel<ABK_MAX_POLES>;

@@ -637,7 +637,7 @@ class DistEngine:
         return pencil
 
     # -- 4. binning + all-reduce ---------------------------------------------------------------------------
-    def bin_pencils(self, plan, Lbox, kedges, muedges, poles, f1, f1s, f2, f2s, W_d, scale):
+    def bin_pencils(self, plan, Lbox, kedges, muedges, poles, f1, f1s, f2, f2s, W_d, scale, W_sym=False):
         import torch
 
         eng, n = self.eng, plan.n
@@ -662,6 +662,7 @@ class DistEngine:
         req.real_in = None
         req.scale = float(scale)
         req.finish = 1
+        req.w_symmetric = int(W_sym)
         base = tables_d.data_ptr()
         req.kedges2 = base
         req.muedges2 = base + 4 * (Nk + 1)
@@ -783,7 +784,7 @@ def calc_power(pos, Lbox, kbins=None, mubins=None, k_max=None, logk=False, paste
     with _phase('bin + all-reduce'):
         binned = de.bin_pencils(plan, float(Lbox), kbins, mubins, poles_arr, g1[0], g1[1] if interlaced else None,
                                 None if g2 is None else g2[0], g2[1] if (g2 is not None and interlaced) else None, W_d,
-                                scale)
+                                scale, W_sym=(W is None) or bool(np.array_equal(np.asarray(W)[1:], np.asarray(W)[:0:-1])))
     P = ps._package_pk(binned, Lbox, mubins, poles_arr, squeeze_mu_axis)
     kbins, mubins = np.asarray(kbins), np.asarray(mubins)
     res = dict(k_min=kbins[:-1], k_max=kbins[1:], k_mid=(kbins[1:] + kbins[:-1]) * 0.5, k_avg=P['k_avg'],

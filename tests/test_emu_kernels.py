@@ -191,3 +191,57 @@ def test_emu_transpose_scatter_p2p(emu, nranks, n):
         nyl = js[r + 1] - js[r]
         got = pencils[r][: n * nyl * nzc].reshape(n, nyl, nzc)
         np.testing.assert_array_equal(got, full[:, js[r]:js[r + 1], :])
+
+
+@pytest.mark.parametrize('n,j0,j1,cross', [(12, 3, 9, False), (9, 0, 4, True), (7, 2, 7, False), (16, 0, 16, True)])
+def test_emu_pencil_pair_binning_matches_one_mode_kernel(emu, n, j0, j1, cross):
+    """power_bin_pair_kernel (pencil layout, +-i' mirror pairs share the bin arithmetic) against power_bin2_kernel (one mode at
+    a time) on the same pencil: mode counts identical, sums equal to float32 round-off -- even and odd meshes (the unpaired
+    i' = -n/2 or -(n+1)/2 plane), auto and cross spectra, interlaced + compensated."""
+    from abacusutils_b200._lib import BinRequest, KMesh
+    from abacusutils_b200.analysis.power_spectrum import get_W_compensated, legendre_coefficients
+
+    rng = np.random.default_rng(100 * n + j0)
+    nzc, nyl, L = n // 2 + 1, j1 - j0, 100.0
+    shape = (n, nyl, nzc)
+
+    def mesh():
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+    f1, f1s = mesh(), mesh()
+    f2, f2s = (mesh(), mesh()) if cross else (None, None)
+    W = np.ascontiguousarray(get_W_compensated(L, n, 'TSC', True), np.float32)
+    assert np.array_equal(W[1:], W[:0:-1])
+    Nk, Nmu, poles = 6, 3, np.array([0, 2, 4], np.int64)
+    dk = 2 * np.pi / L
+    kedges2 = ((np.linspace(0.0, np.pi * n / L, Nk + 1) / dk) ** 2).astype(np.float32)
+    muedges2 = (np.linspace(0.0, 1.0, Nmu + 1) ** 2).astype(np.float32)
+    tables = np.concatenate([kedges2, muedges2, legendre_coefficients(poles).reshape(-1)]).astype(np.float32)
+    nb = C.c_size_t()
+    emu.call('abk_power_bin_scratch_bytes', Nk, Nmu, len(poles), C.byref(nb))
+    out = {}
+    for sym in (1, 0):
+        sums = np.zeros(3 * Nk * Nmu + len(poles) * Nk, np.float64)
+        scratch, sptr = aligned(nb.value)
+        req = BinRequest()
+        req.mesh = KMesh(n=n, nzc=nzc, i0=0, i1=n, j0=j0, j1=j1, stride_i=nyl * nzc, stride_j=nzc)
+        req.f1, req.f1s = f1.ctypes.data, f1s.ctypes.data
+        req.f2, req.f2s = (f2.ctypes.data, f2s.ctypes.data) if cross else (None, None)
+        req.real_in, req.W = None, W.ctypes.data
+        req.scale, req.finish, req.w_symmetric = 0.5 / n**3, 1, sym
+        base = tables.ctypes.data
+        req.kedges2, req.muedges2, req.pole_coef = base, base + 4 * (Nk + 1), base + 4 * (Nk + 1 + Nmu + 1)
+        for ip, ell in enumerate(poles):
+            req.pole_ell[ip] = int(ell)
+        req.Nk, req.Nmu, req.Np = Nk, Nmu, len(poles)
+        sb = sums.ctypes.data
+        req.counts, req.sum_p, req.sum_k, req.sum_poles = sb, sb + 8 * Nk * Nmu, sb + 16 * Nk * Nmu, sb + 24 * Nk * Nmu
+        req.scratch, req.scratch_bytes = sptr.value, nb.value
+        emu.call('abk_power_bin', emu.ctx, C.byref(req))
+        emu.call('abk_ctx_sync', emu.ctx)
+        out[sym] = sums
+    nbin = Nk * Nmu
+    np.testing.assert_array_equal(out[1][:nbin].view(np.int64), out[0][:nbin].view(np.int64))
+    assert out[0][:nbin].view(np.int64).sum() > 0
+    scale = np.abs(out[0][nbin:]).max()
+    np.testing.assert_allclose(out[1][nbin:], out[0][nbin:], rtol=2e-5, atol=2e-6 * scale)
