@@ -323,16 +323,20 @@ class _Painter:
 
         # Early deposits (host input): segments [0, split) are deposited on the auxiliary stream while the remaining
         # chunks are still arriving; `cuts` are the ends of the early groups.  Every group costs one full per-cell pass
-        # over the mesh (7.4 ms at nmesh 1024 however few particles it carries); two groups with a 2-3 segment tail measured
-        # best at config 3 (257.3 ms end to end against 260.5 with one group; a shorter tail lets the last early group run
-        # into it: 270 ms).  ABK_EARLY_GROUPS / ABK_TAIL_SEGMENTS are experiment knobs.
+        # over the mesh (7.4 ms at nmesh 1024 however few particles it carries).  One group with a 5-of-14-segment tail is
+        # the default because it is the setting without a cliff: two groups save 3-4 ms on a uniform catalogue with a
+        # 3-segment tail (250 vs 254 ms end to end at config 3) but cost 30 ms as soon as the last early group runs into
+        # the tail -- measured for a clustered catalogue with a 3-segment tail (283 ms; 4 segments: 250.6; one group:
+        # 252.0) and for the uniform one with a 4-segment tail (282 ms): the early deposits run on the high-priority
+        # stream, the bucket kernels behind them starve, the staging ring fills and the PCIe copy stalls.
+        # ABK_EARLY_GROUPS / ABK_TAIL_SEGMENTS are experiment knobs.
         split, cuts = 0, []
         # (Device-resident input does not get early groups: measured at config 3, every extra deposit launch costs its
         # per-tile walk again -- 7.4 ms per grid however few particles it carries -- and the bucket kernels do not
         # speed up next to it: 101.6 / 119.0 / 136.8 ms per step with 1 / 2 / 3 early groups against 82.0.)
         if host and nseg >= 6:
-            groups = max(1, int(os.environ.get('ABK_EARLY_GROUPS', '2')))
-            tail = max(3, -(-3 * nseg // 10)) if groups == 1 else max(2, -(-(2 if groups == 2 else 1.5) * nseg // 10))
+            groups = max(1, int(os.environ.get('ABK_EARLY_GROUPS', '1')))
+            tail = max(3, -(-3 * nseg // 10)) if groups == 1 else max(2, -(-(2.8 if groups == 2 else 1.5) * nseg // 10))
             if os.environ.get('ABK_TAIL_SEGMENTS'):      # experiment knob: segments left for the un-overlapped tail
                 tail = max(1, min(nseg - 1, int(os.environ['ABK_TAIL_SEGMENTS'])))
             split = nseg - int(tail)
