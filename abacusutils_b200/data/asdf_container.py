@@ -78,7 +78,10 @@ def _unshuffle(buf, typesize):
 
 
 def _bitunshuffle(buf, typesize):
-    # c-blosc only bit-shuffles a block whose element count is a multiple of 8 (otherwise it is stored as is);
+    # c-blosc 1.x (what python-blosc 1.x -- the reference's dependency -- wraps; shuffle.c, blosc_internal_bitshuffle) only
+    # bit-shuffles a block whose element count is a multiple of 8 and stores any other block as is.  (c-blosc2 differs: it
+    # shuffles the first n - n % 8 elements and copies the rest; blosc-2 frames are not what Abacus files contain and are
+    # rejected by their header version before they get here.)
     # layout [byte in element][bit][n/8], element 8j in the least significant bit of byte j
     n = len(buf) // typesize
     if n == 0 or n % 8:
@@ -95,6 +98,8 @@ def blosc1_decompress(frame):
     if len(frame) < 16:
         raise ValueError('truncated blosc frame')
     _version, _versionlz, flags, typesize, nbytes, blocksize, cbytes = struct.unpack('<BBBBIII', frame[:16])
+    if _version > 2:      # c-blosc 1.x writes format version 2; blosc-2 frames (>= 3) differ (header, bitshuffle leftovers)
+        raise NotImplementedError(f'blosc format version {_version}: only blosc-1 frames (version 2) are supported')
     if cbytes != len(frame):
         raise ValueError(f'blosc frame length {len(frame)} does not match its header ({cbytes})')
     if nbytes == 0:
